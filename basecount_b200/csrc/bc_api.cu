@@ -1,0 +1,822 @@
+// bc_api.cu -- the C ABI of include/basecount_b200.h over the sm_100a kernels.
+//
+// Host side of the hot path: owns the device accumulators (the reference's
+// np.zeros((L, 6)) at basecount/main.py:132), double-buffered staging for batches that
+// arrive in pinned host memory (H2D on a copy stream, kernels on a compute stream), and
+// the result read-back.  No CPU compute path exists here: every entry point that
+// produces numbers launches CUDA kernels or fails.
+#include "../../include/basecount_b200.h"
+#include "bc_common.cuh"
+#include "k1_count.cuh"
+#include "k2_stats.cuh"
+#include "k3_reduce.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Staging {                 // device copies of one host batch
+    DevBuf ref_read_off, starts, cigar_off, cigar, seq_woff, planes, okmask, exc_read, exc_pos, chunks;
+    Chunk *h_chunks = nullptr;   // pinned
+    size_t h_chunks_cap = 0;
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool used = false;
+};
+
+struct Resident {                // a batch kept in HBM by bc_batch_upload
+    Staging st;
+    BatchView view;
+    uint32_t n_chunks = 0;
+    int G = 32;
+    bool live = false;
+};
+
+}  // namespace
+
+struct bc_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t copy = nullptr, compute = nullptr;
+    std::string err;
+
+    uint32_t n_refs = 0;
+    std::vector<uint32_t> ref_len, col_base;
+    uint64_t stride = 0;
+    uint32_t *d_counts = nullptr;
+    unsigned long long *d_counts64 = nullptr;
+    uint32_t *d_col_base = nullptr, *d_ref_len = nullptr;
+    uint32_t *d_status = nullptr;
+    uint32_t *h_status = nullptr;            // pinned
+    uint64_t reads_since_fold = 0;
+
+    Staging stage[2];
+    uint64_t pushes = 0;
+    std::vector<Resident *> resident;
+
+    DevBuf scratch_cov, scratch_pc, scratch_ent, scratch_sec, scratch_flags, scratch_i64, scratch_misc;
+    SummaryPartial *d_partials = nullptr;
+    size_t partials_cap = 0;
+
+    cudaEvent_t t0 = nullptr, t1 = nullptr, k0 = nullptr, k1 = nullptr;
+    bool k_timed = false;
+    uint64_t launches = 0;
+    int variant = 0;
+};
+
+#define CU(h, expr)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                      \
+            return BC_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+static int fail(bc_handle *h, int code, const char *msg)
+{
+    h->err = msg;
+    return code;
+}
+
+static int ensure(bc_handle *h, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return BC_OK;
+    if (b.p) {
+        CU(h, cudaDeviceSynchronize());
+        CU(h, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 4 + 256;
+    CU(h, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return BC_OK;
+}
+
+static void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+static void release_staging(Staging &s)
+{
+    release(s.ref_read_off); release(s.starts); release(s.cigar_off); release(s.cigar); release(s.seq_woff);
+    release(s.planes); release(s.okmask); release(s.exc_read); release(s.exc_pos); release(s.chunks);
+    if (s.h_chunks) cudaFreeHost(s.h_chunks);
+    s.h_chunks = nullptr;
+    s.h_chunks_cap = 0;
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.done) cudaEventDestroy(s.done);
+    s.copied = s.done = nullptr;
+}
+
+extern "C" {
+
+int bc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *bc_last_error(bc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int bc_create(int device, bc_handle **out)
+{
+    if (!out) return BC_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (basecount_b200 has no CPU path)";
+        return BC_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        g_create_error = "device index out of range";
+        return BC_ERR_ARG;
+    }
+    bc_handle *h = new bc_handle();
+    h->device = device;
+    auto bail = [&](cudaError_t ce, const char *what) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete h;
+        return BC_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    for (cudaEvent_t *ev : {&h->t0, &h->t1, &h->k0, &h->k1})
+        if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail(e, "event");
+    for (Staging &s : h->stage) {
+        if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+        if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    }
+    if ((e = cudaMalloc(&h->d_status, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(h->d_status, 0, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaHostAlloc((void **)&h->h_status, kStatWords * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
+        return bail(e, "cudaHostAlloc");
+    *out = h;
+    return BC_OK;
+}
+
+void bc_destroy(bc_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (Staging &s : h->stage) release_staging(s);
+    for (Resident *r : h->resident) {
+        if (r) {
+            release_staging(r->st);
+            delete r;
+        }
+    }
+    for (DevBuf *b : {&h->scratch_cov, &h->scratch_pc, &h->scratch_ent, &h->scratch_sec, &h->scratch_flags,
+                      &h->scratch_i64, &h->scratch_misc})
+        release(*b);
+    if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_counts) cudaFree(h->d_counts);
+    if (h->d_counts64) cudaFree(h->d_counts64);
+    if (h->d_col_base) cudaFree(h->d_col_base);
+    if (h->d_ref_len) cudaFree(h->d_ref_len);
+    if (h->d_status) cudaFree(h->d_status);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    for (cudaEvent_t ev : {h->t0, h->t1, h->k0, h->k1})
+        if (ev) cudaEventDestroy(ev);
+    if (h->copy) cudaStreamDestroy(h->copy);
+    if (h->compute) cudaStreamDestroy(h->compute);
+    delete h;
+}
+
+int bc_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return BC_ERR_ARG;
+    *out = nullptr;
+    if (bytes == 0) bytes = 1;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? BC_OK : BC_ERR_CUDA;
+}
+
+void bc_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens)
+{
+    if (!h) return BC_ERR_ARG;
+    if (n_refs == 0 || !ref_lens) return fail(h, BC_ERR_ARG, "bc_begin: need at least one reference");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaDeviceSynchronize());
+    uint64_t total = 0;
+    std::vector<uint32_t> cb(n_refs), rl(n_refs);
+    for (uint32_t r = 0; r < n_refs; r++) {
+        if (ref_lens[r] > 0x7FFFFFFFu) return fail(h, BC_ERR_ARG, "bc_begin: reference longer than 2^31-1 (BAM l_ref limit)");
+        rl[r] = ref_lens[r];
+        if (total > 0xFFFFFFFFull - kColAlign) return fail(h, BC_ERR_ARG, "bc_begin: more than 2^32 columns in one handle");
+        cb[r] = (uint32_t)total;
+        total += ((uint64_t)ref_lens[r] + kColAlign - 1) / kColAlign * kColAlign;
+    }
+    total += 32u * 32u;      // slack so a window overhanging the last slot stays inside the allocation
+    if (total > 0xFFFFFFFFull) return fail(h, BC_ERR_ARG, "bc_begin: more than 2^32 columns in one handle");
+    if (total != h->stride || n_refs != h->n_refs) {
+        if (h->d_counts) CU(h, cudaFree(h->d_counts));
+        if (h->d_counts64) CU(h, cudaFree(h->d_counts64));
+        if (h->d_col_base) CU(h, cudaFree(h->d_col_base));
+        if (h->d_ref_len) CU(h, cudaFree(h->d_ref_len));
+        h->d_counts = nullptr;
+        h->d_counts64 = nullptr;
+        h->d_col_base = h->d_ref_len = nullptr;
+        CU(h, cudaMalloc(&h->d_counts, (size_t)total * kPlanes * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->d_col_base, n_refs * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->d_ref_len, n_refs * sizeof(uint32_t)));
+    } else if (h->d_counts64) {
+        CU(h, cudaFree(h->d_counts64));
+        h->d_counts64 = nullptr;
+    }
+    h->stride = total;
+    h->n_refs = n_refs;
+    h->ref_len = rl;
+    h->col_base = cb;
+    h->reads_since_fold = 0;
+    CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)total * kPlanes * sizeof(uint32_t), h->compute));
+    CU(h, cudaMemsetAsync(h->d_status, 0, kStatWords * sizeof(uint32_t), h->compute));
+    CU(h, cudaMemcpyAsync(h->d_col_base, cb.data(), n_refs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
+    CU(h, cudaMemcpyAsync(h->d_ref_len, rl.data(), n_refs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+int bc_reset(bc_handle *h)
+{
+    if (!h) return BC_ERR_ARG;
+    if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->stride * kPlanes * sizeof(uint32_t), h->compute));
+    if (h->d_counts64)
+        CU(h, cudaMemsetAsync(h->d_counts64, 0, (size_t)h->stride * kPlanes * sizeof(unsigned long long), h->compute));
+    h->reads_since_fold = 0;
+    return BC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ batches
+static int pick_group_width(const bc_batch *b, uint64_t total_words)
+{
+    uint64_t mean = b->mean_read_len;
+    if (mean == 0 && b->n_reads) mean = total_words * 32u / b->n_reads;
+    if (mean <= 8u * 32u - 31u) return 8;
+    if (mean <= 16u * 32u - 31u) return 16;
+    return 32;
+}
+
+// Split every slot's reads into per-warp chunks.  Returns the number of chunks.
+static uint32_t build_chunks(bc_handle *h, const uint32_t *ref_read_off, uint32_t n_reads, std::vector<Chunk> &out)
+{
+    out.clear();
+    const uint64_t target_warps = (uint64_t)h->sm_count * 32u;
+    uint32_t per = (uint32_t)std::max<uint64_t>(16, (n_reads + target_warps - 1) / target_warps);
+    per = std::min<uint32_t>(per, 4096);
+    for (uint32_t r = 0; r < h->n_refs; r++) {
+        for (uint32_t a = ref_read_off[r]; a < ref_read_off[r + 1]; a += per) {
+            Chunk c;
+            c.read_begin = a;
+            c.read_end = std::min(a + per, ref_read_off[r + 1]);
+            c.col_base = h->col_base[r];
+            c.ref_len = h->ref_len[r];
+            out.push_back(c);
+        }
+    }
+    return (uint32_t)out.size();
+}
+
+static int validate_batch(bc_handle *h, const bc_batch *b)
+{
+    if (!b) return fail(h, BC_ERR_ARG, "null batch");
+    if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
+    if (b->n_refs != h->n_refs) return fail(h, BC_ERR_ARG, "batch n_refs differs from bc_begin");
+    if (b->n_reads && (!b->ref_read_off || !b->starts || !b->cigar_off || !b->seq_woff))
+        return fail(h, BC_ERR_ARG, "batch is missing a required array");
+    if (b->n_exc && (!b->exc_read || !b->exc_pos)) return fail(h, BC_ERR_ARG, "batch is missing exception arrays");
+    return BC_OK;
+}
+
+// Launch K1 (+ corrections, + exact overflow check) for a batch whose arrays are in HBM.
+static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks, uint32_t n_chunks, int G)
+{
+    if (v.n_reads == 0) return BC_OK;
+    // uint32 counters cannot wrap while fewer than 2^32 reads went in since the last fold
+    if (h->reads_since_fold + v.n_reads > 0xFFFFFFFFull) {
+        const uint64_t n = h->stride * kPlanes;
+        if (!h->d_counts64) {
+            CU(h, cudaMalloc(&h->d_counts64, n * sizeof(unsigned long long)));
+            CU(h, cudaMemsetAsync(h->d_counts64, 0, n * sizeof(unsigned long long), h->compute));
+        }
+        k_fold_counts<<<(unsigned)((n + 255) / 256), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, n);
+        h->launches++;
+        h->reads_since_fold = 0;
+    }
+    h->reads_since_fold += v.n_reads;
+
+    CountView cv;
+    cv.counts = h->d_counts;
+    cv.stride = h->stride;
+    cv.col_base = h->d_col_base;
+    cv.ref_len = h->d_ref_len;
+    cv.status = h->d_status;
+
+    CU(h, cudaEventRecord(h->k0, h->compute));
+    if (h->variant == 1) {
+        k1_count_per_base<<<(v.n_reads + 127) / 128, 128, 0, h->compute>>>(v, cv);
+    } else {
+        const unsigned grid = (n_chunks + kK1WarpsPerCta - 1) / kK1WarpsPerCta;
+        const size_t smem = (size_t)kK1WarpsPerCta * 32 * G * sizeof(uint32_t);
+        const bool ok = v.okmask != nullptr;
+#define K1_LAUNCH(GG)                                                                               \
+    do {                                                                                            \
+        if (ok) k1_count_tiled<GG, true><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks); \
+        else k1_count_tiled<GG, false><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks);   \
+    } while (0)
+        if (G == 8) K1_LAUNCH(8);
+        else if (G == 16) K1_LAUNCH(16);
+        else K1_LAUNCH(32);
+#undef K1_LAUNCH
+    }
+    CU(h, cudaEventRecord(h->k1, h->compute));
+    h->k_timed = true;
+    h->launches++;
+    if (v.n_exc) {
+        k1_exceptions<<<(v.n_exc + 127) / 128, 128, 0, h->compute>>>(v, cv);
+        h->launches++;
+    }
+    k1_check_overflow<<<(v.n_reads + 127) / 128, 128, 0, h->compute>>>(v, cv);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return BC_OK;
+}
+
+static int stage_copy(bc_handle *h, DevBuf &dst, const void *src, size_t bytes, bool src_on_device)
+{
+    if (bytes == 0) return BC_OK;
+    int rc = ensure(h, dst, bytes);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(dst.p, src, bytes, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->copy));
+    return BC_OK;
+}
+
+// Copy a host batch into `st` on the copy stream and fill `view` / chunk table.
+static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &view, uint32_t &n_chunks, int &G)
+{
+    const uint32_t n = b->n_reads;
+    view = BatchView();
+    view.n_reads = n;
+    view.n_refs = b->n_refs;
+    view.n_exc = b->n_exc;
+    n_chunks = 0;
+    G = 32;
+    if (n == 0) return BC_OK;
+    if (b->ref_read_off[0] != 0 || b->ref_read_off[b->n_refs] != n)
+        return fail(h, BC_ERR_ARG, "ref_read_off must start at 0 and end at n_reads");
+    for (uint32_t r = 0; r < b->n_refs; r++)
+        if (b->ref_read_off[r] > b->ref_read_off[r + 1]) return fail(h, BC_ERR_ARG, "ref_read_off must be non-decreasing");
+    const uint64_t n_cigar = b->cigar_off[n];
+    const uint64_t n_words = b->seq_woff[n];
+    if (n_cigar && !b->cigar) return fail(h, BC_ERR_ARG, "batch is missing cigar words");
+    if (n_words && !b->planes) return fail(h, BC_ERR_ARG, "batch is missing sequence planes");
+    G = pick_group_width(b, n_words);
+
+    std::vector<Chunk> chunks;
+    n_chunks = build_chunks(h, b->ref_read_off, n, chunks);
+    if (n_chunks > st.h_chunks_cap) {
+        if (st.h_chunks) CU(h, cudaFreeHost(st.h_chunks));
+        st.h_chunks = nullptr;
+        st.h_chunks_cap = 0;
+        size_t want = (size_t)n_chunks + n_chunks / 2 + 64;
+        CU(h, cudaHostAlloc((void **)&st.h_chunks, want * sizeof(Chunk), cudaHostAllocDefault));
+        st.h_chunks_cap = want;
+    }
+    std::memcpy(st.h_chunks, chunks.data(), (size_t)n_chunks * sizeof(Chunk));
+
+    int rc;
+    if ((rc = stage_copy(h, st.ref_read_off, b->ref_read_off, (size_t)(b->n_refs + 1) * 4, false))) return rc;
+    if ((rc = stage_copy(h, st.starts, b->starts, (size_t)n * 4, false))) return rc;
+    if ((rc = stage_copy(h, st.cigar_off, b->cigar_off, (size_t)(n + 1) * 4, false))) return rc;
+    if ((rc = stage_copy(h, st.cigar, b->cigar, (size_t)n_cigar * 4, false))) return rc;
+    if ((rc = stage_copy(h, st.seq_woff, b->seq_woff, (size_t)(n + 1) * 4, false))) return rc;
+    if ((rc = stage_copy(h, st.planes, b->planes, (size_t)n_words * 8, false))) return rc;
+    if (b->okmask && (rc = stage_copy(h, st.okmask, b->okmask, (size_t)n_words * 4, false))) return rc;
+    if (b->n_exc) {
+        if ((rc = stage_copy(h, st.exc_read, b->exc_read, (size_t)b->n_exc * 4, false))) return rc;
+        if ((rc = stage_copy(h, st.exc_pos, b->exc_pos, (size_t)b->n_exc * 4, false))) return rc;
+    }
+    if ((rc = stage_copy(h, st.chunks, st.h_chunks, (size_t)n_chunks * sizeof(Chunk), false))) return rc;
+
+    view.ref_read_off = (const uint32_t *)st.ref_read_off.p;
+    view.starts = (const uint32_t *)st.starts.p;
+    view.cigar_off = (const uint32_t *)st.cigar_off.p;
+    view.cigar = (const uint32_t *)st.cigar.p;
+    view.seq_woff = (const uint32_t *)st.seq_woff.p;
+    view.planes = (const uint2 *)st.planes.p;
+    view.okmask = b->okmask ? (const uint32_t *)st.okmask.p : nullptr;
+    view.exc_read = (const uint32_t *)st.exc_read.p;
+    view.exc_pos = (const uint32_t *)st.exc_pos.p;
+    return BC_OK;
+}
+
+extern "C" {
+
+int bc_push_batch(bc_handle *h, const bc_batch *b)
+{
+    if (!h) return BC_ERR_ARG;
+    int rc = validate_batch(h, b);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    if (b->on_device) {
+        const uint32_t id = b->reserved;
+        if (id == 0 || id > h->resident.size() || !h->resident[id - 1] || !h->resident[id - 1]->live)
+            return fail(h, BC_ERR_ARG, "on_device batch was not created by bc_batch_upload on this handle");
+        Resident *r = h->resident[id - 1];
+        return launch_count(h, r->view, (const Chunk *)r->st.chunks.p, r->n_chunks, r->G);
+    }
+    Staging &st = h->stage[h->pushes & 1];
+    h->pushes++;
+    if (st.used) {
+        // the kernels that last read this staging set must be done before it is overwritten
+        CU(h, cudaEventSynchronize(st.done));
+    }
+    BatchView view;
+    uint32_t n_chunks;
+    int G;
+    if ((rc = stage_batch(h, st, b, view, n_chunks, G))) return rc;
+    CU(h, cudaEventRecord(st.copied, h->copy));
+    CU(h, cudaStreamWaitEvent(h->compute, st.copied, 0));
+    rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G);
+    CU(h, cudaEventRecord(st.done, h->compute));
+    st.used = true;
+    return rc;
+}
+
+int bc_sync(bc_handle *h)
+{
+    if (!h) return BC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->copy));
+    CU(h, cudaMemcpyAsync(h->h_status, h->d_status, kStatWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    if (h->h_status[kStatIndexError]) {
+        CU(h, cudaMemsetAsync(h->d_status, 0, kStatWords * sizeof(uint32_t), h->compute));
+        return fail(h, BC_ERR_INDEX, "alignment counted past the end of the reference (std::out_of_range in count.cpp)");
+    }
+    if (h->h_status[kStatMaybeOverflow]) {
+        // pieces crossed ref_len but nothing countable lay beyond it: not an error in the reference
+        CU(h, cudaMemsetAsync(h->d_status, 0, kStatWords * sizeof(uint32_t), h->compute));
+    }
+    return BC_OK;
+}
+
+int bc_batch_upload(bc_handle *h, const bc_batch *host, bc_batch *dev)
+{
+    if (!h || !dev) return BC_ERR_ARG;
+    int rc = validate_batch(h, host);
+    if (rc) return rc;
+    if (host->on_device) return fail(h, BC_ERR_ARG, "bc_batch_upload expects host pointers");
+    CU(h, cudaSetDevice(h->device));
+    Resident *r = new Resident();
+    rc = stage_batch(h, r->st, host, r->view, r->n_chunks, r->G);
+    if (rc == BC_OK && cudaStreamSynchronize(h->copy) != cudaSuccess) rc = fail(h, BC_ERR_CUDA, "upload failed");
+    if (rc) {
+        release_staging(r->st);
+        delete r;
+        return rc;
+    }
+    r->live = true;
+    h->resident.push_back(r);
+    *dev = *host;
+    dev->ref_read_off = r->view.ref_read_off;
+    dev->starts = r->view.starts;
+    dev->cigar_off = r->view.cigar_off;
+    dev->cigar = r->view.cigar;
+    dev->seq_woff = r->view.seq_woff;
+    dev->planes = (const uint64_t *)r->view.planes;
+    dev->okmask = r->view.okmask;
+    dev->exc_read = r->view.exc_read;
+    dev->exc_pos = r->view.exc_pos;
+    dev->on_device = 1;
+    dev->reserved = (uint32_t)h->resident.size();
+    return BC_OK;
+}
+
+void bc_batch_free(bc_handle *h, bc_batch *dev)
+{
+    if (!h || !dev || !dev->on_device) return;
+    const uint32_t id = dev->reserved;
+    if (id == 0 || id > h->resident.size() || !h->resident[id - 1]) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    release_staging(h->resident[id - 1]->st);
+    delete h->resident[id - 1];
+    h->resident[id - 1] = nullptr;
+    dev->reserved = 0;
+}
+
+// ------------------------------------------------------------------ results
+int bc_counts(bc_handle *h, uint32_t ref, int64_t *out)
+{
+    if (!h || !out) return BC_ERR_ARG;
+    if (ref >= h->n_refs) return fail(h, BC_ERR_ARG, "reference slot out of range");
+    CU(h, cudaSetDevice(h->device));
+    const uint64_t n = (uint64_t)h->ref_len[ref] * kPlanes;
+    if (n == 0) return BC_OK;
+    int rc = ensure(h, h->scratch_i64, n * sizeof(long long));
+    if (rc) return rc;
+    k_export_counts<<<(unsigned)((n + 255) / 256), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride,
+                                                                        h->col_base[ref], h->ref_len[ref],
+                                                                        (long long *)h->scratch_i64.p);
+    h->launches++;
+    CU(h, cudaMemcpyAsync(out, h->scratch_i64.p, n * sizeof(long long), cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+static int run_rows(bc_handle *h, uint32_t ref, int K, double norm, double norm2, bool want_cov, bool want_pc,
+                    bool want_ent, bool want_sec, bool want_flags)
+{
+    const uint32_t L = h->ref_len[ref];
+    int rc;
+    if (want_cov && (rc = ensure(h, h->scratch_cov, (size_t)L * 8))) return rc;
+    if (want_pc && (rc = ensure(h, h->scratch_pc, (size_t)L * 8 * K))) return rc;
+    if (want_ent && (rc = ensure(h, h->scratch_ent, (size_t)L * 8))) return rc;
+    if (want_sec && (rc = ensure(h, h->scratch_sec, (size_t)L * 8))) return rc;
+    if (want_flags && (rc = ensure(h, h->scratch_flags, (size_t)L))) return rc;
+    k2_stats_rows<<<(L + 255) / 256, 256, 0, h->compute>>>(
+        h->d_counts, h->d_counts64, h->stride, h->col_base[ref], L, K, norm, norm2,
+        want_cov ? (long long *)h->scratch_cov.p : nullptr, want_pc ? (double *)h->scratch_pc.p : nullptr,
+        want_ent ? (double *)h->scratch_ent.p : nullptr, want_sec ? (double *)h->scratch_sec.p : nullptr,
+        want_flags ? (uint8_t *)h->scratch_flags.p : nullptr);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return BC_OK;
+}
+
+int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, int64_t *coverage, double *pc,
+             double *entropy, double *secondary, uint8_t *flags)
+{
+    if (!h) return BC_ERR_ARG;
+    if (ref >= h->n_refs) return fail(h, BC_ERR_ARG, "reference slot out of range");
+    CU(h, cudaSetDevice(h->device));
+    const uint32_t L = h->ref_len[ref];
+    if (L == 0) return BC_OK;
+    const int K = show_n ? 6 : 5;
+    int rc = run_rows(h, ref, K, norm, norm2, coverage, pc, entropy, secondary, flags);
+    if (rc) return rc;
+    if (coverage) CU(h, cudaMemcpyAsync(coverage, h->scratch_cov.p, (size_t)L * 8, cudaMemcpyDeviceToHost, h->compute));
+    if (pc) CU(h, cudaMemcpyAsync(pc, h->scratch_pc.p, (size_t)L * 8 * K, cudaMemcpyDeviceToHost, h->compute));
+    if (entropy) CU(h, cudaMemcpyAsync(entropy, h->scratch_ent.p, (size_t)L * 8, cudaMemcpyDeviceToHost, h->compute));
+    if (secondary) CU(h, cudaMemcpyAsync(secondary, h->scratch_sec.p, (size_t)L * 8, cudaMemcpyDeviceToHost, h->compute));
+    if (flags) CU(h, cudaMemcpyAsync(flags, h->scratch_flags.p, (size_t)L, cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+int bc_summary(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
+               double *entropy_sum)
+{
+    if (!h || !nonzero || !cov_sum || !entropy_sum) return BC_ERR_ARG;
+    if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
+    CU(h, cudaSetDevice(h->device));
+    const uint32_t R = h->n_refs;
+    const size_t need = (size_t)R * kSummaryBlocks;
+    if (need > h->partials_cap) {
+        if (h->d_partials) {
+            CU(h, cudaDeviceSynchronize());
+            CU(h, cudaFree(h->d_partials));
+            h->d_partials = nullptr;
+        }
+        CU(h, cudaMalloc(&h->d_partials, need * sizeof(SummaryPartial)));
+        h->partials_cap = need;
+    }
+    int rc = ensure(h, h->scratch_misc, (size_t)R * 24);
+    if (rc) return rc;
+    long long *d_nz = (long long *)h->scratch_misc.p;
+    long long *d_cs = d_nz + R;
+    double *d_es = (double *)(d_cs + R);
+    const int K = show_n ? 6 : 5;
+    k2_summary_partials<<<dim3(kSummaryBlocks, R), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride,
+                                                                        h->d_col_base, h->d_ref_len, K, norm, norm2,
+                                                                        h->d_partials);
+    k2_summary_final<<<R, kSummaryBlocks, 0, h->compute>>>(h->d_partials, d_nz, d_cs, d_es);
+    h->launches += 2;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(nonzero, d_nz, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaMemcpyAsync(cov_sum, d_cs, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaMemcpyAsync(entropy_sum, d_es, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+int bc_amplicons(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, uint32_t n_tiles,
+                 const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty)
+{
+    if (!h) return BC_ERR_ARG;
+    if (ref >= h->n_refs) return fail(h, BC_ERR_ARG, "reference slot out of range");
+    if (n_tiles == 0) return BC_OK;
+    if (!lo || !hi || !out || !empty) return fail(h, BC_ERR_ARG, "bc_amplicons: null argument");
+    CU(h, cudaSetDevice(h->device));
+    const uint32_t L = h->ref_len[ref];
+    const int K = show_n ? 6 : 5;
+    int rc = BC_OK;
+    if (L) rc = run_rows(h, ref, K, norm, norm2, true, false, true, true, false);
+    if (rc) return rc;
+    // device scratch: lo[T] hi[T] out[6T] empty[T]
+    const size_t bytes = (size_t)n_tiles * (4 + 4 + 48 + 1) + 64;
+    if ((rc = ensure(h, h->scratch_misc, bytes))) return rc;
+    char *base = (char *)h->scratch_misc.p;
+    double *d_out = (double *)base;
+    int32_t *d_lo = (int32_t *)(base + (size_t)n_tiles * 48);
+    int32_t *d_hi = d_lo + n_tiles;
+    uint8_t *d_empty = (uint8_t *)(d_hi + n_tiles);
+    CU(h, cudaMemcpyAsync(d_lo, lo, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, h->compute));
+    CU(h, cudaMemcpyAsync(d_hi, hi, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, h->compute));
+    uint32_t cap = 4096;                        // doubles staged per window (32 KB)
+    k3_amplicons<<<dim3(n_tiles, 3), kK3Threads, (size_t)cap * sizeof(double), h->compute>>>(
+        (const long long *)h->scratch_cov.p, (const double *)h->scratch_ent.p, (const double *)h->scratch_sec.p, L,
+        d_lo, d_hi, n_tiles, cap, d_out, d_empty);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(out, d_out, (size_t)n_tiles * 48, cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaMemcpyAsync(empty, d_empty, (size_t)n_tiles, cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+// ------------------------------------------------------------------ halo exchange (region sharding)
+__global__ void k_halo_export(const uint32_t *__restrict__ c32, uint64_t stride, uint64_t col, uint32_t n,
+                              uint32_t *__restrict__ buf)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * kPlanes) return;
+    buf[t] = c32[(uint64_t)(t / n) * stride + col + (t % n)];
+}
+__global__ void k_halo_add(uint32_t *__restrict__ c32, uint64_t stride, uint64_t col, uint32_t n,
+                           const uint32_t *__restrict__ buf)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * kPlanes) return;
+    c32[(uint64_t)(t / n) * stride + col + (t % n)] += buf[t];
+}
+
+int bc_halo_export(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, uint32_t *dev_buf)
+{
+    if (!h || !dev_buf) return BC_ERR_ARG;
+    if (ref >= h->n_refs || (uint64_t)col_lo + n_cols > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "halo out of range");
+    if (n_cols == 0) return BC_OK;
+    CU(h, cudaSetDevice(h->device));
+    k_halo_export<<<(n_cols * kPlanes + 255) / 256, 256, 0, h->compute>>>(h->d_counts, h->stride,
+                                                                         (uint64_t)h->col_base[ref] + col_lo, n_cols, dev_buf);
+    h->launches++;
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, const uint32_t *dev_buf)
+{
+    if (!h || !dev_buf) return BC_ERR_ARG;
+    if (ref >= h->n_refs || (uint64_t)col_lo + n_cols > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "halo out of range");
+    if (n_cols == 0) return BC_OK;
+    CU(h, cudaSetDevice(h->device));
+    k_halo_add<<<(n_cols * kPlanes + 255) / 256, 256, 0, h->compute>>>(h->d_counts, h->stride,
+                                                                      (uint64_t)h->col_base[ref] + col_lo, n_cols, dev_buf);
+    h->launches++;
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+// ------------------------------------------------------------------ instrumentation
+int bc_timer_start(bc_handle *h)
+{
+    if (!h) return BC_ERR_ARG;
+    CU(h, cudaEventRecord(h->t0, h->compute));
+    return BC_OK;
+}
+
+int bc_timer_stop(bc_handle *h, float *ms)
+{
+    if (!h || !ms) return BC_ERR_ARG;
+    CU(h, cudaEventRecord(h->t1, h->compute));
+    CU(h, cudaEventSynchronize(h->t1));
+    CU(h, cudaEventElapsedTime(ms, h->t0, h->t1));
+    return BC_OK;
+}
+
+int bc_last_count_kernel_ms(bc_handle *h, float *ms)
+{
+    if (!h || !ms) return BC_ERR_ARG;
+    if (!h->k_timed) return fail(h, BC_ERR_STATE, "no counting kernel has run");
+    CU(h, cudaEventSynchronize(h->k1));
+    CU(h, cudaEventElapsedTime(ms, h->k0, h->k1));
+    return BC_OK;
+}
+
+uint64_t bc_kernel_launches(bc_handle *h) { return h ? h->launches : 0; }
+
+int bc_set_count_variant(bc_handle *h, int variant)
+{
+    if (!h || variant < 0 || variant > 1) return BC_ERR_ARG;
+    h->variant = variant;
+    return BC_OK;
+}
+
+// ------------------------------------------------------------------ host packer
+uint64_t bc_pack_words(uint32_t n_reads, const uint64_t *seq_off)
+{
+    uint64_t w = 0;
+    for (uint32_t i = 0; i < n_reads; i++) w += (seq_off[i + 1] - seq_off[i] + 31) / 32;
+    return w;
+}
+
+int bc_pack_reads(uint32_t n_reads, const uint8_t *seq, const uint8_t *qual, const uint64_t *seq_off,
+                  const uint32_t *cigar, const uint32_t *cigar_off, uint32_t min_base_quality,
+                  uint32_t *seq_woff_out, uint64_t *planes_out, uint32_t *okmask_out, uint32_t *exc_read_out,
+                  uint32_t *exc_pos_out, uint32_t exc_cap, uint32_t *n_exc)
+{
+    if (!seq_off || !seq_woff_out || !n_exc) return BC_ERR_ARG;
+    if (min_base_quality > 0 && (!okmask_out || !qual)) return BC_ERR_ARG;
+    // letter class: 0..3 = A,C,G,T; 4 = N; 5 = anything else (never counted, count.cpp:58-65)
+    uint8_t cls[256];
+    std::memset(cls, 5, sizeof(cls));
+    cls['A'] = 0; cls['C'] = 1; cls['G'] = 2; cls['T'] = 3; cls['N'] = 4;
+    uint64_t w = 0;
+    uint64_t ne = 0;
+    int status = BC_OK;
+    for (uint32_t i = 0; i < n_reads; i++) {
+        const uint64_t s0 = seq_off[i], len = seq_off[i + 1] - s0;
+        if (w > 0xFFFFFFFFull) return BC_ERR_ARG;
+        seq_woff_out[i] = (uint32_t)w;
+        if (cigar && cigar_off) {          // count.cpp:56,58 index quals/read unchecked: reject what would be UB there
+            uint64_t rp = 0;
+            for (uint32_t c = cigar_off[i]; c < cigar_off[i + 1]; c++) {
+                const uint32_t op = cigar[c] & 0xFu, l = cigar[c] >> 4;
+                if (op == 0 || op == 7 || op == 8) {
+                    if (l && rp + l > len) status = BC_ERR_READ_OVERRUN;
+                    rp += l;
+                } else if (op == 1) {
+                    rp += l;
+                }
+            }
+        }
+        for (uint64_t j0 = 0; j0 < len; j0 += 32, w++) {
+            const uint32_t m = (uint32_t)std::min<uint64_t>(32, len - j0);
+            uint32_t lo = 0, hi = 0, ok = 0;
+            const uint8_t *sp = seq + s0 + j0;
+            const uint8_t *qp = qual ? qual + s0 + j0 : nullptr;
+            for (uint32_t j = 0; j < m; j++) {
+                const uint8_t c = cls[sp[j]];
+                const bool pass = !qp || qp[j] >= min_base_quality;
+                if (c < 4) {
+                    lo |= (uint32_t)(c & 1u) << j;
+                    hi |= (uint32_t)(c >> 1) << j;
+                    ok |= (uint32_t)pass << j;
+                } else {
+                    uint32_t flags = 0;
+                    if (min_base_quality == 0) flags = (c == 4) ? 3u : 2u;     // undo the 'A', maybe count N
+                    else if (c == 4 && pass) flags = 1u;                       // masked out already; count N
+                    if (flags) {
+                        if (ne < exc_cap && exc_read_out && exc_pos_out) {
+                            exc_read_out[ne] = i;
+                            exc_pos_out[ne] = (uint32_t)((j0 + j) << 2) | flags;
+                        }
+                        ne++;
+                    }
+                }
+            }
+            if (planes_out) planes_out[w] = (uint64_t)lo | ((uint64_t)hi << 32);
+            if (okmask_out) okmask_out[w] = ok;
+        }
+        if (len >= (1ull << 30)) return BC_ERR_ARG;
+    }
+    if (w > 0xFFFFFFFFull || ne > 0xFFFFFFFFull) return BC_ERR_ARG;
+    seq_woff_out[n_reads] = (uint32_t)w;
+    *n_exc = (uint32_t)ne;
+    return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,448 @@
+// k1_count.cuh -- K1: CIGAR walk + per-position base counting on sm_100a.
+//
+// Replaces the loop nest of the reference operator (basecount/count.cpp:22-97).
+//
+// Design (B200-first, nothing here mirrors the reference's scalar loop):
+//   * A warp owns a chunk of consecutive reads of one reference slot.  Its 32 lanes
+//     form S = 32/G "read slots" of G lanes; lane (slot, w) covers the 32 reference
+//     columns of window word w.  All slots share ONE window of 32*G columns, so window
+//     moves and flushes are warp-uniform (no divergence between slots).
+//   * Sequence data is 2-bit, bit-planar (lo/hi plane): one 64-bit load + a funnel
+//     shift aligns 32 bases of a read onto a 32-column window word; three LOP3 build
+//     the masked one-hot words for A/C/G/T.  No per-base work anywhere.
+//   * Counts are accumulated VERTICALLY in registers as bit-sliced counters
+//     (carry-save adders, Harley-Seal style): ~3 LOP3 per 32 bases per base letter.
+//   * A flush converts the bit-sliced counters to integers (byte-packed extraction,
+//     PRMT transposes, shared-memory staging) and adds them to the HBM count planes
+//     with coalesced 128-byte RED.ADD -- one atomic per column per flush instead of
+//     one per base.
+//   * D / N ops add to the DS plane directly (rare); letters the 2-bit code cannot
+//     express (N, IUPAC, lower case) are a sparse correction pass (k1_exceptions).
+#pragma once
+#include "bc_common.cuh"
+
+namespace bc {
+
+constexpr int kK1WarpsPerCta = 8;
+constexpr int kK1Threads = kK1WarpsPerCta * 32;
+constexpr int kNB = 8;                       // bit planes per vertical counter (counts to 255)
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
+__device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b)
+{
+    uint32_t t = a + b;
+    return t < a ? 0xFFFFFFFFu : t;
+}
+
+// Vertical counters of one lane: for each of A,C,G,T, kNB bit planes over the lane's
+// 32 columns, plus the not-yet-paired carries of the first three adder levels.
+struct VCounters {
+    uint32_t pl[4][kNB];
+    uint32_t pend[4][3];
+    __device__ __forceinline__ void clear()
+    {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+#pragma unroll
+            for (int k = 0; k < kNB; k++) pl[b][k] = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) pend[b][k] = 0;
+        }
+    }
+    // Add one 32-column mask per letter.  `cnt` = inputs added so far (warp-uniform), so
+    // every branch below is uniform.
+    __device__ __forceinline__ void add(const uint32_t x[4], uint32_t cnt)
+    {
+        if ((cnt & 1u) == 0u) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) pend[b][0] = x[b];
+            return;
+        }
+        uint32_t c1[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            c1[b] = maj3(pl[b][0], pend[b][0], x[b]);
+            pl[b][0] ^= pend[b][0] ^ x[b];
+        }
+        if ((cnt & 2u) == 0u) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) pend[b][1] = c1[b];
+            return;
+        }
+        uint32_t c2[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            c2[b] = maj3(pl[b][1], pend[b][1], c1[b]);
+            pl[b][1] ^= pend[b][1] ^ c1[b];
+        }
+        if ((cnt & 4u) == 0u) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) pend[b][2] = c2[b];
+            return;
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            uint32_t c = maj3(pl[b][2], pend[b][2], c2[b]);
+            pl[b][2] ^= pend[b][2] ^ c2[b];
+#pragma unroll
+            for (int k = 3; k < kNB; k++) {          // ripple the weight-8 carry upwards
+                uint32_t t = pl[b][k] & c;
+                pl[b][k] ^= c;
+                c = t;
+            }
+        }
+    }
+};
+
+// Convert the warp's vertical counters to integers and add them to the HBM planes.
+// fbuf: this warp's staging area, 4 * 32*G bytes.  win_col = global column of window word 0.
+template <int G>
+__device__ __forceinline__ void flush_counters(VCounters &vc, uint32_t cnt, uint32_t *fbuf, uint64_t win_col,
+                                               uint32_t *__restrict__ counts, uint64_t stride, int lane)
+{
+    const int slot = lane / G, wl = lane % G;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        uint32_t v[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) {
+            // byte t of acc = count of column jj + 8t
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < kNB; k++) {
+                if ((cnt >> k) == 0u) break;                     // uniform: higher planes are empty
+                acc += ((vc.pl[b][k] >> jj) & 0x01010101u) << k;
+            }
+            if (cnt & 1u) acc += (vc.pend[b][0] >> jj) & 0x01010101u;
+            if (cnt & 2u) acc += ((vc.pend[b][1] >> jj) & 0x01010101u) << 1;
+            if (cnt & 4u) acc += ((vc.pend[b][2] >> jj) & 0x01010101u) << 2;
+#pragma unroll
+            for (int d = G; d < 32; d <<= 1) acc += __shfl_xor_sync(kFull, acc, d);   // sum the read slots
+            v[jj] = acc;
+        }
+        if (slot == 0) {
+            // 4x4 byte transposes: out word (t,h) = columns 8t+4h .. 8t+4h+3
+            uint8_t *row = reinterpret_cast<uint8_t *>(fbuf) + b * (32 * G) + 32 * wl;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    uint32_t sel = (uint32_t)t | ((uint32_t)(4 + t) << 4);
+                    uint32_t lo = __byte_perm(v[4 * h + 0], v[4 * h + 1], sel);
+                    uint32_t hi = __byte_perm(v[4 * h + 2], v[4 * h + 3], sel);
+                    *reinterpret_cast<uint32_t *>(row + 8 * t + 4 * h) = __byte_perm(lo, hi, 0x5410);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(fbuf);
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        uint32_t *plane = counts + (uint64_t)b * stride + win_col;
+        for (int w = 0; w < G; w++) {
+            uint32_t val = bytes[b * (32 * G) + 32 * w + lane];
+            if (val) atomicAdd(plane + 32 * w + lane, val);     // RED.ADD, 128 B per warp instruction
+        }
+    }
+    __syncwarp();
+    vc.clear();
+}
+
+template <int G, bool HAS_OK>
+__global__ void __launch_bounds__(kK1Threads)
+k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks)
+{
+    constexpr int S = 32 / G;
+    constexpr uint32_t kCntMax = 255u / S;          // byte-packed slot sums must stay <= 255
+    constexpr uint32_t kWin = 32u * G;              // window columns
+    constexpr uint32_t kMaxFit = kWin - 31u;        // a piece this long fits a fresh window at any alignment
+    extern __shared__ uint32_t k1_smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp_in_cta = threadIdx.x >> 5;
+    const uint32_t warp_id = blockIdx.x * kK1WarpsPerCta + warp_in_cta;
+    if (warp_id >= n_chunks) return;
+    uint32_t *fbuf = k1_smem + warp_in_cta * (32 * G);
+    const int slot = lane / G, wl = lane % G;
+    const uint32_t slot_lead_below = (slot == 0) ? 0u : ((1u << (slot * G)) - 1u);
+
+    const Chunk ch = chunks[warp_id];
+    const uint32_t ref_len = ch.ref_len;
+    uint32_t cursor = ch.read_begin;
+
+    // per read-slot state (replicated over the slot's G lanes)
+    uint32_t cur = 0, cend = 0, ref_pos = 0, read_pos = 0, wbase = 0, nwords = 0;
+    bool exhausted = false;
+    uint32_t pp = 0, pq = 0, pn = 0;                // pending M/=/X piece: ref pos, read pos, length
+    // warp-uniform window + counter state
+    uint32_t win_lo = 0, cnt = 0;
+    bool win_valid = false;
+    VCounters vc;
+    vc.clear();
+
+    for (;;) {
+        // ---- A: read slots that finished their read pull the next ones, in order
+        const bool need = (pn == 0u) && (cur == cend) && !exhausted;
+        const uint32_t need_mask = __ballot_sync(kFull, need && wl == 0);
+        if (need_mask) {
+            if (need) {
+                const uint32_t idx = cursor + __popc(need_mask & slot_lead_below);
+                if (idx < ch.read_end) {
+                    ref_pos = __ldg(bv.starts + idx);
+                    cur = __ldg(bv.cigar_off + idx);
+                    cend = __ldg(bv.cigar_off + idx + 1);
+                    wbase = __ldg(bv.seq_woff + idx);
+                    nwords = __ldg(bv.seq_woff + idx + 1) - wbase;
+                    read_pos = 0;
+                } else {
+                    exhausted = true;
+                }
+            }
+            cursor += __popc(need_mask);
+        }
+        // ---- B: no piece pending -> consume one CIGAR op (count.cpp:40-96)
+        if (pn == 0u && cur < cend) {
+            const uint32_t cw = __ldg(bv.cigar + cur);
+            cur++;
+            const uint32_t op = cw & 0xFu, len = cw >> 4;
+            if (op_is_match(op)) {                                   // count.cpp:51
+                pp = ref_pos;
+                pq = read_pos;
+                pn = len;
+                ref_pos = sat_add(ref_pos, len);
+                read_pos = sat_add(read_pos, len);
+                if (pn && (pp >= ref_len || pn > ref_len - pp)) {    // would index past the matrix
+                    if (wl == 0) cv.status[kStatMaybeOverflow] = 1u; // exactness decided by k1_check_overflow
+                    pn = pp < ref_len ? ref_len - pp : 0u;
+                }
+            } else if (op == 1u) {                                   // insertion, count.cpp:74
+                read_pos = sat_add(read_pos, len);
+            } else if (op_is_refskip(op)) {                          // deletion / skip, count.cpp:80-87
+                uint32_t lim = ref_pos < ref_len ? min(len, ref_len - ref_pos) : 0u;
+                if (lim < len && wl == 0) cv.status[kStatIndexError] = 1u;
+                uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + ch.col_base + ref_pos;
+                for (uint32_t t = wl; t < lim; t += G) atomicAdd(ds + t, 1u);
+                ref_pos = sat_add(ref_pos, len);
+            }                                                        // S,H,P,B: ignored, count.cpp:92-95
+        }
+        // ---- C: done?
+        const bool active = pn > 0u;
+        if (!__any_sync(kFull, active || cur < cend || !exhausted)) break;
+        // ---- D: which pieces can go into the current window?
+        const uint32_t win_hi = win_lo + kWin;
+        const bool fits = active && win_valid && pp >= win_lo && pp < win_hi &&
+                          (pn <= win_hi - pp || pn > kMaxFit);
+        if (__ballot_sync(kFull, fits) == 0u) {
+            if (__ballot_sync(kFull, active) == 0u) continue;        // still walking ops / fetching
+            if (cnt) {
+                flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
+                cnt = 0;
+            }
+            const uint32_t lowest = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu);
+            win_lo = lowest & ~31u;
+            win_valid = true;
+            continue;
+        }
+        // ---- E: one masked 32-column word per lane, added to the vertical counters
+        uint32_t x[4] = {0u, 0u, 0u, 0u};
+        uint32_t n1 = 0;
+        if (fits) {
+            n1 = min(pn, win_hi - pp);
+            const int rel = (int)(win_lo + 32u * (uint32_t)wl) - (int)pp;   // lane word starts at piece offset rel
+            const int a = max(rel, 0), e = min(rel + 32, (int)n1);
+            if (a < e) {
+                const int bit = (int)pq + rel;                        // read bit index of the word's column 0
+                const int k = bit >> 5, sh = bit & 31;
+                uint2 w0 = make_uint2(0u, 0u), w1 = make_uint2(0u, 0u);
+                uint32_t o0 = 0u, o1 = 0u;
+                if (k >= 0 && (uint32_t)k < nwords) {
+                    w0 = __ldg(bv.planes + wbase + k);
+                    if (HAS_OK) o0 = __ldg(bv.okmask + wbase + k);
+                }
+                if (k + 1 >= 0 && (uint32_t)(k + 1) < nwords) {
+                    w1 = __ldg(bv.planes + wbase + k + 1);
+                    if (HAS_OK) o1 = __ldg(bv.okmask + wbase + k + 1);
+                }
+                const uint32_t lo = __funnelshift_r(w0.x, w1.x, sh);
+                const uint32_t hi = __funnelshift_r(w0.y, w1.y, sh);
+                const int lo_bit = a - rel, hi_bit = e - rel;         // [lo_bit, hi_bit) of this word are in the piece
+                uint32_t m = (hi_bit >= 32 ? 0xFFFFFFFFu : ((1u << hi_bit) - 1u)) & (0xFFFFFFFFu << lo_bit);
+                if (HAS_OK) m &= __funnelshift_r(o0, o1, sh);
+                x[0] = ~hi & ~lo & m;                                 // A
+                x[1] = ~hi & lo & m;                                  // C
+                x[2] = hi & ~lo & m;                                  // G
+                x[3] = hi & lo & m;                                   // T
+            }
+        }
+        vc.add(x, cnt);
+        pp += n1;
+        pq += n1;
+        pn -= n1;
+        if (++cnt == kCntMax) {
+            flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
+            cnt = 0;
+        }
+    }
+    if (cnt) flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
+}
+
+// Cross-check variant: one thread per read, one RED per base.  Same inputs, same planes.
+__global__ void k1_count_per_base(BatchView bv, CountView cv)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bv.n_reads) return;
+    const uint32_t r = slot_of_read(bv.ref_read_off, bv.n_refs, i);
+    const uint32_t ref_len = cv.ref_len[r];
+    const uint64_t base = cv.col_base[r];
+    uint32_t ref_pos = bv.starts[i], read_pos = 0;
+    const uint32_t wbase = bv.seq_woff[i], nwords = bv.seq_woff[i + 1] - wbase;
+    for (uint32_t c = bv.cigar_off[i]; c < bv.cigar_off[i + 1]; c++) {
+        const uint32_t op = bv.cigar[c] & 0xFu, len = bv.cigar[c] >> 4;
+        if (op_is_match(op)) {
+            for (uint32_t j = 0; j < len; j++) {
+                const uint32_t rp = read_pos + j, col = ref_pos + j;
+                if ((rp >> 5) >= nwords) break;
+                const uint2 w = bv.planes[wbase + (rp >> 5)];
+                const uint32_t code = ((w.x >> (rp & 31)) & 1u) | (((w.y >> (rp & 31)) & 1u) << 1);
+                const bool ok = bv.okmask ? ((bv.okmask[wbase + (rp >> 5)] >> (rp & 31)) & 1u) : true;
+                if (!ok) continue;
+                if (col >= ref_len || col < ref_pos) { cv.status[kStatMaybeOverflow] = 1u; continue; }
+                atomicAdd(cv.counts + (uint64_t)code * cv.stride + base + col, 1u);
+            }
+            ref_pos = sat_add(ref_pos, len);
+            read_pos = sat_add(read_pos, len);
+        } else if (op == 1u) {
+            read_pos = sat_add(read_pos, len);
+        } else if (op_is_refskip(op)) {
+            for (uint32_t j = 0; j < len; j++) {
+                const uint32_t col = ref_pos + j;
+                if (col >= ref_len || col < ref_pos) { cv.status[kStatIndexError] = 1u; break; }
+                atomicAdd(cv.counts + (uint64_t)kPlaneDS * cv.stride + base + col, 1u);
+            }
+            ref_pos = sat_add(ref_pos, len);
+        }
+    }
+}
+
+// Map a read position to its reference column by walking the read's CIGAR.
+// Returns false if the position lies in an insertion (or past the alignment).
+__device__ __forceinline__ bool read_pos_to_col(const BatchView &bv, uint32_t i, uint32_t pos, uint32_t *col)
+{
+    uint32_t ref_pos = bv.starts[i], read_pos = 0;
+    for (uint32_t c = bv.cigar_off[i]; c < bv.cigar_off[i + 1]; c++) {
+        const uint32_t op = bv.cigar[c] & 0xFu, len = bv.cigar[c] >> 4;
+        if (op_is_match(op)) {
+            if (pos >= read_pos && pos - read_pos < len) {
+                const uint32_t t = ref_pos + (pos - read_pos);
+                if (t < ref_pos) return false;      // wrapped: far past any reference
+                *col = t;
+                return true;
+            }
+            ref_pos = sat_add(ref_pos, len);
+            read_pos = sat_add(read_pos, len);
+        } else if (op == 1u) {
+            if (pos >= read_pos && pos - read_pos < len) return false;
+            read_pos = sat_add(read_pos, len);
+        } else if (op_is_refskip(op)) {
+            ref_pos = sat_add(ref_pos, len);
+        }
+    }
+    return false;
+}
+
+// Sparse corrections for letters outside ACGT (see bc_batch.exc_* in the header).
+__global__ void k1_exceptions(BatchView bv, CountView cv)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= bv.n_exc) return;
+    const uint32_t i = bv.exc_read[e];
+    const uint32_t pos = bv.exc_pos[e] >> 2, flags = bv.exc_pos[e] & 3u;
+    if (i >= bv.n_reads) return;
+    uint32_t col;
+    if (!read_pos_to_col(bv, i, pos, &col)) return;
+    const uint32_t r = slot_of_read(bv.ref_read_off, bv.n_refs, i);
+    const uint64_t base = cv.col_base[r];
+    if (col >= cv.ref_len[r]) {
+        if (flags & 1u) cv.status[kStatIndexError] = 1u;   // an N that counts, past the end (count.cpp:64)
+        return;                                            // flag 2: the main pass clipped it already
+    }
+    if (flags & 2u) atomicAdd(cv.counts + base + col, 0xFFFFFFFFu);                              // undo the 'A'
+    if (flags & 1u) atomicAdd(cv.counts + (uint64_t)kPlaneN * cv.stride + base + col, 1u);     // count.cpp:64
+}
+
+__device__ __forceinline__ uint32_t find_exception(const BatchView &bv, uint32_t i, uint32_t pos)
+{
+    // exceptions are sorted by (read, pos); returns flags or 0xFFFFFFFF if absent
+    uint32_t lo = 0, hi = bv.n_exc;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint32_t r = bv.exc_read[mid], p = bv.exc_pos[mid] >> 2;
+        if (r < i || (r == i && p < pos)) lo = mid + 1; else hi = mid;
+    }
+    if (lo < bv.n_exc && bv.exc_read[lo] == i && (bv.exc_pos[lo] >> 2) == pos) return bv.exc_pos[lo] & 3u;
+    return 0xFFFFFFFFu;
+}
+
+// Runs only when a piece crossed ref_len: decides, base by base, whether the reference
+// would have thrown (an INCREMENT at refPos >= refLen, count.cpp:60-64) -- bases that fail
+// the quality test or are not in ACGTN never index the matrix and never throw.
+__global__ void k1_check_overflow(BatchView bv, CountView cv)
+{
+    if (cv.status[kStatMaybeOverflow] == 0u) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bv.n_reads) return;
+    const uint32_t r = slot_of_read(bv.ref_read_off, bv.n_refs, i);
+    const uint32_t ref_len = cv.ref_len[r];
+    uint32_t ref_pos = bv.starts[i], read_pos = 0;
+    const uint32_t wbase = bv.seq_woff[i], nwords = bv.seq_woff[i + 1] - wbase;
+    for (uint32_t c = bv.cigar_off[i]; c < bv.cigar_off[i + 1]; c++) {
+        const uint32_t op = bv.cigar[c] & 0xFu, len = bv.cigar[c] >> 4;
+        if (op_is_match(op)) {
+            if (len && (ref_pos >= ref_len || len > ref_len - ref_pos)) {
+                const uint32_t first = ref_pos >= ref_len ? 0u : ref_len - ref_pos;
+                for (uint32_t j = first; j < len; j++) {
+                    const uint32_t rp = read_pos + j;
+                    if (rp < read_pos || (rp >> 5) >= nwords) break;
+                    bool counted;
+                    const uint32_t ex = find_exception(bv, i, rp);
+                    if (bv.okmask) {
+                        counted = ((bv.okmask[wbase + (rp >> 5)] >> (rp & 31)) & 1u) || (ex != 0xFFFFFFFFu && (ex & 1u));
+                    } else {
+                        counted = (ex == 0xFFFFFFFFu) || (ex & 1u) || !(ex & 2u);
+                    }
+                    if (counted) { cv.status[kStatIndexError] = 1u; return; }
+                }
+            }
+            ref_pos = sat_add(ref_pos, len);
+            read_pos = sat_add(read_pos, len);
+        } else if (op == 1u) {
+            read_pos = sat_add(read_pos, len);
+        } else if (op_is_refskip(op)) {
+            ref_pos = sat_add(ref_pos, len);
+        }
+    }
+}
+
+// uint32 per-batch counters -> int64 totals (only needed past 2^32 reads; main.py:132,155)
+__global__ void k_fold_counts(uint32_t *__restrict__ c32, unsigned long long *__restrict__ c64, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    c64[i] += c32[i];
+    c32[i] = 0u;
+}
+
+// planes -> refLen x 6 int64 row-major (the layout the reference hands to get_stats)
+__global__ void k_export_counts(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64,
+                                uint64_t stride, uint64_t col_base, uint32_t ref_len, long long *__restrict__ out)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)ref_len * kPlanes) return;
+    const uint32_t pos = (uint32_t)(t / kPlanes), p = (uint32_t)(t % kPlanes);
+    const uint64_t src = (uint64_t)p * stride + col_base + pos;
+    out[t] = (long long)c32[src] + (c64 ? (long long)c64[src] : 0ll);
+}
+
+}  // namespace bc

@@ -1,0 +1,176 @@
+// k2_stats.cuh -- K2: fused per-position statistics, and the --summarise reduction.
+//
+// Replaces get_stats / get_entropy (basecount/main.py:10-53) and the three reductions
+// of the summarise block (main.py:479-485).  One thread per reference position reads the
+// six count planes (coalesced, 4 B per lane per plane) and produces coverage, the K
+// percentages, normalised entropy and secondary entropy in float64 with the reference's
+// exact operation order:
+//     p_i  = c_i / coverage                         (main.py:40)
+//     pc_i = 100 * p_i                              (main.py:41)  -- divide, then scale
+//     H    = norm * sum_i( -(p_i * log2 p_i) )      (main.py:11,42)
+// `sum` is Python's builtin: on CPython >= 3.12 a Neumaier-compensated float sum that
+// starts from int 0; neumaier_sum() below restates it so the only difference left between
+// the two implementations is log2 itself (CUDA libdevice vs glibc, both < 1 ulp).
+// Compiled with -fmad=false so nothing is contracted.
+#pragma once
+#include "bc_common.cuh"
+
+namespace bc {
+
+struct PosStats {
+    long long cov;
+    double pc[6];
+    double ent, sec;
+    uint32_t flags;     // bit0: coverage == 0, bit1: secondary coverage == 0
+};
+
+__device__ __forceinline__ double neumaier_entropy(const long long *c, int n, long long total, int skip)
+{
+    double hi = 0.0, lo = 0.0;
+    const double tot = (double)total;
+    for (int i = 0; i < n; i++) {
+        if (i == skip || c[i] == 0) continue;            // p == 0 contributes int 0 (main.py:11)
+        const double p = (double)c[i] / tot;
+        const double x = -(p * log2(p));
+        const double t = hi + x;
+        if (fabs(hi) >= fabs(x)) lo += (hi - t) + x; else lo += (x - t) + hi;
+        hi = t;
+    }
+    if (lo != 0.0 && isfinite(lo)) return hi + lo;
+    return hi;
+}
+
+__device__ __forceinline__ void position_stats(const long long *c, int K, double norm, double norm2, PosStats &o)
+{
+    long long cov = 0;
+    for (int i = 0; i < K; i++) cov += c[i];                          // main.py:37
+    o.cov = cov;
+    o.flags = 0;
+    if (cov == 0) {                                                   // main.py:34-36
+        for (int i = 0; i < K; i++) o.pc[i] = -1.0;
+        o.ent = 1.0;
+        o.sec = 1.0;
+        o.flags = 3u;
+        return;
+    }
+    const double dcov = (double)cov;
+    for (int i = 0; i < K; i++) o.pc[i] = 100.0 * ((double)c[i] / dcov);
+    o.ent = norm * neumaier_entropy(c, K, cov, -1);
+    int top = 0;
+    for (int i = 1; i < K; i++) if (c[i] > c[top]) top = i;           // first maximum, np.argmax (main.py:45)
+    const long long rest = cov - c[top];
+    if (rest == 0) {                                                  // main.py:47
+        o.sec = 1.0;
+        o.flags = 2u;
+    } else {
+        o.sec = norm2 * neumaier_entropy(c, K, rest, top);            // main.py:48-53
+    }
+}
+
+__device__ __forceinline__ void load_counts(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64,
+                                            uint64_t stride, uint64_t col, int K, long long *c)
+{
+#pragma unroll
+    for (int p = 0; p < kPlanes; p++) {
+        if (p < K) {
+            const uint64_t a = (uint64_t)p * stride + col;
+            c[p] = (long long)c32[a] + (c64 ? (long long)c64[a] : 0ll);
+        }
+    }
+}
+
+// Per-position outputs for one slot (TSV / records / amplicon inputs).  Any output may be NULL.
+__global__ void __launch_bounds__(256)
+k2_stats_rows(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64, uint64_t stride,
+              uint64_t col_base, uint32_t ref_len, int K, double norm, double norm2,
+              long long *__restrict__ coverage, double *__restrict__ pc, double *__restrict__ entropy,
+              double *__restrict__ secondary, uint8_t *__restrict__ flags)
+{
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= ref_len) return;
+    long long c[6];
+    load_counts(c32, c64, stride, col_base + pos, K, c);
+    PosStats s;
+    position_stats(c, K, norm, norm2, s);
+    if (coverage) coverage[pos] = s.cov;
+    if (pc) for (int i = 0; i < K; i++) pc[(uint64_t)i * ref_len + pos] = s.pc[i];
+    if (entropy) entropy[pos] = s.ent;
+    if (secondary) secondary[pos] = s.sec;
+    if (flags) flags[pos] = (uint8_t)s.flags;
+}
+
+struct SummaryPartial {
+    long long nonzero;
+    long long cov_sum;
+    double ent_sum;
+};
+
+constexpr int kSummaryBlocks = 64;    // partials per slot (fixed -> deterministic reduction order)
+
+// Fused stats + summarise partials for ALL slots: grid = (kSummaryBlocks, n_refs).
+__global__ void __launch_bounds__(256)
+k2_summary_partials(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64, uint64_t stride,
+                    const uint32_t *__restrict__ col_base, const uint32_t *__restrict__ ref_len, int K,
+                    double norm, double norm2, SummaryPartial *__restrict__ partials)
+{
+    const uint32_t r = blockIdx.y;
+    const uint32_t L = ref_len[r];
+    const uint64_t base = col_base[r];
+    long long nz = 0, cs = 0;
+    double es = 0.0;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < L; pos += gridDim.x * blockDim.x) {
+        long long c[6];
+        load_counts(c32, c64, stride, base + pos, K, c);
+        PosStats s;
+        position_stats(c, K, norm, norm2, s);
+        nz += (s.cov != 0);
+        cs += s.cov;
+        es += s.ent;
+    }
+    __shared__ long long s_nz[256], s_cs[256];
+    __shared__ double s_es[256];
+    s_nz[threadIdx.x] = nz;
+    s_cs[threadIdx.x] = cs;
+    s_es[threadIdx.x] = es;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            s_nz[threadIdx.x] += s_nz[threadIdx.x + d];
+            s_cs[threadIdx.x] += s_cs[threadIdx.x + d];
+            s_es[threadIdx.x] += s_es[threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        SummaryPartial p;
+        p.nonzero = s_nz[0];
+        p.cov_sum = s_cs[0];
+        p.ent_sum = s_es[0];
+        partials[(uint64_t)r * gridDim.x + blockIdx.x] = p;
+    }
+}
+
+// grid = n_refs, block = kSummaryBlocks: fixed-order tree over the partials.
+__global__ void k2_summary_final(const SummaryPartial *__restrict__ partials, long long *__restrict__ nonzero,
+                                 long long *__restrict__ cov_sum, double *__restrict__ ent_sum)
+{
+    __shared__ SummaryPartial s[kSummaryBlocks];
+    const uint32_t r = blockIdx.x;
+    s[threadIdx.x] = partials[(uint64_t)r * kSummaryBlocks + threadIdx.x];
+    __syncthreads();
+    for (int d = kSummaryBlocks / 2; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            s[threadIdx.x].nonzero += s[threadIdx.x + d].nonzero;
+            s[threadIdx.x].cov_sum += s[threadIdx.x + d].cov_sum;
+            s[threadIdx.x].ent_sum += s[threadIdx.x + d].ent_sum;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        nonzero[r] = s[0].nonzero;
+        cov_sum[r] = s[0].cov_sum;
+        ent_sum[r] = s[0].ent_sum;
+    }
+}
+
+}  // namespace bc

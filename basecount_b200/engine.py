@@ -1,0 +1,162 @@
+"""Python face of the C ABI: one Engine = one GPU's accumulators, streams and kernels."""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from .pack import PackedBatch
+
+
+def norm_factors(show_n_bases: bool):
+    """(1/log2(K), 1/log2(K-1)) computed exactly as the reference does (main.py:22-25)."""
+    k = 6 if show_n_bases else 5
+    return 1 / math.log2(k), 1 / math.log2(k - 1)
+
+
+class ResidentBatch:
+    """A packed batch kept in HBM (bench kernel-only timing; repeated counting)."""
+
+    def __init__(self, engine: "Engine", host: PackedBatch):
+        self.engine = engine
+        self.host = host
+        self.struct = _lib.BcBatch()
+        _lib.check(engine._h, _lib.lib().bc_batch_upload(engine._h, ctypes.byref(host.as_struct()),
+                                                         ctypes.byref(self.struct)))
+
+    def free(self):
+        if self.struct is not None and self.engine._h:
+            _lib.lib().bc_batch_free(self.engine._h, ctypes.byref(self.struct))
+        self.struct = None
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._L = _lib.lib()
+        self._h = ctypes.c_void_p()
+        rc = self._L.bc_create(int(device), ctypes.byref(self._h))
+        if rc != _lib.BC_OK:
+            msg = self._L.bc_last_error(None)
+            self._h = None
+            raise RuntimeError(f"bc_create(device={device}) failed: {msg.decode() if msg else rc}")
+        self.device = device
+        self.ref_lens = []
+        self._keepalive = []
+
+    # -- lifecycle
+    def close(self):
+        if self._h:
+            self._L.bc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- accumulators
+    def begin(self, ref_lens):
+        lens = np.ascontiguousarray(ref_lens, dtype=np.int64)
+        if lens.ndim != 1 or lens.size == 0 or (lens < 0).any():
+            raise TypeError("ref_lens must be a non-empty list of unsigned ints")
+        arr = lens.astype(np.uint32)
+        _lib.check(self._h, self._L.bc_begin(self._h, arr.size, _lib.ptr(arr)))
+        self.ref_lens = [int(x) for x in lens]
+        self._keepalive.clear()
+
+    def reset(self):
+        """Zero the accumulators again, keeping the slots (asynchronous)."""
+        _lib.check(self._h, self._L.bc_reset(self._h))
+
+    # -- the operator
+    def push(self, batch):
+        """Queue one batch (PackedBatch in host memory, or ResidentBatch in HBM). Asynchronous."""
+        if isinstance(batch, ResidentBatch):
+            _lib.check(self._h, self._L.bc_push_batch(self._h, ctypes.byref(batch.struct)))
+            return
+        self._keepalive.append(batch)           # host buffers must outlive the async copies
+        _lib.check(self._h, self._L.bc_push_batch(self._h, ctypes.byref(batch.as_struct())))
+
+    def sync(self):
+        try:
+            _lib.check(self._h, self._L.bc_sync(self._h))
+        finally:
+            self._keepalive.clear()
+
+    def upload(self, packed: PackedBatch) -> ResidentBatch:
+        return ResidentBatch(self, packed)
+
+    # -- results
+    def counts(self, ref: int = 0) -> np.ndarray:
+        out = np.empty((self.ref_lens[ref], 6), dtype=np.int64)
+        _lib.check(self._h, self._L.bc_counts(self._h, ref, _lib.ptr(out)))
+        return out
+
+    def stats(self, ref: int = 0, show_n_bases: bool = False, want_pc: bool = True):
+        L = self.ref_lens[ref]
+        k = 6 if show_n_bases else 5
+        n1, n2 = norm_factors(show_n_bases)
+        cov = np.empty(L, dtype=np.int64)
+        pc = np.empty((k, L), dtype=np.float64) if want_pc else None
+        ent = np.empty(L, dtype=np.float64)
+        sec = np.empty(L, dtype=np.float64)
+        flags = np.empty(L, dtype=np.uint8)
+        _lib.check(self._h, self._L.bc_stats(self._h, ref, int(show_n_bases), n1, n2, _lib.ptr(cov), _lib.ptr(pc),
+                                             _lib.ptr(ent), _lib.ptr(sec), _lib.ptr(flags)))
+        return {"coverage": cov, "pc": pc, "entropy": ent, "secondary": sec, "flags": flags}
+
+    def summary(self, show_n_bases: bool = False):
+        r = len(self.ref_lens)
+        n1, n2 = norm_factors(show_n_bases)
+        nz = np.empty(r, dtype=np.int64)
+        cs = np.empty(r, dtype=np.int64)
+        es = np.empty(r, dtype=np.float64)
+        _lib.check(self._h, self._L.bc_summary(self._h, int(show_n_bases), n1, n2, _lib.ptr(nz), _lib.ptr(cs), _lib.ptr(es)))
+        return nz, cs, es
+
+    def amplicons(self, ref: int, lo, hi, show_n_bases: bool = False):
+        lo = np.ascontiguousarray(lo, dtype=np.int32)
+        hi = np.ascontiguousarray(hi, dtype=np.int32)
+        t = int(lo.shape[0])
+        out = np.empty((6, t), dtype=np.float64)
+        empty = np.zeros(t, dtype=np.uint8)
+        n1, n2 = norm_factors(show_n_bases)
+        _lib.check(self._h, self._L.bc_amplicons(self._h, ref, int(show_n_bases), n1, n2, t, _lib.ptr(lo), _lib.ptr(hi),
+                                                 _lib.ptr(out), _lib.ptr(empty)))
+        return out, empty
+
+    # -- region sharding
+    def halo_export(self, ref: int, col_lo: int, n_cols: int, dev_ptr: int):
+        _lib.check(self._h, self._L.bc_halo_export(self._h, ref, col_lo, n_cols, ctypes.c_void_p(dev_ptr)))
+
+    def halo_add(self, ref: int, col_lo: int, n_cols: int, dev_ptr: int):
+        _lib.check(self._h, self._L.bc_halo_add(self._h, ref, col_lo, n_cols, ctypes.c_void_p(dev_ptr)))
+
+    # -- instrumentation
+    def timer_start(self):
+        _lib.check(self._h, self._L.bc_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float()
+        _lib.check(self._h, self._L.bc_timer_stop(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def last_count_kernel_ms(self) -> float:
+        ms = ctypes.c_float()
+        _lib.check(self._h, self._L.bc_last_count_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def kernel_launches(self) -> int:
+        return int(self._L.bc_kernel_launches(self._h))
+
+    def set_count_variant(self, variant: int):
+        _lib.check(self._h, self._L.bc_set_count_variant(self._h, variant))

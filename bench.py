@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- aligned bases counted per second on the pileup counting hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+One "step" = one pass of the hot path over one batch: zero the accumulators, K1 (CIGAR
+walk + count, with its sparse corrections), K2+K3 (--summarise reductions) and the
+read-back of the per-sample summary scalars.
+
+Default workload (`cfg2x12`): BASELINE.json configs[1] -- the SARS-CoV-2 29,903 bp
+reference, ~124k synthetic 400 bp amplicon reads per sample, `--summarise` -- batched as
+12 independent samples per GPU (configs[3]: 96 samples over 8 GPUs = 12 per GPU), so the
+per-step input (~180 MB) exceeds the 126 MB L2 and N GPUs weak-scale to 12*N samples with
+no data-path collective.  Two different resident batches alternate between steps.
+
+The JSON line carries `value` (inputs resident in HBM, CUDA-event timed), `e2e` (the same
+step through the C ABI from pinned host buffers, H2D and D2H inside the timed region),
+`roofline` for the counting kernel against MEASURED_PEAKS.json and `cpu_baseline`
+(the compiled reference operator + the oracle's port of get_stats on one host core).
+`--impl reference` times the reference's CPU path with every host core (one process per
+sample); it is the only arm that executes oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aligned_bases_per_sec"
+UNIT = "aligned bases/s"
+SAMPLES_PER_GPU = 12
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2x12", choices=["cfg2x12", "cfg3", "cfg5"])
+    ap.add_argument("--samples-per-gpu", type=int, default=SAMPLES_PER_GPU)
+    ap.add_argument("--reads-per-sample", type=int, default=124_000)
+    ap.add_argument("--cfg5-reads", type=int, default=12_888_833)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="0 tiled bit-sliced K1, 1 per-base atomics K1")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- workloads
+def make_samples(seeds, n_reads):
+    from basecount_b200 import synth
+    from basecount_b200.records import select_reads
+    return [select_reads(synth.amplicon_sample(seed=s, n_reads=n_reads), 0, 0) for s in seeds]
+
+
+def build_workload(args, rank):
+    """Returns (list of ReadBatch lists [one per alternating batch], ref_lens, label)."""
+    from basecount_b200 import synth
+    from basecount_b200.records import select_reads
+    if args.workload == "cfg2x12":
+        s = args.samples_per_gpu
+        base = 100 + rank * 2 * s
+        sets = [make_samples(range(base, base + s), args.reads_per_sample),
+                make_samples(range(base + s, base + 2 * s), args.reads_per_sample)]
+        return sets, [synth.SARS2_LEN] * s, f"cfg2_summarise_x{s}_samples_per_gpu"
+    if args.workload == "cfg3":
+        sets = [[select_reads(synth.deep_short_read_sample(seed=3 + 10 * rank + i), 0, 0)] for i in range(2)]
+        return sets, [synth.SARS2_LEN], "cfg3_2M_reads_150bp"
+    n = args.cfg5_reads
+    L = int(synth.CHR20_LEN * (n / 12_888_833))
+    sets = [[select_reads(synth.uniform_short_read_sample(seed=5 + rank, ref_len=L, n_reads=n), 0, 0)]]
+    return sets, [L], f"cfg5_uniform_150bp_L{L}"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU legs (execute oracle/)
+def _cpu_sample_worker(payload):
+    """One sample through the reference's CPU path: compiled count.cpp bcount (oracle/_ref) when
+    present, else the C port; then the oracle's port of get_stats + the summarise block."""
+    from oracle import bcount as obc
+    from oracle import stats as ost
+    lists, ref_len, use_ref = payload
+    t0 = time.perf_counter()
+    if use_ref:
+        counts = obc.load_ref_bcount()(ref_len, 0, *lists)
+    else:
+        from basecount_b200.records import ReadBatch
+        counts = obc.bcount_flat(ref_len, 0, ReadBatch.from_lists(*lists)).tolist()
+    t1 = time.perf_counter()
+    cov, ent, _ = ost.per_position_vectors(counts)
+    ost.summary(cov, ent, ref_len)
+    return t1 - t0, time.perf_counter() - t1
+
+
+def cpu_baseline(samples, ref_len, n_samples=3):
+    """Single core (the reference is single-threaded): bcount + get_stats + summary on a bounded sample."""
+    from oracle import bcount as obc
+    use_ref = obc.load_ref_bcount() is not None
+    chosen = samples[:n_samples]
+    bases = sum(b.aligned_bases() for b in chosen)
+    payloads = [(b.to_lists(), ref_len, use_ref) for b in chosen]      # list building is not timed (pysam's job)
+    t_count = t_stats = 0.0
+    for p in payloads:
+        a, b = _cpu_sample_worker(p)
+        t_count += a
+        t_stats += b
+    return {"value": bases / (t_count + t_stats), "unit": UNIT, "cores": 1,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"{len(chosen)} of the step's samples ({bases} aligned bases): "
+                      f"{'compiled count.cpp bcount (oracle/_ref)' if use_ref else 'C port of bcount'} {t_count:.2f}s "
+                      f"+ python port of get_stats/summarise {t_stats:.2f}s; Python-list inputs prebuilt"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on every host core (one process per sample)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import concurrent.futures as cf
+    from basecount_b200 import synth
+    from oracle import bcount as obc
+    use_ref = obc.load_ref_bcount() is not None
+    cores = os.cpu_count() or 1
+    per_step = max(1, min(args.samples_per_gpu, cores))
+    samples = make_samples(range(100, 100 + per_step), args.reads_per_sample)
+    bases = sum(b.aligned_bases() for b in samples)
+    payloads = [(b.to_lists(), synth.SARS2_LEN, use_ref) for b in samples]
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    with cf.ProcessPoolExecutor(max_workers=per_step) as ex:
+        for _ in range(warm):
+            list(ex.map(_cpu_sample_worker, payloads))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            list(ex.map(_cpu_sample_worker, payloads))
+        dt = time.perf_counter() - t0
+    value = bases * steps / dt
+    sample = (f"each step = {per_step} samples x {args.reads_per_sample} reads in {per_step} processes "
+              f"(argument pickling to the workers included); steps capped at {steps}, warmup {warm}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"cfg2_summarise_x{per_step}_samples", "reads_per_sample": args.reads_per_sample,
+                       "ref_len": synth.SARS2_LEN},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": per_step, "kind": "reference" if use_ref else "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: basecount_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    import __graft_entry__ as ge
+    ge.build()
+    from basecount_b200.engine import Engine
+    from basecount_b200.pack import pack_batches
+
+    sets, ref_lens, label = build_workload(args, rank)
+    eng = Engine(local)
+    eng.set_count_variant(args.variant)
+    eng.begin(ref_lens)
+    packed = [pack_batches(s, 0, pinned=True) for s in sets]
+    resident = [eng.upload(p) for p in packed]
+    bases_per_step = [p.aligned_bases for p in packed]
+    alg_bytes = [p.algorithmic_bytes(ref_lens) for p in packed]
+    d2h_bytes = len(ref_lens) * 24
+
+    def step_resident(i):
+        eng.reset()
+        eng.push(resident[i % len(resident)])
+        return eng.summary(False)                 # K2 + K3, D2H of the per-sample scalars, sync
+
+    def step_e2e(i):
+        eng.reset()
+        eng.push(packed[i % len(packed)])         # pinned host SoA -> H2D -> K1
+        out = eng.summary(False)
+        eng.sync()
+        return out
+
+    # ---- correctness guard: the timed configuration must produce the oracle's summary
+    # (size-independent property: the synthetic reads hold only A,C,G,T,N, so every aligned base
+    # lands in exactly one cell of its sample's matrix)
+    nz, cs, _ = step_resident(0)
+    eng.sync()
+    c0 = eng.counts(0)
+    assert int(c0.sum()) == sets[0][0].aligned_bases(), "cells do not add up to the aligned bases"
+    assert int(cs[0]) == int(c0[:, :5].sum()) and int(nz[0]) == int((c0[:, :5].sum(axis=1) != 0).sum())
+
+    # ---- value: inputs resident in HBM
+    for i in range(args.warmup):
+        step_resident(i)
+    eng.sync()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    k1_ms = []
+    launches0 = eng.kernel_launches()
+    eng.timer_start()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        step_resident(i)
+        k1_ms.append((eng.last_count_kernel_ms(), i % len(resident)))
+    ms_dev = eng.timer_stop()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    launches = eng.kernel_launches() - launches0
+    ms_dev = max_over_ranks(ms_dev)
+    total_bases = sum_over_ranks(float(sum(bases_per_step[i % len(resident)] for i in range(args.steps))))
+    value = total_bases / (ms_dev * 1e-3)
+
+    # ---- e2e: pinned host buffers through the C ABI, copies inside the timed region
+    for i in range(args.warmup):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_bases / e2e_s
+    h2d = int(np.mean([packed[i % len(packed)].h2d_bytes() for i in range(args.steps)]))
+
+    # ---- roofline of the counting kernel (K1): algorithmic bytes / its own device time
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    k1_avg_ms = float(np.mean([m for m, _ in k1_ms]))
+    k1_bytes = float(np.mean([alg_bytes[j] for _, j in k1_ms]))
+    achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9
+    k1_bases = float(np.mean([bases_per_step[j] for _, j in k1_ms]))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": label, "samples_per_gpu": len(ref_lens), "reads_per_step_per_gpu": packed[0].n_reads,
+                   "aligned_bases_per_step_per_gpu": bases_per_step[0], "ref_len": ref_lens[0],
+                   "l2": f"inputs {packed[0].h2d_bytes() / 1e6:.0f} MB per step > 126 MB L2; two resident batches alternate",
+                   "timing": "CUDA events on the engine's compute stream; max over ranks", "k1_variant": args.variant},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "timing": "host wall clock, device-synchronised both sides"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k1_count_tiled" if args.variant == 0 else "k1_count_per_base",
+                     "kernel_ms": k1_avg_ms, "algorithmic_bytes_per_launch": k1_bytes,
+                     "bytes_per_aligned_base": k1_bytes / k1_bases, "kernel_aligned_bases_per_s": k1_bases / (k1_avg_ms * 1e-3),
+                     "peak_source": peak_src},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "wall_s_timed_region": t_wall,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cfg2x12":
+        line["cpu_baseline"] = cpu_baseline(sets[0], ref_lens[0])
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for r in resident:
+        r.free()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

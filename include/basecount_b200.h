@@ -1,0 +1,179 @@
+/*
+ * basecount_b200.h -- C ABI of the B200-native pileup counting path.
+ *
+ * This is the drop-in boundary for the ONE native operator of tombch/basecount,
+ *     count.bcount(refLen, minBaseQuality, reads, qualities, starts, ctuples)
+ *     (reference: basecount/count.cpp:7-14, bound at count.cpp:102-105, called from
+ *      basecount/main.py:146-153 and main.py:179-186)
+ * plus the numeric work the reference does around it in Python:
+ *     int64 accumulation across chunks          main.py:132,155,188
+ *     per-position statistics (get_stats)       main.py:10-79
+ *     --summarise reductions                    main.py:479-485
+ *     --summarise-with-bed amplicon vectors     main.py:519-551
+ *
+ * Plain C: pointers and sizes only, no torch / pybind types.  Every function
+ * returns a bc_status (0 = OK).  The Python side (basecount_b200/_lib.py) loads
+ * libbasecount_b200.so with ctypes and maps the codes to the exceptions the
+ * reference raises (BC_ERR_INDEX -> IndexError as pybind11 does for the
+ * std::out_of_range thrown by .at() at count.cpp:60-64,85; BC_ERR_ARG -> TypeError).
+ *
+ * There is no CPU implementation behind this ABI: without a CUDA device every
+ * compute entry point fails with BC_ERR_CUDA.
+ */
+#ifndef BASECOUNT_B200_H
+#define BASECOUNT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bc_status {
+    BC_OK = 0,
+    BC_ERR_ARG = 1,        /* bad argument / malformed batch           -> TypeError  */
+    BC_ERR_INDEX = 2,      /* a counted event fell at refPos >= refLen -> IndexError */
+    BC_ERR_CUDA = 3,       /* CUDA runtime failure (message in bc_last_error)        */
+    BC_ERR_STATE = 4,      /* call out of order (no bc_begin, ...)                   */
+    BC_ERR_READ_OVERRUN = 5 /* CIGAR consumes more bases than the read holds (UB in the reference) */
+} bc_status;
+
+typedef struct bc_handle bc_handle;
+
+/*
+ * One batch of reads in structure-of-arrays form.  This replaces the four Python
+ * lists of count.cpp:10-13 (reads, qualities, starts, ctuples):
+ *
+ *   starts[i]      reference_start of read i, relative to ITS reference  (count.cpp:35)
+ *   cigar[...]     BAM-native words  len << 4 | op ; read i owns
+ *                  cigar[cigar_off[i] .. cigar_off[i+1])                  (count.cpp:40-46)
+ *   planes[...]    the query_alignment_sequence, 2 bits per base, bit-planar:
+ *                  base j of read i is bit (j & 31) of word
+ *                  planes[seq_woff[i] + (j >> 5)]; the low 32 bits of the 64-bit
+ *                  word hold bit 0 of the code, the high 32 bits hold bit 1
+ *                  (A=0 C=1 G=2 T=3; anything else is stored as 0 and listed in exc_*).
+ *                  Every read starts on a fresh 64-bit word; unused bits are 0.
+ *   okmask[...]    optional (NULL when min_base_quality == 0): one 32-bit word per
+ *                  planes word, bit set <=> quality >= minBaseQuality AND letter in ACGT
+ *                  (the test at count.cpp:56 evaluated by the packer).
+ *   exc_read/exc_pos  sparse list of bases the 2-bit code cannot express, sorted by
+ *                  (read, pos):  exc_pos = pos << 2 | flags,
+ *                  flag 1 = count column N (letter 'N' that passes the quality test, count.cpp:64),
+ *                  flag 2 = the main pass counted this base as 'A' and must be undone
+ *                           (only ever set when okmask == NULL).
+ *   ref_read_off   reads are grouped by reference slot: slot r owns reads
+ *                  [ref_read_off[r], ref_read_off[r+1]); n_refs+1 entries, matching bc_begin.
+ *
+ * Reads sorted by start within a slot are the fast case (coordinate-sorted BAM);
+ * any order is counted correctly.
+ */
+typedef struct bc_batch {
+    uint32_t n_reads;
+    uint32_t n_refs;
+    const uint32_t *ref_read_off;   /* n_refs + 1 */
+    const uint32_t *starts;         /* n_reads */
+    const uint32_t *cigar_off;      /* n_reads + 1 */
+    const uint32_t *cigar;          /* cigar_off[n_reads] */
+    const uint32_t *seq_woff;       /* n_reads + 1, in 64-bit words */
+    const uint64_t *planes;         /* seq_woff[n_reads] */
+    const uint32_t *okmask;         /* seq_woff[n_reads] or NULL */
+    uint32_t n_exc;
+    const uint32_t *exc_read;       /* n_exc */
+    const uint32_t *exc_pos;        /* n_exc */
+    uint32_t on_device;             /* 0: host pointers (copied by bc_push_batch); 1: device pointers */
+    uint32_t sorted_hint;           /* 1 if starts are non-decreasing within every slot */
+    uint32_t mean_read_len;         /* packer's estimate, picks the lane-group width; 0 = unknown */
+    uint32_t reserved;
+} bc_batch;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+int bc_create(int device, bc_handle **out);
+void bc_destroy(bc_handle *h);
+const char *bc_last_error(bc_handle *h);     /* h may be NULL: last create error */
+int bc_device_count(void);
+
+/* Pinned host memory for batches and results (cudaHostAlloc). */
+int bc_host_alloc(size_t bytes, void **out);
+void bc_host_free(void *p);
+
+/* ---- accumulators (replaces np.zeros((L,6)) at main.py:132) ----------------- */
+/* Allocate and zero one refLen x 6 accumulator per reference slot. */
+int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens);
+/* Zero the accumulators of the current slots again (asynchronous, compute stream). */
+int bc_reset(bc_handle *h);
+
+/* ---- the operator (replaces bcount + np.add, main.py:146-157 / 179-189) ----- */
+/* Asynchronous: H2D on the copy stream (host batches), counting kernels on the
+ * compute stream.  Host buffers must stay valid until bc_sync. */
+int bc_push_batch(bc_handle *h, const bc_batch *b);
+/* Wait for everything pushed so far; returns BC_ERR_INDEX / BC_ERR_READ_OVERRUN if any
+ * batch hit the reference's error conditions (accumulators are then unspecified). */
+int bc_sync(bc_handle *h);
+
+/* Keep a batch resident in HBM (bench: kernel-only timing).  dev receives device
+ * pointers and on_device = 1; release with bc_batch_free. */
+int bc_batch_upload(bc_handle *h, const bc_batch *host, bc_batch *dev);
+void bc_batch_free(bc_handle *h, bc_batch *dev);
+
+/* ---- results ---------------------------------------------------------------- */
+/* refLen x 6 int64, row-major, columns A,C,G,T,DS,N (count.cpp:16-17; int64 as main.py:132). */
+int bc_counts(bc_handle *h, uint32_t ref, int64_t *out);
+
+/* Per-position statistics (get_stats, main.py:14-53).  K = show_n ? 6 : 5.
+ * norm = 1/log2(K), norm2 = 1/log2(K-1) (main.py:24-25, computed by the caller so the
+ * constants are bit-identical to the reference's).
+ * Outputs (any may be NULL): coverage[L]; pc[K*L] (pc[k*L + pos]); entropy[L];
+ * secondary[L]; flags[L]: bit0 = coverage 0 (reference emits int -1 / 1 / 1, main.py:34-36),
+ * bit1 = secondary coverage 0 (secondary_entropy stays int 1, main.py:47).  The float arrays
+ * hold -1.0 / 1.0 / 1.0 at flagged positions. */
+int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
+             int64_t *coverage, double *pc, double *entropy, double *secondary, uint8_t *flags);
+
+/* --summarise reductions for ALL slots in one pass (main.py:479-485): per slot the
+ * number of positions with coverage != 0, the sum of coverage and the sum of entropy
+ * (entropy = 1 at zero coverage). */
+int bc_summary(bc_handle *h, int show_n, double norm, double norm2,
+               int64_t *nonzero, int64_t *cov_sum, double *entropy_sum);
+
+/* --summarise-with-bed amplicon vectors (main.py:519-551) for one slot.
+ * Window t covers 0-based positions lo[t]..hi[t] inclusive, clipped to the reference.
+ * out[6*n_tiles]: rows mean_cov, median_cov, mean_ent, median_ent, mean_sec, median_sec;
+ * empty[t] = 1 where the window holds no position (reference prints int -1). */
+int bc_amplicons(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
+                 uint32_t n_tiles, const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty);
+
+/* ---- region sharding (config 5): boundary-column halo exchange --------------- */
+/* Copy / add the u32 counts of columns [col_lo, col_lo + n_cols) of a slot, all six
+ * planes (6 * n_cols values, plane-major).  buf is a DEVICE pointer (e.g. a torch tensor
+ * handed to torch.distributed send/recv over NCCL). */
+int bc_halo_export(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, uint32_t *dev_buf);
+int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, const uint32_t *dev_buf);
+
+/* ---- host-side packer (replaces pybind11's list -> std::vector casters) -------- */
+/* Sizes needed for bc_pack_reads outputs, from the per-read base counts. */
+uint64_t bc_pack_words(uint32_t n_reads, const uint64_t *seq_off);
+/* ASCII bases + phred bytes -> planes / okmask / exception list.
+ * okmask_out may be NULL iff min_base_quality == 0.  exc arrays must hold exc_cap
+ * entries; *n_exc receives the number needed (call again with more room if > exc_cap).
+ * Also validates that no CIGAR consumes more bases than its read holds. */
+int bc_pack_reads(uint32_t n_reads, const uint8_t *seq, const uint8_t *qual, const uint64_t *seq_off,
+                  const uint32_t *cigar, const uint32_t *cigar_off, uint32_t min_base_quality,
+                  uint32_t *seq_woff_out, uint64_t *planes_out, uint32_t *okmask_out,
+                  uint32_t *exc_read_out, uint32_t *exc_pos_out, uint32_t exc_cap, uint32_t *n_exc);
+
+/* ---- instrumentation --------------------------------------------------------- */
+/* CUDA-event timing on the compute stream (bench.py: kernel-only figures). */
+int bc_timer_start(bc_handle *h);
+int bc_timer_stop(bc_handle *h, float *ms);
+/* Device time of the last counting-kernel launch alone (events around K1), and launches so far. */
+int bc_last_count_kernel_ms(bc_handle *h, float *ms);
+uint64_t bc_kernel_launches(bc_handle *h);
+/* Debug / cross-check: 0 = tiled bit-sliced kernel (default), 1 = one-thread-per-read
+ * per-base atomics.  Both are CUDA; there is no host path. */
+int bc_set_count_variant(bc_handle *h, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASECOUNT_B200_H */

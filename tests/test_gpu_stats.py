@@ -1,0 +1,125 @@
+"""Parity of K2 (per-position statistics) and K3 (summary, amplicon vectors) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from basecount_b200 import synth
+from basecount_b200.records import ReadBatch, select_reads
+
+pytestmark = pytest.mark.gpu
+REL = 1e-6          # BASELINE.json north_star: pc_* and entropy within 1e-6 relative before rounding
+TIGHT = 1e-12       # what we actually hold (only log2's last ulp differs)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from basecount_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def load_counts(eng, counts):
+    """Put an arbitrary count matrix on the device by pushing synthetic single-base reads."""
+    from basecount_b200.pack import pack_batches
+    counts = np.asarray(counts, dtype=np.int64)
+    L = counts.shape[0]
+    reads, quals, starts, ctuples = [], [], [], []
+    letters = "ACGT?N"
+    for pos in range(L):
+        for col in range(6):
+            k = int(counts[pos, col])
+            if k == 0:
+                continue
+            if col == 4:
+                reads += [""] * k
+                quals += [[]] * k
+                starts += [pos] * k
+                ctuples += [[(2, 1)]] * k
+            else:
+                reads += [letters[col]] * k
+                quals += [[30]] * k
+                starts += [pos] * k
+                ctuples += [[(0, 1)]] * k
+    eng.begin([L])
+    eng.push(pack_batches(ReadBatch.from_lists(reads, quals, starts, ctuples), 0))
+    eng.sync()
+    assert np.array_equal(eng.counts(0), counts)
+
+
+def small_golden_counts():
+    g = load_golden("stats.json.gz")
+    return [c for c in g["counts"] if sum(c) < 5000]
+
+
+@pytest.mark.parametrize("show_n", [False, True])
+def test_stats_vs_oracle(eng, show_n):
+    from oracle import stats as ost
+    counts = small_golden_counts()
+    load_counts(eng, counts)
+    s = eng.stats(0, show_n)
+    k = 6 if show_n else 5
+    for pos, row in enumerate(counts):
+        cov, c, pcs, ent, sec = ost.position_stats(row, show_n)
+        assert int(s["coverage"][pos]) == cov
+        f = int(s["flags"][pos])
+        assert bool(f & 1) == (cov == 0)
+        assert bool(f & 2) == isinstance(sec, int)
+        for i in range(k):
+            assert s["pc"][i, pos] == float(pcs[i])                 # divisions are IEEE-exact: bit-identical
+        assert s["entropy"][pos] == pytest.approx(float(ent), rel=TIGHT, abs=1e-300)
+        assert s["secondary"][pos] == pytest.approx(float(sec), rel=TIGHT, abs=1e-300)
+        assert abs(s["entropy"][pos] - float(ent)) <= REL * abs(float(ent))
+
+
+def test_summary_and_amplicons_vs_oracle(eng, tmp_path):
+    from basecount_b200.pack import pack_batches
+    from oracle import bcount as obc
+    from oracle import stats as ost
+    rec = synth.amplicon_sample(seed=21, n_reads=900, ref_len=3000, ref_name="toy")
+    b = select_reads(rec, 0, 0)
+    counts = obc.bcount_flat(3000, 0, b).astype(np.int64).tolist()
+    eng.begin([3000])
+    eng.push(pack_batches(b, 0))
+    eng.sync()
+    for show_n in (False, True):
+        cov, ent, sec = ost.per_position_vectors(counts, show_n)
+        nz, cs, es = eng.summary(show_n)
+        assert int(nz[0]) == sum(1 for x in cov if x != 0)
+        assert int(cs[0]) == sum(cov)
+        assert float(es[0]) == pytest.approx(float(np.sum(ent)), rel=TIGHT)
+        windows = [(-5, 10), (0, 0), (100, 99), (2990, 5000), (3000, 3100), (50, 449), (300, 700), (0, 2999), (17, 18)]
+        want = ost.amplicon_vectors(cov, ent, sec, windows)
+        got, empty = eng.amplicons(0, [w[0] for w in windows], [w[1] for w in windows], show_n)
+        for t, (lo, hi) in enumerate(windows):
+            is_empty = isinstance(want[0][t], int)
+            assert bool(empty[t]) == is_empty, (lo, hi)
+            for k in range(6):
+                if is_empty:
+                    assert got[k, t] == -1.0
+                elif k < 2:
+                    assert got[k, t] == float(want[k][t])          # coverage mean / median: exact
+                else:
+                    assert got[k, t] == pytest.approx(float(want[k][t]), rel=TIGHT, abs=1e-300)
+
+
+def test_amplicon_window_larger_than_staging(eng):
+    from basecount_b200.pack import pack_batches
+    from oracle import bcount as obc
+    from oracle import stats as ost
+    rec = synth.uniform_short_read_sample(seed=8, ref_len=12000, n_reads=3000, read_len=150, ref_name="x")
+    b = select_reads(rec, 0, 0)
+    counts = obc.bcount_flat(12000, 0, b).astype(np.int64).tolist()
+    eng.begin([12000])
+    eng.push(pack_batches(b, 0))
+    eng.sync()
+    cov, ent, sec = ost.per_position_vectors(counts)
+    windows = [(0, 11999), (100, 9000), (5, 4100), (0, 4095)]
+    want = ost.amplicon_vectors(cov, ent, sec, windows)
+    got, _ = eng.amplicons(0, [w[0] for w in windows], [w[1] for w in windows])
+    for t in range(len(windows)):
+        for k in range(6):
+            if k in (1, 3, 5):
+                assert got[k, t] == float(want[k][t])               # medians are exact selections
+            else:
+                assert got[k, t] == pytest.approx(float(want[k][t]), rel=TIGHT)
