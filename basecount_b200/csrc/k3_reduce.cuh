@@ -19,26 +19,69 @@ constexpr int kK3Threads = 256;
 // < 8 elements: running sum from -0.0; <= 128: eight strided accumulators combined as
 // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) then the tail; otherwise split at n/2 rounded down
 // to a multiple of 8.  np.mean over a list is np.add.reduce over the float64 array / n.
-__device__ double np_pairwise(const double *a, uint32_t n)
+__device__ __forceinline__ double np_pairwise_leaf(const double *a, uint32_t n)   // n <= 128
 {
     if (n < 8) {
         double r = -0.0;
         for (uint32_t i = 0; i < n; i++) r += a[i];
         return r;
     }
-    if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; j++) r[j] = a[j];
-        uint32_t i = 8;
-        for (; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; j++) r[j] += a[i + j];
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; i++) res += a[i];
-        return res;
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    uint32_t i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
     }
-    uint32_t n2 = n / 2;
-    n2 -= n2 % 8;
-    return np_pairwise(a, n2) + np_pairwise(a + n2, n - n2);
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+// The recursion "sum(a, n) = sum(a, n2) + sum(a + n2, n - n2)" unrolled onto an explicit
+// stack (device recursion would need a run-time stack size).  Depth <= log2(n / 64) < 32.
+__device__ double np_pairwise(const double *a, uint32_t n)
+{
+    uint32_t off_s[32], n_s[32];
+    double left_s[32];
+    uint8_t state_s[32];                    // 0: fresh, 1: left child pending, 2: right child pending
+    int sp = 0;
+    off_s[0] = 0;
+    n_s[0] = n;
+    state_s[0] = 0;
+    double ret = 0.0;
+    for (;;) {
+        const uint32_t off = off_s[sp], m = n_s[sp];
+        if (state_s[sp] == 0) {
+            if (m <= 128) {
+                ret = np_pairwise_leaf(a + off, m);
+                if (sp == 0) return ret;
+                sp--;
+                continue;
+            }
+            uint32_t n2 = m / 2;
+            n2 -= n2 % 8;
+            state_s[sp] = 1;
+            sp++;
+            off_s[sp] = off;
+            n_s[sp] = n2;
+            state_s[sp] = 0;
+        } else if (state_s[sp] == 1) {
+            left_s[sp] = ret;
+            uint32_t n2 = m / 2;
+            n2 -= n2 % 8;
+            state_s[sp] = 2;
+            sp++;
+            off_s[sp] = off + n2;
+            n_s[sp] = m - n2;
+            state_s[sp] = 0;
+        } else {
+            ret = left_s[sp] + ret;
+            if (sp == 0) return ret;
+            sp--;
+        }
+    }
 }
 
 __device__ __forceinline__ double window_value(int metric, const long long *cov, const double *ent,

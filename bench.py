@@ -59,9 +59,26 @@ def parse():
 
 # ----------------------------------------------------------------------------- workloads
 def make_samples(seeds, n_reads):
+    """Synthetic config-1/2 samples, filtered and trimmed as get_basecounts would (cached in /tmp
+    so repeated invocations on one box, e.g. plain run then ncu, do not regenerate)."""
     from basecount_b200 import synth
-    from basecount_b200.records import select_reads
-    return [select_reads(synth.amplicon_sample(seed=s, n_reads=n_reads), 0, 0) for s in seeds]
+    from basecount_b200.records import ReadBatch, select_reads
+    out = []
+    for s in seeds:
+        path = f"/tmp/bc_bench_sample_{s}_{n_reads}.npz"
+        if os.path.exists(path):
+            z = np.load(path)
+            out.append(ReadBatch(z["starts"], z["cigar"], z["cigar_off"], z["seq"], z["qual"], z["seq_off"]))
+            continue
+        b = select_reads(synth.amplicon_sample(seed=s, n_reads=n_reads), 0, 0)
+        try:
+            np.savez(path + ".tmp.npz", starts=b.starts, cigar=b.cigar, cigar_off=b.cigar_off, seq=b.seq, qual=b.qual,
+                     seq_off=b.seq_off)
+            os.replace(path + ".tmp.npz", path)
+        except OSError:
+            pass
+        out.append(b)
+    return out
 
 
 def build_workload(args, rank):
