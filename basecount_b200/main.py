@@ -1,0 +1,371 @@
+"""Host side of the pileup counting path: the reference's Python API and CLI over the GPU engine.
+
+Mirrors the public surface of basecount/main.py -- get_basecounts (main.py:110-205),
+class BaseCount (main.py:208-359), handle_arg / run (main.py:362-595) -- with the same
+argument names, defaults, column names, row layout, error messages and printed text.
+What differs is underneath: alignments are decoded in bulk into flat arrays, packed to
+2-bit SoA batches in native code, counted by K1 on the GPU, and the statistics /
+summary / amplicon numbers come from K2 / K3 instead of per-position Python loops.
+
+Deliberate, documented divergences (DESIGN.md section "Reference quirks"):
+  * references are reported in BAM-header order, not Python set order (main.py:92);
+  * with --references, reads on other contigs are skipped (the reference raises KeyError
+    at main.py:166; its own tests' copy of the pipeline guards this, tests/test_basecount.py:300).
+"""
+from __future__ import annotations
+
+import argparse
+
+import numpy as np
+
+from .engine import Engine
+from .pack import pack_batches
+from .records import FLAG_UNMAPPED, ReadBatch, Records, select_reads
+from .scheme import load_scheme
+from .version import __version__
+
+BASES = ("A", "C", "G", "T", "DS", "N")          # column order of the count matrix (count.cpp:16-17, main.py:16)
+
+_ENGINE = None
+
+
+def _engine() -> Engine:
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine(0)
+    return _ENGINE
+
+
+# ----------------------------------------------------------------------------- alignment input
+def _records_via_pysam(bam):
+    """If a real pysam is installed, read through it exactly as the reference does
+    (main.py:95-100,127) and convert to flat Records.  Returns None when pysam is absent."""
+    try:
+        import pysam
+    except ImportError:
+        return None
+    old = pysam.set_verbosity(0)
+    f = pysam.AlignmentFile(bam, mode="rb")
+    pysam.set_verbosity(old)
+    names, lengths = list(f.references), list(f.lengths)
+    idx = {n: i for i, n in enumerate(names)}
+    ref_id, pos, mapq, flag, cig, coff, seqs, quals, soff = [], [], [], [], [], [0], [], [], [0]
+    for r in f.fetch(until_eof=True):
+        ref_id.append(idx.get(r.reference_name, -1))
+        pos.append(r.reference_start)
+        mapq.append(r.mapping_quality)
+        flag.append(r.flag)
+        s, q = r.query_sequence, r.query_qualities
+        if s is None or q is None:
+            if not (r.flag & FLAG_UNMAPPED):
+                raise TypeError("read without SEQ or QUAL")        # the reference passes None to bcount -> TypeError
+            s, q = "", []
+        for op, ln in (r.cigartuples or []):
+            cig.append((ln << 4) | op)
+        coff.append(len(cig))
+        seqs.append(s)
+        quals.append(np.asarray(q, dtype=np.uint8))
+        soff.append(soff[-1] + len(s))
+    f.close()
+    return Records(names, lengths, np.asarray(ref_id, np.int32), np.asarray(pos, np.int32), np.asarray(mapq, np.uint8),
+                   np.asarray(flag, np.uint16), np.asarray(cig, np.uint32), np.asarray(coff, np.int64),
+                   np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8),
+                   np.concatenate(quals) if quals else np.zeros(0, np.uint8), np.asarray(soff, np.int64))
+
+
+def load_records(bam) -> Records:
+    if isinstance(bam, Records):
+        return bam
+    rec = _records_via_pysam(bam)
+    if rec is None:
+        from . import bamio
+        rec = bamio.read_bam(bam)
+    return rec
+
+
+def _slice_records(rec: Records, a: int, b: int) -> Records:
+    c0, c1 = int(rec.cigar_off[a]), int(rec.cigar_off[b])
+    s0, s1 = int(rec.seq_off[a]), int(rec.seq_off[b])
+    return Records(rec.ref_names, rec.ref_lengths, rec.ref_id[a:b], rec.pos[a:b], rec.mapq[a:b], rec.flag[a:b],
+                   rec.cigar[c0:c1], rec.cigar_off[a:b + 1] - c0, rec.seq[s0:s1], rec.qual[s0:s1],
+                   rec.seq_off[a:b + 1] - s0)
+
+
+def get_references(all_references, references=None):
+    """Validate the requested references (main.py:82-92); BAM-header order is kept."""
+    if references is None:
+        return list(all_references)
+    for reference in references:
+        if not (reference in all_references):
+            raise Exception(f"{reference} is not a valid reference")
+    wanted = set(references)
+    return [r for r in all_references if r in wanted]
+
+
+# ----------------------------------------------------------------------------- counting
+class Pileup:
+    """Counts of one BAM held on the device, plus lazily fetched statistics."""
+
+    def __init__(self, engine, references, lengths, num_reads, show_n_bases):
+        self.engine = engine
+        self.references = references
+        self.lengths = lengths
+        self.num_reads = num_reads
+        self.show_n_bases = show_n_bases
+        self._stats = {}
+        self._counts = {}
+
+    def counts(self, i):
+        if i not in self._counts:
+            self._counts[i] = self.engine.counts(i)
+        return self._counts[i]
+
+    def stats(self, i):
+        if i not in self._stats:
+            self._stats[i] = self.engine.stats(i, self.show_n_bases)
+        return self._stats[i]
+
+
+def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quality=0, chunk_size=1000000,
+                     show_n_bases=False, engine=None) -> Pileup:
+    """BAM -> device count matrices (the numeric part of get_basecounts, main.py:119-189)."""
+    rec = load_records(bam)
+    refs = get_references(rec.ref_names, references)
+    ids = [rec.ref_names.index(r) for r in refs]
+    lengths = [int(rec.ref_lengths[i]) for i in ids]
+    eng = engine or _engine()
+    num_reads = [0] * len(refs)
+    if refs:
+        eng.begin(lengths)
+        # The reference flushes every `chunk_size` kept reads (main.py:142); the counts do not
+        # depend on where the chunks fall, so chunking here only bounds the packed buffers.
+        keep = ((rec.flag & FLAG_UNMAPPED) == 0) & (rec.mapq >= min_mapping_quality) & np.isin(rec.ref_id, ids)
+        csum = np.cumsum(keep)
+        total = int(csum[-1]) if csum.size else 0
+        chunk_size = max(int(chunk_size), 1)
+        cuts = [0]
+        for k in range(chunk_size, total, chunk_size):
+            cuts.append(int(np.searchsorted(csum, k, side="left")) + 1)
+        cuts.append(rec.n)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b <= a:
+                continue
+            part = _slice_records(rec, a, b) if (a, b) != (0, rec.n) else rec
+            batches = [select_reads(part, rid, min_mapping_quality) for rid in ids]
+            for j, bt in enumerate(batches):
+                num_reads[j] += bt.n
+            eng.push(pack_batches(batches, min_base_quality))
+            eng.sync()
+    return Pileup(eng, refs, lengths, num_reads, show_n_bases)
+
+
+def build_rows(ref, counts, st, show_n_bases=False, long_format=False):
+    """Row lists with the reference's cell types (main.py:55-78): ints for counts and for the
+    zero-coverage sentinels (-1 / 1 / 1), Python floats elsewhere."""
+    k = 6 if show_n_bases else 5
+    L = counts.shape[0]
+    cnt = counts[:, :k].tolist()
+    cov = st["coverage"].tolist()
+    pcs = st["pc"].T.tolist()
+    ent = st["entropy"].tolist()
+    sec = st["secondary"].tolist()
+    flags = st["flags"].tolist()
+    minus = [-1] * k
+    rows = []
+    names = BASES[:k]
+    for i in range(L):
+        f = flags[i]
+        p = minus if f & 1 else pcs[i]
+        e = 1 if f & 1 else ent[i]
+        s = 1 if f & 2 else sec[i]
+        if long_format:
+            c = cnt[i]
+            for j in range(k):
+                rows.append([ref, i + 1, cov[i], names[j], c[j], p[j], e, s])
+        else:
+            rows.append([ref, i + 1, cov[i], *cnt[i], *p, e, s])
+    return rows
+
+
+def get_basecounts(bam, references=None, min_base_quality=0, min_mapping_quality=0, chunk_size=1000000,
+                   show_n_bases=False, long_format=False):
+    """Same contract as the reference: {ref: {"rows": [...], "num_reads": int}} (main.py:192-205)."""
+    pile = count_alignments(bam, references, min_base_quality, min_mapping_quality, chunk_size, show_n_bases)
+    out = {}
+    for i, ref in enumerate(pile.references):
+        out[ref] = {"rows": build_rows(ref, pile.counts(i), pile.stats(i), show_n_bases, long_format),
+                    "num_reads": pile.num_reads[i]}
+    return out
+
+
+def column_names(show_n_bases=False, long_format=False):
+    if long_format:
+        return ["reference", "position", "coverage", "base", "count", "percentage", "entropy", "secondary_entropy"]
+    letters = ["a", "c", "g", "t", "ds"] + (["n"] if show_n_bases else [])
+    return (["reference", "position", "coverage"] + ["num_" + x for x in letters] + ["pc_" + x for x in letters] +
+            ["entropy", "secondary_entropy"])
+
+
+class BaseCount:
+    def __init__(self, bam, references=None, min_base_quality=0, min_mapping_quality=0, chunk_size=1000000,
+                 show_n_bases=False, long_format=False):
+        """
+        Generate and store basecount data.
+
+        * `bam`: path to a BAM file (no index needed).
+        * `references`: names of the references to count; `None` = every reference.
+        * `min_base_quality` / `min_mapping_quality`: inclusion thresholds. Default `0`.
+        * `chunk_size`: max reads packed and sent to the GPU at a time. Default `1000000`.
+        * `show_n_bases`: report `N` counts and include them in the statistics.
+        * `long_format`: one row per (position, base) instead of one row per position.
+        """
+        self.columns = column_names(show_n_bases, long_format)
+        self._show_n, self._long = show_n_bases, long_format
+        self._pile = count_alignments(bam, references, min_base_quality, min_mapping_quality, chunk_size, show_n_bases)
+        self.references = list(self._pile.references)
+        self.reference_lengths = dict(zip(self.references, self._pile.lengths))
+        self._data = None
+
+    @property
+    def data(self):
+        """{ref: {"rows": [...], "num_reads": int}}; rows are materialised on first use."""
+        if self._data is None:
+            p = self._pile
+            self._data = {ref: {"rows": build_rows(ref, p.counts(i), p.stats(i), self._show_n, self._long),
+                                "num_reads": p.num_reads[i]} for i, ref in enumerate(self.references)}
+        return self._data
+
+    def _index(self, reference):
+        if reference not in self.reference_lengths:
+            raise Exception(f"{reference} is not a valid reference")
+        return self.references.index(reference)
+
+    def rows(self, reference=None):
+        """Iterator of row lists; restricted to `reference` if given."""
+        if reference is not None:
+            self._index(reference)
+        for ref in ([reference] if reference is not None else self.references):
+            yield from self.data[ref]["rows"]
+
+    def records(self, reference=None):
+        """Iterator of dicts keyed by column name; restricted to `reference` if given."""
+        for row in self.rows(reference):
+            yield dict(zip(self.columns, row))
+
+    def num_reads(self, reference=None):
+        """Total reads counted, over all references or for one."""
+        if reference is None:
+            return sum(self._pile.num_reads)
+        return self._pile.num_reads[self._index(reference)]
+
+    def _vectors(self, reference):
+        which = range(len(self.references)) if reference is None else [self._index(reference)]
+        rep = len(BASES[:6 if self._show_n else 5]) if self._long else 1       # long format repeats each position
+        cov = [np.repeat(self._pile.stats(i)["coverage"], rep) for i in which]
+        ent = [np.repeat(self._pile.stats(i)["entropy"], rep) for i in which]
+        return (np.concatenate(cov) if cov else np.zeros(0, np.int64),
+                np.concatenate(ent) if ent else np.zeros(0, np.float64))
+
+    def mean_coverage(self, reference=None):
+        """Mean coverage over all positions (np.mean of the coverage column, main.py:325-340)."""
+        cov, _ = self._vectors(reference)
+        return np.mean(cov)
+
+    def mean_entropy(self, reference=None, min_coverage=0):
+        """Mean entropy over positions with coverage >= min_coverage (main.py:342-359)."""
+        cov, ent = self._vectors(reference)
+        return np.mean(ent[cov >= min_coverage])
+
+    # -- device-side reductions used by the CLI's summarise modes
+    def summary(self, reference):
+        """(pc_reference_coverage, avg_depth, avg_entropy) from K3 (main.py:479-485)."""
+        i = self._index(reference)
+        if not hasattr(self, "_summary"):
+            self._summary = self._pile.engine.summary(self._show_n)
+        nz, cs, es = self._summary
+        L = self.reference_lengths[reference]
+        return 100 * (int(nz[i]) / L), np.float64(int(cs[i])) / L, np.float64(es[i]) / L
+
+    def amplicon_vectors(self, reference, scheme):
+        """The six per-amplicon vectors in print order (main.py:506-551); ints -1 for empty windows."""
+        i = self._index(reference)
+        lo = [t[2]["inside_start"] for t in scheme]
+        hi = [t[2]["inside_end"] for t in scheme]
+        if not scheme:
+            return [[] for _ in range(6)]
+        out, empty = self._pile.engine.amplicons(i, lo, hi, self._show_n)
+        return [[-1 if empty[t] else np.float64(out[k, t]) for t in range(len(scheme))] for k in range(6)]
+
+
+def handle_arg(arg, name, default=None, provided_once=False):
+    """`action="append"` values -> one value (must be given once) or the union of lists (main.py:362-375)."""
+    if arg is None:
+        return default
+    if provided_once:
+        if len(arg) > 1:
+            raise Exception(f"Argument --{name} can only be provided once")
+        return arg[0]
+    return list({a for a_list in arg for a in a_list})
+
+
+AMPLICON_VECTOR_NAMES = ("mean_coverage_amplicon_vector", "median_coverage_amplicon_vector",
+                         "mean_entropy_amplicon_vector", "median_entropy_amplicon_vector",
+                         "mean_secondary_entropy_amplicon_vector", "median_secondary_entropy_amplicon_vector")
+
+
+def run(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("bam", help="Path to BAM file (an index file is not required)")
+    parser.add_argument("-v", "--version", action="version", version=__version__)
+    parser.add_argument("--references", default=None, nargs="+", action="append",
+                        help="Choose specific reference(s) to run basecount on")
+    parser.add_argument("--min-base-quality", default=None, action="append", help="Default value: 0")
+    parser.add_argument("--min-mapping-quality", default=None, action="append", help="Default value: 0")
+    parser.add_argument("--chunk-size", default=None, action="append",
+                        help="Max number of reads loaded into memory and basecounted at a given time. Default value: 1000000")
+    parser.add_argument("--show-n-bases", default=False, action="store_true",
+                        help="Show counts of 'N' bases from reads, and include them in statistics")
+    group = parser.add_mutually_exclusive_group()
+    group.add_argument("--long-format", default=False, action="store_true",
+                       help="Output per-position statistics in long format, instead of the default wide format")
+    group.add_argument("--summarise", default=False, action="store_true", help="Output summary statistics")
+    group.add_argument("--summarise-with-bed", default=None, action="append", metavar="BED_FILE",
+                       help="Output summary statistics and amplicon vectors (calculated using the provided BED file)")
+    parser.add_argument("--decimal-places", default=None, action="append", help="Default value: 3")
+    args = parser.parse_args(argv)
+
+    references = handle_arg(args.references, "references")
+    min_base_quality = int(handle_arg(args.min_base_quality, "min-base-quality", default=0, provided_once=True))
+    min_mapping_quality = int(handle_arg(args.min_mapping_quality, "min-mapping-quality", default=0, provided_once=True))
+    chunk_size = int(handle_arg(args.chunk_size, "chunk-size", default=1000000, provided_once=True))
+    bed = handle_arg(args.summarise_with_bed, "bed", provided_once=True)
+    decimal_places = int(handle_arg(args.decimal_places, "decimal_places", default=3, provided_once=True))
+
+    bc = BaseCount(args.bam, references=references, min_base_quality=min_base_quality,
+                   min_mapping_quality=min_mapping_quality, chunk_size=chunk_size, show_n_bases=args.show_n_bases,
+                   long_format=args.long_format)
+
+    if (not args.summarise) and (bed is None):
+        out = ["\t".join(bc.columns)]
+        for row in bc.rows():
+            out.append("\t".join([x if isinstance(x, str) else str(round(x, decimal_places)) for x in row]))
+        print("\n".join(out))
+        return
+
+    for ref in bc.references:
+        pc_ref_coverage, avg_coverage, avg_entropy = bc.summary(ref)
+        summary_stats = {
+            "reference_name": ref,
+            "reference_length": round(bc.reference_lengths[ref], decimal_places),
+            "num_reads": round(bc.num_reads(ref), decimal_places),
+            "pc_reference_coverage": round(pc_ref_coverage, decimal_places),
+            "avg_depth": round(avg_coverage, decimal_places),
+            "avg_entropy": round(avg_entropy, decimal_places),
+        }
+        for name, val in summary_stats.items():
+            print(name, val, sep="\t")
+        if bed is not None:
+            scheme = load_scheme(bed)
+            vectors = bc.amplicon_vectors(ref, scheme)
+            for name, vec in zip(AMPLICON_VECTOR_NAMES, vectors):
+                print(name, ", ".join([str(round(x, decimal_places)) for x in vec]) if vec else "-", sep="\t")
