@@ -41,6 +41,7 @@ struct Resident {                // a batch kept in HBM by bc_batch_upload
     BatchView view;
     uint32_t n_chunks = 0;
     int G = 32;
+    uint32_t mean_words = 1;
     bool live = false;
 };
 
@@ -321,7 +322,8 @@ static int validate_batch(bc_handle *h, const bc_batch *b)
 }
 
 // Launch K1 (+ corrections, + exact overflow check) for a batch whose arrays are in HBM.
-static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks, uint32_t n_chunks, int G)
+static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks, uint32_t n_chunks, int G,
+                        uint32_t mean_words)
 {
     if (v.n_reads == 0) return BC_OK;
     // uint32 counters cannot wrap while fewer than 2^32 reads went in since the last fold
@@ -349,12 +351,21 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
         k1_count_per_base<<<(v.n_reads + 127) / 128, 128, 0, h->compute>>>(v, cv);
     } else {
         const unsigned grid = (n_chunks + kK1WarpsPerCta - 1) / kK1WarpsPerCta;
-        const size_t smem = (size_t)kK1WarpsPerCta * 32 * G * sizeof(uint32_t);
         const bool ok = v.okmask != nullptr;
-#define K1_LAUNCH(GG)                                                                               \
-    do {                                                                                            \
-        if (ok) k1_count_tiled<GG, true><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks); \
-        else k1_count_tiled<GG, false><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks);   \
+        // reads per staging block: a block's plane words must fit one pipeline stage
+        const uint32_t words_per_read = std::max<uint32_t>(1, mean_words);
+        const uint32_t rpb = std::max<uint32_t>(2, std::min<uint32_t>(32, (kSeqCap * 9 / 10) / words_per_read));
+#define K1_LAUNCH(GG)                                                                                          \
+    do {                                                                                                       \
+        if (ok) {                                                                                              \
+            const size_t smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<GG, true>();                       \
+            CU(h, cudaFuncSetAttribute(k1_count_tiled<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k1_count_tiled<GG, true><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb);  \
+        } else {                                                                                               \
+            const size_t smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<GG, false>();                      \
+            CU(h, cudaFuncSetAttribute(k1_count_tiled<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k1_count_tiled<GG, false><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb); \
+        }                                                                                                      \
     } while (0)
         if (G == 8) K1_LAUNCH(8);
         else if (G == 16) K1_LAUNCH(16);
@@ -384,7 +395,8 @@ static int stage_copy(bc_handle *h, DevBuf &dst, const void *src, size_t bytes, 
 }
 
 // Copy a host batch into `st` on the copy stream and fill `view` / chunk table.
-static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &view, uint32_t &n_chunks, int &G)
+static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &view, uint32_t &n_chunks, int &G,
+                       uint32_t &mean_words)
 {
     const uint32_t n = b->n_reads;
     view = BatchView();
@@ -393,6 +405,7 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
     view.n_exc = b->n_exc;
     n_chunks = 0;
     G = 32;
+    mean_words = 1;
     if (n == 0) return BC_OK;
     if (b->ref_read_off[0] != 0 || b->ref_read_off[b->n_refs] != n)
         return fail(h, BC_ERR_ARG, "ref_read_off must start at 0 and end at n_reads");
@@ -403,6 +416,7 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
     if (n_cigar && !b->cigar) return fail(h, BC_ERR_ARG, "batch is missing cigar words");
     if (n_words && !b->planes) return fail(h, BC_ERR_ARG, "batch is missing sequence planes");
     G = pick_group_width(b, n_words);
+    mean_words = (uint32_t)((n_words + n - 1) / n);
 
     std::vector<Chunk> chunks;
     n_chunks = build_chunks(h, b->ref_read_off, n, chunks);
@@ -455,7 +469,7 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
         if (id == 0 || id > h->resident.size() || !h->resident[id - 1] || !h->resident[id - 1]->live)
             return fail(h, BC_ERR_ARG, "on_device batch was not created by bc_batch_upload on this handle");
         Resident *r = h->resident[id - 1];
-        return launch_count(h, r->view, (const Chunk *)r->st.chunks.p, r->n_chunks, r->G);
+        return launch_count(h, r->view, (const Chunk *)r->st.chunks.p, r->n_chunks, r->G, r->mean_words);
     }
     Staging &st = h->stage[h->pushes & 1];
     h->pushes++;
@@ -464,12 +478,12 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
         CU(h, cudaEventSynchronize(st.done));
     }
     BatchView view;
-    uint32_t n_chunks;
+    uint32_t n_chunks, mean_words;
     int G;
-    if ((rc = stage_batch(h, st, b, view, n_chunks, G))) return rc;
+    if ((rc = stage_batch(h, st, b, view, n_chunks, G, mean_words))) return rc;
     CU(h, cudaEventRecord(st.copied, h->copy));
     CU(h, cudaStreamWaitEvent(h->compute, st.copied, 0));
-    rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G);
+    rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G, mean_words);
     CU(h, cudaEventRecord(st.done, h->compute));
     st.used = true;
     return rc;
@@ -501,7 +515,7 @@ int bc_batch_upload(bc_handle *h, const bc_batch *host, bc_batch *dev)
     if (host->on_device) return fail(h, BC_ERR_ARG, "bc_batch_upload expects host pointers");
     CU(h, cudaSetDevice(h->device));
     Resident *r = new Resident();
-    rc = stage_batch(h, r->st, host, r->view, r->n_chunks, r->G);
+    rc = stage_batch(h, r->st, host, r->view, r->n_chunks, r->G, r->mean_words);
     if (rc == BC_OK && cudaStreamSynchronize(h->copy) != cudaSuccess) rc = fail(h, BC_ERR_CUDA, "upload failed");
     if (rc) {
         release_staging(r->st);

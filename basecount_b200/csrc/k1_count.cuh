@@ -150,140 +150,290 @@ __device__ __forceinline__ void flush_counters(VCounters &vc, uint32_t cnt, uint
     vc.clear();
 }
 
+// ---- TMA (1-D bulk async copy) + mbarrier helpers -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Staging capacities per warp and per pipeline stage.
+constexpr uint32_t kSeqCap = 512;     // 64-bit plane words  (4 KB)   -- 32 reads x 400 bp = 416 words
+constexpr uint32_t kCigCap = 256;     // CIGAR words         (1 KB)
+constexpr int kStages = 2;
+
 template <int G, bool HAS_OK>
-__global__ void __launch_bounds__(kK1Threads)
-k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks)
+__host__ __device__ constexpr uint32_t k1_warp_smem_bytes()
+{
+    return kStages * kSeqCap * 8u + (HAS_OK ? kStages * kSeqCap * 4u : 0u) + kStages * kCigCap * 4u + 128u * G + 128u;
+}
+
+struct BlockMeta {            // lane l holds the metadata of read (block_first + l)
+    uint32_t start, cbase, ncig, wbase, nwords;
+};
+struct StagedRange {          // what one pipeline stage holds (warp-uniform)
+    uint32_t s_lo, s_n;       // plane / okmask words [s_lo, s_lo + s_n)
+    uint32_t c_lo, c_n;       // CIGAR words        [c_lo, c_lo + c_n)
+};
+
+// The counting kernel.  One warp = one chunk of consecutive reads, processed in blocks of
+// `rpb` <= 32 reads: the block's metadata sits in registers (one read per lane, handed to the
+// read slots by shuffle), its sequence / CIGAR words are staged in shared memory by TMA bulk
+// copies two blocks ahead, so the inner loop touches only registers and shared memory.
+template <int G, bool HAS_OK>
+__global__ void __launch_bounds__(kK1Threads, 2)
+k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb)
 {
     constexpr int S = 32 / G;
     constexpr uint32_t kCntMax = 255u / S;          // byte-packed slot sums must stay <= 255
     constexpr uint32_t kWin = 32u * G;              // window columns
     constexpr uint32_t kMaxFit = kWin - 31u;        // a piece this long fits a fresh window at any alignment
-    extern __shared__ uint32_t k1_smem[];
+    extern __shared__ __align__(128) unsigned char k1_smem[];
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
     const uint32_t warp_id = blockIdx.x * kK1WarpsPerCta + warp_in_cta;
-    if (warp_id >= n_chunks) return;
-    uint32_t *fbuf = k1_smem + warp_in_cta * (32 * G);
+    if (warp_id >= n_chunks) return;                // warps are independent: no CTA-wide barrier anywhere
+
+    unsigned char *wsm = k1_smem + (size_t)warp_in_cta * k1_warp_smem_bytes<G, HAS_OK>();
+    uint2 *seq_buf = reinterpret_cast<uint2 *>(wsm);
+    uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kSeqCap * 8u);
+    uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kSeqCap * 8u + (HAS_OK ? kStages * kSeqCap * 4u : 0u));
+    uint32_t *fbuf = cig_buf + kStages * kCigCap;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(fbuf) + 128u * G);
+
     const int slot = lane / G, wl = lane % G;
     const uint32_t slot_lead_below = (slot == 0) ? 0u : ((1u << (slot * G)) - 1u);
 
     const Chunk ch = chunks[warp_id];
     const uint32_t ref_len = ch.ref_len;
-    uint32_t cursor = ch.read_begin;
+    const uint32_t rb = ch.read_begin, re = ch.read_end;
+    const uint32_t nblk = (re - rb + rpb - 1) / rpb;
 
-    // per read-slot state (replicated over the slot's G lanes)
-    uint32_t cur = 0, cend = 0, ref_pos = 0, read_pos = 0, wbase = 0, nwords = 0;
-    bool exhausted = false;
-    uint32_t pp = 0, pq = 0, pn = 0;                // pending M/=/X piece: ref pos, read pos, length
-    // warp-uniform window + counter state
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto load_meta = [&](uint32_t blk) {
+        BlockMeta m = {0u, 0u, 0u, 0u, 0u};
+        const uint64_t idx = (uint64_t)rb + (uint64_t)blk * rpb + lane;
+        if ((uint32_t)lane < rpb && idx < re) {
+            m.start = __ldg(bv.starts + idx);
+            m.cbase = __ldg(bv.cigar_off + idx);
+            m.ncig = __ldg(bv.cigar_off + idx + 1) - m.cbase;
+            m.wbase = __ldg(bv.seq_woff + idx);
+            m.nwords = __ldg(bv.seq_woff + idx + 1) - m.wbase;
+        }
+        return m;
+    };
+    // Stage the words of block `blk` (metadata m) into pipeline stage b.
+    auto issue_block = [&](uint32_t blk, const BlockMeta &m, int b) {
+        const uint32_t nvalid = min(rpb, re - (rb + blk * rpb));
+        const uint32_t s0 = __shfl_sync(kFull, m.wbase, 0);
+        const uint32_t s1 = __shfl_sync(kFull, m.wbase + m.nwords, (int)nvalid - 1);
+        const uint32_t c0 = __shfl_sync(kFull, m.cbase, 0);
+        const uint32_t c1 = __shfl_sync(kFull, m.cbase + m.ncig, (int)nvalid - 1);
+        StagedRange r;
+        r.s_lo = s0 & ~3u;                                           // 32 B / 16 B aligned sources
+        r.s_n = min(((s1 + 3u) & ~3u) - r.s_lo, kSeqCap);
+        r.c_lo = c0 & ~3u;
+        r.c_n = min(((c1 + 3u) & ~3u) - r.c_lo, kCigCap);
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage
+            const uint32_t bytes = r.s_n * 8u + (HAS_OK ? r.s_n * 4u : 0u) + r.c_n * 4u;
+            mbar_expect_tx(&bars[b], bytes);
+            if (r.s_n) {
+                bulk_g2s(seq_buf + b * kSeqCap, bv.planes + r.s_lo, r.s_n * 8u, &bars[b]);
+                if (HAS_OK) bulk_g2s(ok_buf + b * kSeqCap, bv.okmask + r.s_lo, r.s_n * 4u, &bars[b]);
+            }
+            if (r.c_n) bulk_g2s(cig_buf + b * kCigCap, bv.cigar + r.c_lo, r.c_n * 4u, &bars[b]);
+        }
+        return r;
+    };
+
+    BlockMeta m0 = load_meta(0), m1 = load_meta(1), m2 = load_meta(2);
+    StagedRange rg_cur = issue_block(0, m0, 0);
+    StagedRange rg_nxt = {0u, 0u, 0u, 0u};
+    if (nblk > 1) rg_nxt = issue_block(1, m1, 1);
+    uint32_t parity = 0;                            // bit b: phase to wait for on stage b
+
+    // warp-uniform window + counter state (persist across blocks)
     uint32_t win_lo = 0, cnt = 0;
     bool win_valid = false;
     VCounters vc;
     vc.clear();
 
-    for (;;) {
-        // ---- A: read slots that finished their read pull the next ones, in order
-        const bool need = (pn == 0u) && (cur == cend) && !exhausted;
-        const uint32_t need_mask = __ballot_sync(kFull, need && wl == 0);
-        if (need_mask) {
-            if (need) {
+    for (uint32_t j = 0; j < nblk; j++) {
+        const int b = (int)(j & 1u);
+        mbar_wait(&bars[b], (parity >> b) & 1u);
+        parity ^= 1u << b;
+        const uint2 *sq = seq_buf + b * kSeqCap;
+        const uint32_t *okb = ok_buf + b * kSeqCap;
+        const uint32_t *cg = cig_buf + b * kCigCap;
+        const uint32_t blk_lo = rb + j * rpb, blk_hi = min(blk_lo + rpb, re);
+        uint32_t cursor = blk_lo;
+
+        // per read-slot state (replicated over the slot's G lanes)
+        uint32_t cur = 0, cend = 0, ref_pos = 0, read_pos = 0, wbase = 0, nwords = 0;
+        bool exhausted = false;
+        uint32_t pp = 0, pq = 0, pn = 0;            // pending M/=/X piece: ref pos, read pos, length
+
+        for (;;) {
+            // ---- A: read slots that finished their read pull the next ones of this block, in order
+            const bool need = (pn == 0u) && (cur == cend) && !exhausted;
+            const uint32_t need_mask = __ballot_sync(kFull, need && wl == 0);
+            if (need_mask) {
                 const uint32_t idx = cursor + __popc(need_mask & slot_lead_below);
-                if (idx < ch.read_end) {
-                    ref_pos = __ldg(bv.starts + idx);
-                    cur = __ldg(bv.cigar_off + idx);
-                    cend = __ldg(bv.cigar_off + idx + 1);
-                    wbase = __ldg(bv.seq_woff + idx);
-                    nwords = __ldg(bv.seq_woff + idx + 1) - wbase;
+                const bool take = need && idx < blk_hi;
+                const int src = take ? (int)(idx - blk_lo) : 0;
+                const uint32_t t_start = __shfl_sync(kFull, m0.start, src);
+                const uint32_t t_cbase = __shfl_sync(kFull, m0.cbase, src);
+                const uint32_t t_ncig = __shfl_sync(kFull, m0.ncig, src);
+                const uint32_t t_wbase = __shfl_sync(kFull, m0.wbase, src);
+                const uint32_t t_nwords = __shfl_sync(kFull, m0.nwords, src);
+                if (take) {
+                    ref_pos = t_start;
+                    cur = t_cbase;
+                    cend = t_cbase + t_ncig;
+                    wbase = t_wbase;
+                    nwords = t_nwords;
                     read_pos = 0;
-                } else {
+                } else if (need) {
                     exhausted = true;
                 }
+                cursor += __popc(need_mask);
             }
-            cursor += __popc(need_mask);
-        }
-        // ---- B: no piece pending -> consume one CIGAR op (count.cpp:40-96)
-        if (pn == 0u && cur < cend) {
-            const uint32_t cw = __ldg(bv.cigar + cur);
-            cur++;
-            const uint32_t op = cw & 0xFu, len = cw >> 4;
-            if (op_is_match(op)) {                                   // count.cpp:51
-                pp = ref_pos;
-                pq = read_pos;
-                pn = len;
-                ref_pos = sat_add(ref_pos, len);
-                read_pos = sat_add(read_pos, len);
-                if (pn && (pp >= ref_len || pn > ref_len - pp)) {    // would index past the matrix
-                    if (wl == 0) cv.status[kStatMaybeOverflow] = 1u; // exactness decided by k1_check_overflow
-                    pn = pp < ref_len ? ref_len - pp : 0u;
+            // ---- B: no piece pending -> consume one CIGAR op (count.cpp:40-96)
+            if (pn == 0u && cur < cend) {
+                const uint32_t ci = cur - rg_cur.c_lo;
+                const uint32_t cw = ci < rg_cur.c_n ? cg[ci] : __ldg(bv.cigar + cur);
+                cur++;
+                const uint32_t op = cw & 0xFu, len = cw >> 4;
+                if (op_is_match(op)) {                                   // count.cpp:51
+                    pp = ref_pos;
+                    pq = read_pos;
+                    pn = len;
+                    ref_pos = sat_add(ref_pos, len);
+                    read_pos = sat_add(read_pos, len);
+                    if (pn && (pp >= ref_len || pn > ref_len - pp)) {    // would index past the matrix
+                        if (wl == 0) cv.status[kStatMaybeOverflow] = 1u; // exactness decided by k1_check_overflow
+                        pn = pp < ref_len ? ref_len - pp : 0u;
+                    }
+                } else if (op == 1u) {                                   // insertion, count.cpp:74
+                    read_pos = sat_add(read_pos, len);
+                } else if (op_is_refskip(op)) {                          // deletion / skip, count.cpp:80-87
+                    uint32_t lim = ref_pos < ref_len ? min(len, ref_len - ref_pos) : 0u;
+                    if (lim < len && wl == 0) cv.status[kStatIndexError] = 1u;
+                    uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + ch.col_base + ref_pos;
+                    for (uint32_t t = wl; t < lim; t += G) atomicAdd(ds + t, 1u);
+                    ref_pos = sat_add(ref_pos, len);
+                }                                                        // S,H,P,B: ignored, count.cpp:92-95
+            }
+            // ---- C: block done?
+            const bool active = pn > 0u;
+            if (!__any_sync(kFull, active || cur < cend || !exhausted)) break;
+            // ---- D: which pieces can go into the current window?
+            const uint32_t win_hi = win_lo + kWin;
+            const bool fits = active && win_valid && pp >= win_lo && pp < win_hi &&
+                              (pn <= win_hi - pp || pn > kMaxFit);
+            if (__ballot_sync(kFull, fits) == 0u) {
+                if (__ballot_sync(kFull, active) == 0u) continue;        // still walking ops / fetching
+                if (cnt) {
+                    flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
+                    cnt = 0;
                 }
-            } else if (op == 1u) {                                   // insertion, count.cpp:74
-                read_pos = sat_add(read_pos, len);
-            } else if (op_is_refskip(op)) {                          // deletion / skip, count.cpp:80-87
-                uint32_t lim = ref_pos < ref_len ? min(len, ref_len - ref_pos) : 0u;
-                if (lim < len && wl == 0) cv.status[kStatIndexError] = 1u;
-                uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + ch.col_base + ref_pos;
-                for (uint32_t t = wl; t < lim; t += G) atomicAdd(ds + t, 1u);
-                ref_pos = sat_add(ref_pos, len);
-            }                                                        // S,H,P,B: ignored, count.cpp:92-95
-        }
-        // ---- C: done?
-        const bool active = pn > 0u;
-        if (!__any_sync(kFull, active || cur < cend || !exhausted)) break;
-        // ---- D: which pieces can go into the current window?
-        const uint32_t win_hi = win_lo + kWin;
-        const bool fits = active && win_valid && pp >= win_lo && pp < win_hi &&
-                          (pn <= win_hi - pp || pn > kMaxFit);
-        if (__ballot_sync(kFull, fits) == 0u) {
-            if (__ballot_sync(kFull, active) == 0u) continue;        // still walking ops / fetching
-            if (cnt) {
+                const uint32_t lowest = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu);
+                win_lo = lowest & ~31u;
+                win_valid = true;
+                continue;
+            }
+            // ---- E: one masked 32-column word per lane, added to the vertical counters
+            uint32_t x[4] = {0u, 0u, 0u, 0u};
+            uint32_t n1 = 0;
+            if (fits) {
+                n1 = min(pn, win_hi - pp);
+                const int rel = (int)(win_lo + 32u * (uint32_t)wl) - (int)pp;   // lane word starts at piece offset rel
+                const int a = max(rel, 0), e = min(rel + 32, (int)n1);
+                if (a < e) {
+                    const int bit = (int)pq + rel;                        // read bit index of the word's column 0
+                    const int k = bit >> 5, sh = bit & 31;
+                    uint2 w0 = make_uint2(0u, 0u), w1 = make_uint2(0u, 0u);
+                    uint32_t o0 = 0u, o1 = 0u;
+                    if (k >= 0 && (uint32_t)k < nwords) {
+                        const uint32_t g = wbase + (uint32_t)k, si = g - rg_cur.s_lo;
+                        if (si < rg_cur.s_n) {
+                            w0 = sq[si];
+                            if (HAS_OK) o0 = okb[si];
+                        } else {
+                            w0 = __ldg(bv.planes + g);
+                            if (HAS_OK) o0 = __ldg(bv.okmask + g);
+                        }
+                    }
+                    if (k + 1 >= 0 && (uint32_t)(k + 1) < nwords) {
+                        const uint32_t g = wbase + (uint32_t)(k + 1), si = g - rg_cur.s_lo;
+                        if (si < rg_cur.s_n) {
+                            w1 = sq[si];
+                            if (HAS_OK) o1 = okb[si];
+                        } else {
+                            w1 = __ldg(bv.planes + g);
+                            if (HAS_OK) o1 = __ldg(bv.okmask + g);
+                        }
+                    }
+                    const uint32_t lo = __funnelshift_r(w0.x, w1.x, sh);
+                    const uint32_t hi = __funnelshift_r(w0.y, w1.y, sh);
+                    const int lo_bit = a - rel, hi_bit = e - rel;         // [lo_bit, hi_bit) of this word are in the piece
+                    uint32_t m = (hi_bit >= 32 ? 0xFFFFFFFFu : ((1u << hi_bit) - 1u)) & (0xFFFFFFFFu << lo_bit);
+                    if (HAS_OK) m &= __funnelshift_r(o0, o1, sh);
+                    x[0] = ~hi & ~lo & m;                                 // A
+                    x[1] = ~hi & lo & m;                                  // C
+                    x[2] = hi & ~lo & m;                                  // G
+                    x[3] = hi & lo & m;                                   // T
+                }
+            }
+            vc.add(x, cnt);
+            pp += n1;
+            pq += n1;
+            pn -= n1;
+            if (++cnt == kCntMax) {
                 flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
                 cnt = 0;
             }
-            const uint32_t lowest = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu);
-            win_lo = lowest & ~31u;
-            win_valid = true;
-            continue;
         }
-        // ---- E: one masked 32-column word per lane, added to the vertical counters
-        uint32_t x[4] = {0u, 0u, 0u, 0u};
-        uint32_t n1 = 0;
-        if (fits) {
-            n1 = min(pn, win_hi - pp);
-            const int rel = (int)(win_lo + 32u * (uint32_t)wl) - (int)pp;   // lane word starts at piece offset rel
-            const int a = max(rel, 0), e = min(rel + 32, (int)n1);
-            if (a < e) {
-                const int bit = (int)pq + rel;                        // read bit index of the word's column 0
-                const int k = bit >> 5, sh = bit & 31;
-                uint2 w0 = make_uint2(0u, 0u), w1 = make_uint2(0u, 0u);
-                uint32_t o0 = 0u, o1 = 0u;
-                if (k >= 0 && (uint32_t)k < nwords) {
-                    w0 = __ldg(bv.planes + wbase + k);
-                    if (HAS_OK) o0 = __ldg(bv.okmask + wbase + k);
-                }
-                if (k + 1 >= 0 && (uint32_t)(k + 1) < nwords) {
-                    w1 = __ldg(bv.planes + wbase + k + 1);
-                    if (HAS_OK) o1 = __ldg(bv.okmask + wbase + k + 1);
-                }
-                const uint32_t lo = __funnelshift_r(w0.x, w1.x, sh);
-                const uint32_t hi = __funnelshift_r(w0.y, w1.y, sh);
-                const int lo_bit = a - rel, hi_bit = e - rel;         // [lo_bit, hi_bit) of this word are in the piece
-                uint32_t m = (hi_bit >= 32 ? 0xFFFFFFFFu : ((1u << hi_bit) - 1u)) & (0xFFFFFFFFu << lo_bit);
-                if (HAS_OK) m &= __funnelshift_r(o0, o1, sh);
-                x[0] = ~hi & ~lo & m;                                 // A
-                x[1] = ~hi & lo & m;                                  // C
-                x[2] = hi & ~lo & m;                                  // G
-                x[3] = hi & lo & m;                                   // T
-            }
-        }
-        vc.add(x, cnt);
-        pp += n1;
-        pq += n1;
-        pn -= n1;
-        if (++cnt == kCntMax) {
-            flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
-            cnt = 0;
-        }
+        // ---- stage b is free again: refill it with block j+2, rotate the metadata pipeline
+        __syncwarp();
+        m0 = m1;
+        m1 = m2;
+        rg_cur = rg_nxt;
+        if (j + 2 < nblk) rg_nxt = issue_block(j + 2, m1, b);
+        m2 = load_meta(j + 3);
     }
     if (cnt) flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
 }
