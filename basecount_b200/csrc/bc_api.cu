@@ -283,10 +283,11 @@ int bc_reset(bc_handle *h)
 // ------------------------------------------------------------------ batches
 static int pick_group_width(const bc_batch *b, uint64_t total_words)
 {
+    // window = 32 * kW * G columns must hold a typical read at any 32-column alignment
     uint64_t mean = b->mean_read_len;
     if (mean == 0 && b->n_reads) mean = total_words * 32u / b->n_reads;
-    if (mean <= 8u * 32u - 31u) return 8;
-    if (mean <= 16u * 32u - 31u) return 16;
+    for (int G : {4, 8, 16})
+        if (mean + mean / 8 <= 32u * kW * G - 31u) return G;
     return 32;
 }
 
@@ -367,7 +368,8 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
             k1_count_tiled<GG, false><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb); \
         }                                                                                                      \
     } while (0)
-        if (G == 8) K1_LAUNCH(8);
+        if (G == 4) K1_LAUNCH(4);
+        else if (G == 8) K1_LAUNCH(8);
         else if (G == 16) K1_LAUNCH(16);
         else K1_LAUNCH(32);
 #undef K1_LAUNCH

@@ -23,7 +23,8 @@
 
 namespace bc {
 
-constexpr int kK1WarpsPerCta = 8;
+constexpr int kK1WarpsPerCta = 4;
+constexpr int kK1MinCtas = 3;
 constexpr int kK1Threads = kK1WarpsPerCta * 32;
 constexpr int kNB = 8;                       // bit planes per vertical counter (counts to 255)
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -95,61 +96,6 @@ struct VCounters {
     }
 };
 
-// Convert the warp's vertical counters to integers and add them to the HBM planes.
-// fbuf: this warp's staging area, 4 * 32*G bytes.  win_col = global column of window word 0.
-template <int G>
-__device__ __forceinline__ void flush_counters(VCounters &vc, uint32_t cnt, uint32_t *fbuf, uint64_t win_col,
-                                               uint32_t *__restrict__ counts, uint64_t stride, int lane)
-{
-    const int slot = lane / G, wl = lane % G;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        uint32_t v[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; jj++) {
-            // byte t of acc = count of column jj + 8t
-            uint32_t acc = 0;
-#pragma unroll
-            for (int k = 0; k < kNB; k++) {
-                if ((cnt >> k) == 0u) break;                     // uniform: higher planes are empty
-                acc += ((vc.pl[b][k] >> jj) & 0x01010101u) << k;
-            }
-            if (cnt & 1u) acc += (vc.pend[b][0] >> jj) & 0x01010101u;
-            if (cnt & 2u) acc += ((vc.pend[b][1] >> jj) & 0x01010101u) << 1;
-            if (cnt & 4u) acc += ((vc.pend[b][2] >> jj) & 0x01010101u) << 2;
-#pragma unroll
-            for (int d = G; d < 32; d <<= 1) acc += __shfl_xor_sync(kFull, acc, d);   // sum the read slots
-            v[jj] = acc;
-        }
-        if (slot == 0) {
-            // 4x4 byte transposes: out word (t,h) = columns 8t+4h .. 8t+4h+3
-            uint8_t *row = reinterpret_cast<uint8_t *>(fbuf) + b * (32 * G) + 32 * wl;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    uint32_t sel = (uint32_t)t | ((uint32_t)(4 + t) << 4);
-                    uint32_t lo = __byte_perm(v[4 * h + 0], v[4 * h + 1], sel);
-                    uint32_t hi = __byte_perm(v[4 * h + 2], v[4 * h + 3], sel);
-                    *reinterpret_cast<uint32_t *>(row + 8 * t + 4 * h) = __byte_perm(lo, hi, 0x5410);
-                }
-            }
-        }
-    }
-    __syncwarp();
-    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(fbuf);
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        uint32_t *plane = counts + (uint64_t)b * stride + win_col;
-        for (int w = 0; w < G; w++) {
-            uint32_t val = bytes[b * (32 * G) + 32 * w + lane];
-            if (val) atomicAdd(plane + 32 * w + lane, val);     // RED.ADD, 128 B per warp instruction
-        }
-    }
-    __syncwarp();
-    vc.clear();
-}
-
 // ---- TMA (1-D bulk async copy) + mbarrier helpers -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -182,15 +128,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// Staging capacities per warp and per pipeline stage.
-constexpr uint32_t kSeqCap = 512;     // 64-bit plane words  (4 KB)   -- 32 reads x 400 bp = 416 words
-constexpr uint32_t kCigCap = 256;     // CIGAR words         (1 KB)
+// ---- geometry -----------------------------------------------------------------------------
+// A warp's 32 lanes form S = 32/G read slots of G lanes; every lane covers W consecutive
+// 32-column window words, so the (warp-shared) window spans 32*W*G reference columns.
+constexpr int kW = 2;
+constexpr uint32_t kSeqCap = 512;     // staged 64-bit plane words per stage (4 KB): 32 reads x 400 bp = 416 words
+constexpr uint32_t kSeqPad = 4;       // guard words so clamped out-of-piece loads stay inside the stage
+constexpr uint32_t kCigCap = 256;     // staged CIGAR words per stage (1 KB)
 constexpr int kStages = 2;
+constexpr uint32_t kCntMax = 255u;    // per-slot count limit of the 8-plane counters
 
 template <int G, bool HAS_OK>
 __host__ __device__ constexpr uint32_t k1_warp_smem_bytes()
 {
-    return kStages * kSeqCap * 8u + (HAS_OK ? kStages * kSeqCap * 4u : 0u) + kStages * kCigCap * 4u + 128u * G + 128u;
+    return kStages * (kSeqCap + kSeqPad) * 8u + (HAS_OK ? kStages * (kSeqCap + kSeqPad) * 4u : 0u) +
+           kStages * kCigCap * 4u + /* flush row: 32*W*G columns x u16 */ 64u * kW * G + /* order lists */ 64u +
+           /* mbarriers */ 64u;
 }
 
 struct BlockMeta {            // lane l holds the metadata of read (block_first + l)
@@ -201,18 +154,122 @@ struct StagedRange {          // what one pipeline stage holds (warp-uniform)
     uint32_t c_lo, c_n;       // CIGAR words        [c_lo, c_lo + c_n)
 };
 
-// The counting kernel.  One warp = one chunk of consecutive reads, processed in blocks of
-// `rpb` <= 32 reads: the block's metadata sits in registers (one read per lane, handed to the
-// read slots by shuffle), its sequence / CIGAR words are staged in shared memory by TMA bulk
-// copies two blocks ahead, so the inner loop touches only registers and shared memory.
+// Convert the warp's vertical counters to integers and add them to the HBM planes.
+// Byte-packed extraction per slot, widened to 16 bit before the S read slots are summed
+// (so each slot may hold up to 255), staged in shared memory one letter at a time and
+// written with coalesced RED.ADD (128 B per warp instruction).
+template <int G>
+__device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt, uint16_t *frow, uint64_t win_col,
+                                               uint32_t *__restrict__ counts, uint64_t stride, int lane)
+{
+    constexpr int S = 32 / G;
+    const int slot = lane / G, wl = lane % G;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+#pragma unroll
+        for (int w = 0; w < kW; w++) {
+            uint16_t *dst = frow + (kW * wl + w) * 32;
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                uint32_t acc = 0;                     // byte t = count of column jj + 8t (this slot only)
+#pragma unroll
+                for (int k = 0; k < kNB; k++) {
+                    if ((cnt >> k) == 0u) break;      // uniform: higher planes are empty
+                    acc += ((vc[w].pl[b][k] >> jj) & 0x01010101u) << k;
+                }
+                if (cnt & 1u) acc += (vc[w].pend[b][0] >> jj) & 0x01010101u;
+                if (cnt & 2u) acc += ((vc[w].pend[b][1] >> jj) & 0x01010101u) << 1;
+                if (cnt & 4u) acc += ((vc[w].pend[b][2] >> jj) & 0x01010101u) << 2;
+                uint32_t ev = acc & 0x00FF00FFu;          // columns jj, jj+16
+                uint32_t od = (acc >> 8) & 0x00FF00FFu;   // columns jj+8, jj+24
+#pragma unroll
+                for (int d = G; d < 32; d <<= 1) {        // sum the read slots (<= 8 * 255 fits 16 bit)
+                    ev += __shfl_xor_sync(kFull, ev, d);
+                    od += __shfl_xor_sync(kFull, od, d);
+                }
+                if ((jj % S) == slot) {
+                    dst[jj] = (uint16_t)ev;
+                    dst[jj + 16] = (uint16_t)(ev >> 16);
+                    dst[jj + 8] = (uint16_t)od;
+                    dst[jj + 24] = (uint16_t)(od >> 16);
+                }
+            }
+        }
+        __syncwarp();
+        uint32_t *plane = counts + (uint64_t)b * stride + win_col;
+        for (int w = 0; w < kW * G; w++) {
+            const uint32_t val = frow[32 * w + lane];
+            if (val) atomicAdd(plane + 32 * w + lane, val);     // RED.ADD, 128 B per warp instruction
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int w = 0; w < kW; w++) vc[w].clear();
+}
+
+// Masked one-hot words of one piece for this lane's kW window words.
+//   pp / pq / n1 : reference start, read start and length of the (window-clipped) piece
+//   sidx         : stage index of the read's word 0 (>= kSeqPad) when the read is fully staged, else -1
 template <int G, bool HAS_OK>
-__global__ void __launch_bounds__(kK1Threads, 2)
+__device__ __forceinline__ void piece_words(uint32_t (&x)[kW][4], uint32_t pp, uint32_t pq, uint32_t n1, uint32_t win_lo,
+                                            int wl, const uint2 *__restrict__ sq, const uint32_t *__restrict__ okb,
+                                            int sidx, const BatchView &bv, uint32_t wbase, uint32_t nwords)
+{
+    const int rel = (int)(win_lo + 32u * kW * (uint32_t)wl) - (int)pp;   // piece offset of this lane's column 0
+    const int lo_off = max(-rel, 0), hi_off = min((int)n1 - rel, 32 * kW);
+    if (lo_off >= hi_off) return;                                      // x stays 0
+    const int bit = (int)pq + rel;                                     // read bit index of the lane's column 0
+    const int k = bit >> 5, sh = bit & 31;
+    uint2 r[kW + 1];
+    uint32_t o[kW + 1];
+    if (sidx >= 0) {
+        // Fully staged: out-of-piece words are masked away below, so only memory safety matters.
+        const int base = min(max(sidx + k, 0), (int)(kSeqCap + kSeqPad) - (kW + 1));
+#pragma unroll
+        for (int i = 0; i <= kW; i++) {
+            r[i] = sq[base + i];
+            if (HAS_OK) o[i] = okb[base + i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i <= kW; i++) {
+            r[i] = make_uint2(0u, 0u);
+            o[i] = 0u;
+            if (k + i >= 0 && (uint32_t)(k + i) < nwords) {
+                r[i] = __ldg(bv.planes + wbase + (uint32_t)(k + i));
+                if (HAS_OK) o[i] = __ldg(bv.okmask + wbase + (uint32_t)(k + i));
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+        const int a = min(max(lo_off - 32 * w, 0), 32), e = min(max(hi_off - 32 * w, 0), 32);
+        uint32_t m = 0u;
+        if (a < e) m = (e >= 32 ? 0xFFFFFFFFu : ((1u << e) - 1u)) & (0xFFFFFFFFu << a);
+        if (HAS_OK) m &= __funnelshift_r(o[w], o[w + 1], sh);
+        const uint32_t lo = __funnelshift_r(r[w].x, r[w + 1].x, sh);
+        const uint32_t hi = __funnelshift_r(r[w].y, r[w + 1].y, sh);
+        x[w][0] = ~hi & ~lo & m;                                       // A
+        x[w][1] = ~hi & lo & m;                                        // C
+        x[w][2] = hi & ~lo & m;                                        // G
+        x[w][3] = hi & lo & m;                                         // T
+    }
+}
+
+// The counting kernel.  One warp = one chunk of consecutive reads, processed in blocks of
+// `rpb` <= 32 reads.  Per block: metadata sits in registers (one read per lane, handed to the
+// read slots by shuffle); sequence / CIGAR words were staged in shared memory by TMA bulk
+// copies two blocks ahead.  Reads that are a single M/=/X run (the common case) go through a
+// branch-free fast loop, S reads per iteration; the rest (indels, clips, long or unstaged
+// reads, reads deferred by a window move) go through the general CIGAR state machine.
+template <int G, bool HAS_OK>
+__global__ void __launch_bounds__(kK1Threads, kK1MinCtas)
 k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb)
 {
     constexpr int S = 32 / G;
-    constexpr uint32_t kCntMax = 255u / S;          // byte-packed slot sums must stay <= 255
-    constexpr uint32_t kWin = 32u * G;              // window columns
+    constexpr uint32_t kWin = 32u * kW * G;         // window columns
     constexpr uint32_t kMaxFit = kWin - 31u;        // a piece this long fits a fresh window at any alignment
+    constexpr uint32_t kStageWords = kSeqCap + kSeqPad;
     extern __shared__ __align__(128) unsigned char k1_smem[];
 
     const int lane = threadIdx.x & 31;
@@ -222,18 +279,22 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
 
     unsigned char *wsm = k1_smem + (size_t)warp_in_cta * k1_warp_smem_bytes<G, HAS_OK>();
     uint2 *seq_buf = reinterpret_cast<uint2 *>(wsm);
-    uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kSeqCap * 8u);
-    uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kSeqCap * 8u + (HAS_OK ? kStages * kSeqCap * 4u : 0u));
-    uint32_t *fbuf = cig_buf + kStages * kCigCap;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(fbuf) + 128u * G);
+    uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u);
+    uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u + (HAS_OK ? kStages * kStageWords * 4u : 0u));
+    uint16_t *frow = reinterpret_cast<uint16_t *>(cig_buf + kStages * kCigCap);
+    uint8_t *order1 = reinterpret_cast<uint8_t *>(frow) + 64u * kW * G;
+    uint8_t *order2 = order1 + 32;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(order2 + 32);
 
     const int slot = lane / G, wl = lane % G;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t slot_lead_below = (slot == 0) ? 0u : ((1u << (slot * G)) - 1u);
 
     const Chunk ch = chunks[warp_id];
     const uint32_t ref_len = ch.ref_len;
     const uint32_t rb = ch.read_begin, re = ch.read_end;
     const uint32_t nblk = (re - rb + rpb - 1) / rpb;
+    const uint64_t col0 = ch.col_base;
 
     if (lane == 0) {
         mbar_init(&bars[0], 1);
@@ -271,8 +332,8 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             const uint32_t bytes = r.s_n * 8u + (HAS_OK ? r.s_n * 4u : 0u) + r.c_n * 4u;
             mbar_expect_tx(&bars[b], bytes);
             if (r.s_n) {
-                bulk_g2s(seq_buf + b * kSeqCap, bv.planes + r.s_lo, r.s_n * 8u, &bars[b]);
-                if (HAS_OK) bulk_g2s(ok_buf + b * kSeqCap, bv.okmask + r.s_lo, r.s_n * 4u, &bars[b]);
+                bulk_g2s(seq_buf + b * kStageWords + kSeqPad, bv.planes + r.s_lo, r.s_n * 8u, &bars[b]);
+                if (HAS_OK) bulk_g2s(ok_buf + b * kStageWords + kSeqPad, bv.okmask + r.s_lo, r.s_n * 4u, &bars[b]);
             }
             if (r.c_n) bulk_g2s(cig_buf + b * kCigCap, bv.cigar + r.c_lo, r.c_n * 4u, &bars[b]);
         }
@@ -280,7 +341,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     };
 
     BlockMeta m0 = load_meta(0), m1 = load_meta(1), m2 = load_meta(2);
-    StagedRange rg_cur = issue_block(0, m0, 0);
+    StagedRange rg = issue_block(0, m0, 0);
     StagedRange rg_nxt = {0u, 0u, 0u, 0u};
     if (nblk > 1) rg_nxt = issue_block(1, m1, 1);
     uint32_t parity = 0;                            // bit b: phase to wait for on stage b
@@ -288,154 +349,178 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     // warp-uniform window + counter state (persist across blocks)
     uint32_t win_lo = 0, cnt = 0;
     bool win_valid = false;
-    VCounters vc;
-    vc.clear();
+    VCounters vc[kW];
+#pragma unroll
+    for (int w = 0; w < kW; w++) vc[w].clear();
+
+    auto do_flush = [&]() {
+        flush_counters<G>(vc, cnt, frow, col0 + win_lo, cv.counts, cv.stride, lane);
+        cnt = 0;
+    };
+    auto accumulate = [&](uint32_t (&x)[kW][4]) {
+#pragma unroll
+        for (int w = 0; w < kW; w++) vc[w].add(x[w], cnt);
+        if (++cnt == kCntMax) do_flush();
+    };
 
     for (uint32_t j = 0; j < nblk; j++) {
         const int b = (int)(j & 1u);
         mbar_wait(&bars[b], (parity >> b) & 1u);
         parity ^= 1u << b;
-        const uint2 *sq = seq_buf + b * kSeqCap;
-        const uint32_t *okb = ok_buf + b * kSeqCap;
+        const uint2 *sq = seq_buf + b * kStageWords;
+        const uint32_t *okb = ok_buf + b * kStageWords;
         const uint32_t *cg = cig_buf + b * kCigCap;
-        const uint32_t blk_lo = rb + j * rpb, blk_hi = min(blk_lo + rpb, re);
-        uint32_t cursor = blk_lo;
+        const uint32_t nvalid = min(rpb, re - (rb + j * rpb));
 
-        // per read-slot state (replicated over the slot's G lanes)
-        uint32_t cur = 0, cend = 0, ref_pos = 0, read_pos = 0, wbase = 0, nwords = 0;
-        bool exhausted = false;
-        uint32_t pp = 0, pq = 0, pn = 0;            // pending M/=/X piece: ref pos, read pos, length
+        // ---- per-read classification, one read per lane
+        const bool valid = (uint32_t)lane < nvalid;
+        uint32_t cig0 = 0u;
+        if (valid && m0.ncig) {
+            const uint32_t ci = m0.cbase - rg.c_lo;
+            cig0 = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + m0.cbase);
+        }
+        const bool staged = valid && (m0.wbase - rg.s_lo) <= rg.s_n && (m0.wbase - rg.s_lo) + m0.nwords <= rg.s_n;
+        const int my_sidx = staged ? (int)(m0.wbase - rg.s_lo + kSeqPad) : -1;
+        uint32_t p_len = cig0 >> 4;
+        const bool one_match = valid && m0.ncig == 1u && op_is_match(cig0 & 0xFu);
+        bool simple = one_match && staged && p_len <= kMaxFit;
+        if (simple && p_len && (m0.start >= ref_len || p_len > ref_len - m0.start)) {   // would index past the matrix
+            cv.status[kStatMaybeOverflow] = 1u;                      // exactness decided by k1_check_overflow
+            p_len = m0.start < ref_len ? ref_len - m0.start : 0u;
+        }
+        const uint32_t simple_mask = __ballot_sync(kFull, simple && p_len);
+        uint32_t rest_mask = __ballot_sync(kFull, valid && m0.ncig && !simple);
+        if ((simple_mask >> lane) & 1u) order1[__popc(simple_mask & lt_mask)] = (uint8_t)lane;
+        __syncwarp();
 
-        for (;;) {
-            // ---- A: read slots that finished their read pull the next ones of this block, in order
-            const bool need = (pn == 0u) && (cur == cend) && !exhausted;
-            const uint32_t need_mask = __ballot_sync(kFull, need && wl == 0);
-            if (need_mask) {
-                const uint32_t idx = cursor + __popc(need_mask & slot_lead_below);
-                const bool take = need && idx < blk_hi;
-                const int src = take ? (int)(idx - blk_lo) : 0;
-                const uint32_t t_start = __shfl_sync(kFull, m0.start, src);
-                const uint32_t t_cbase = __shfl_sync(kFull, m0.cbase, src);
-                const uint32_t t_ncig = __shfl_sync(kFull, m0.ncig, src);
-                const uint32_t t_wbase = __shfl_sync(kFull, m0.wbase, src);
-                const uint32_t t_nwords = __shfl_sync(kFull, m0.nwords, src);
-                if (take) {
-                    ref_pos = t_start;
-                    cur = t_cbase;
-                    cend = t_cbase + t_ncig;
-                    wbase = t_wbase;
-                    nwords = t_nwords;
-                    read_pos = 0;
-                } else if (need) {
-                    exhausted = true;
+        // ---- fast loop: S single-run reads per iteration
+        const uint32_t n_simple = __popc(simple_mask);
+        for (uint32_t t = 0; t * S < n_simple;) {
+            const uint32_t kk = t * S + slot;
+            const bool have = kk < n_simple;
+            const int src = have ? (int)order1[kk] : 0;
+            const uint32_t pp = __shfl_sync(kFull, m0.start, src);
+            const uint32_t pn = __shfl_sync(kFull, p_len, src);
+            const int sidx = __shfl_sync(kFull, my_sidx, src);
+            const bool fits = have && win_valid && pp >= win_lo && (pp - win_lo) <= kWin - pn;
+            const uint32_t have_mask = __ballot_sync(kFull, have);
+            const uint32_t fit_mask = __ballot_sync(kFull, fits);
+            if (fit_mask != have_mask) {
+                if (fit_mask == 0u) {                                // nobody fits: move the window
+                    if (cnt) do_flush();
+                    win_lo = __reduce_min_sync(kFull, have ? pp : 0xFFFFFFFFu) & ~31u;
+                    win_valid = true;
+                    continue;
                 }
-                cursor += __popc(need_mask);
+                // reads that do not fit this window are left to the general loop below
+                rest_mask |= __reduce_or_sync(kFull, (have && !fits && wl == 0) ? (1u << src) : 0u);
             }
-            // ---- B: no piece pending -> consume one CIGAR op (count.cpp:40-96)
-            if (pn == 0u && cur < cend) {
-                const uint32_t ci = cur - rg_cur.c_lo;
-                const uint32_t cw = ci < rg_cur.c_n ? cg[ci] : __ldg(bv.cigar + cur);
-                cur++;
-                const uint32_t op = cw & 0xFu, len = cw >> 4;
-                if (op_is_match(op)) {                                   // count.cpp:51
-                    pp = ref_pos;
-                    pq = read_pos;
-                    pn = len;
-                    ref_pos = sat_add(ref_pos, len);
-                    read_pos = sat_add(read_pos, len);
-                    if (pn && (pp >= ref_len || pn > ref_len - pp)) {    // would index past the matrix
-                        if (wl == 0) cv.status[kStatMaybeOverflow] = 1u; // exactness decided by k1_check_overflow
-                        pn = pp < ref_len ? ref_len - pp : 0u;
+            uint32_t x[kW][4] = {};
+            if (fits) piece_words<G, HAS_OK>(x, pp, 0u, pn, win_lo, wl, sq, okb, sidx, bv, 0u, 0u);
+            accumulate(x);
+            t++;
+        }
+
+        // ---- general loop: CIGAR state machine over the remaining reads of the block
+        if (rest_mask) {
+            if ((rest_mask >> lane) & 1u) order2[__popc(rest_mask & lt_mask)] = (uint8_t)lane;
+            __syncwarp();
+            const uint32_t n_rest = __popc(rest_mask);
+            uint32_t cursor = 0;
+            // per read-slot state (replicated over the slot's G lanes)
+            uint32_t cur = 0, cend = 0, ref_pos = 0, read_pos = 0, wbase = 0, nwords = 0;
+            int sidx = -1;
+            bool exhausted = false;
+            uint32_t pp = 0, pq = 0, pn = 0;        // pending M/=/X piece: ref pos, read pos, length
+            for (;;) {
+                // A: read slots that finished their read pull the next ones, in order
+                const bool need = (pn == 0u) && (cur == cend) && !exhausted;
+                const uint32_t need_mask = __ballot_sync(kFull, need && wl == 0);
+                if (need_mask) {
+                    const uint32_t idx = cursor + __popc(need_mask & slot_lead_below);
+                    const bool take = need && idx < n_rest;
+                    const int src = take ? (int)order2[idx] : 0;
+                    const uint32_t t_start = __shfl_sync(kFull, m0.start, src);
+                    const uint32_t t_cbase = __shfl_sync(kFull, m0.cbase, src);
+                    const uint32_t t_ncig = __shfl_sync(kFull, m0.ncig, src);
+                    const uint32_t t_wbase = __shfl_sync(kFull, m0.wbase, src);
+                    const uint32_t t_nwords = __shfl_sync(kFull, m0.nwords, src);
+                    const int t_sidx = __shfl_sync(kFull, my_sidx, src);
+                    if (take) {
+                        ref_pos = t_start;
+                        cur = t_cbase;
+                        cend = t_cbase + t_ncig;
+                        wbase = t_wbase;
+                        nwords = t_nwords;
+                        sidx = t_sidx;
+                        read_pos = 0;
+                    } else if (need) {
+                        exhausted = true;
                     }
-                } else if (op == 1u) {                                   // insertion, count.cpp:74
-                    read_pos = sat_add(read_pos, len);
-                } else if (op_is_refskip(op)) {                          // deletion / skip, count.cpp:80-87
-                    uint32_t lim = ref_pos < ref_len ? min(len, ref_len - ref_pos) : 0u;
-                    if (lim < len && wl == 0) cv.status[kStatIndexError] = 1u;
-                    uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + ch.col_base + ref_pos;
-                    for (uint32_t t = wl; t < lim; t += G) atomicAdd(ds + t, 1u);
-                    ref_pos = sat_add(ref_pos, len);
-                }                                                        // S,H,P,B: ignored, count.cpp:92-95
-            }
-            // ---- C: block done?
-            const bool active = pn > 0u;
-            if (!__any_sync(kFull, active || cur < cend || !exhausted)) break;
-            // ---- D: which pieces can go into the current window?
-            const uint32_t win_hi = win_lo + kWin;
-            const bool fits = active && win_valid && pp >= win_lo && pp < win_hi &&
-                              (pn <= win_hi - pp || pn > kMaxFit);
-            if (__ballot_sync(kFull, fits) == 0u) {
-                if (__ballot_sync(kFull, active) == 0u) continue;        // still walking ops / fetching
-                if (cnt) {
-                    flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
-                    cnt = 0;
+                    cursor += __popc(need_mask);
                 }
-                const uint32_t lowest = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu);
-                win_lo = lowest & ~31u;
-                win_valid = true;
-                continue;
-            }
-            // ---- E: one masked 32-column word per lane, added to the vertical counters
-            uint32_t x[4] = {0u, 0u, 0u, 0u};
-            uint32_t n1 = 0;
-            if (fits) {
-                n1 = min(pn, win_hi - pp);
-                const int rel = (int)(win_lo + 32u * (uint32_t)wl) - (int)pp;   // lane word starts at piece offset rel
-                const int a = max(rel, 0), e = min(rel + 32, (int)n1);
-                if (a < e) {
-                    const int bit = (int)pq + rel;                        // read bit index of the word's column 0
-                    const int k = bit >> 5, sh = bit & 31;
-                    uint2 w0 = make_uint2(0u, 0u), w1 = make_uint2(0u, 0u);
-                    uint32_t o0 = 0u, o1 = 0u;
-                    if (k >= 0 && (uint32_t)k < nwords) {
-                        const uint32_t g = wbase + (uint32_t)k, si = g - rg_cur.s_lo;
-                        if (si < rg_cur.s_n) {
-                            w0 = sq[si];
-                            if (HAS_OK) o0 = okb[si];
-                        } else {
-                            w0 = __ldg(bv.planes + g);
-                            if (HAS_OK) o0 = __ldg(bv.okmask + g);
+                // B: no piece pending -> consume one CIGAR op (count.cpp:40-96)
+                if (pn == 0u && cur < cend) {
+                    const uint32_t ci = cur - rg.c_lo;
+                    const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + cur);
+                    cur++;
+                    const uint32_t op = cw & 0xFu, len = cw >> 4;
+                    if (op_is_match(op)) {                                   // count.cpp:51
+                        pp = ref_pos;
+                        pq = read_pos;
+                        pn = len;
+                        ref_pos = sat_add(ref_pos, len);
+                        read_pos = sat_add(read_pos, len);
+                        if (pn && (pp >= ref_len || pn > ref_len - pp)) {    // would index past the matrix
+                            if (wl == 0) cv.status[kStatMaybeOverflow] = 1u;
+                            pn = pp < ref_len ? ref_len - pp : 0u;
                         }
-                    }
-                    if (k + 1 >= 0 && (uint32_t)(k + 1) < nwords) {
-                        const uint32_t g = wbase + (uint32_t)(k + 1), si = g - rg_cur.s_lo;
-                        if (si < rg_cur.s_n) {
-                            w1 = sq[si];
-                            if (HAS_OK) o1 = okb[si];
-                        } else {
-                            w1 = __ldg(bv.planes + g);
-                            if (HAS_OK) o1 = __ldg(bv.okmask + g);
-                        }
-                    }
-                    const uint32_t lo = __funnelshift_r(w0.x, w1.x, sh);
-                    const uint32_t hi = __funnelshift_r(w0.y, w1.y, sh);
-                    const int lo_bit = a - rel, hi_bit = e - rel;         // [lo_bit, hi_bit) of this word are in the piece
-                    uint32_t m = (hi_bit >= 32 ? 0xFFFFFFFFu : ((1u << hi_bit) - 1u)) & (0xFFFFFFFFu << lo_bit);
-                    if (HAS_OK) m &= __funnelshift_r(o0, o1, sh);
-                    x[0] = ~hi & ~lo & m;                                 // A
-                    x[1] = ~hi & lo & m;                                  // C
-                    x[2] = hi & ~lo & m;                                  // G
-                    x[3] = hi & lo & m;                                   // T
+                    } else if (op == 1u) {                                   // insertion, count.cpp:74
+                        read_pos = sat_add(read_pos, len);
+                    } else if (op_is_refskip(op)) {                          // deletion / skip, count.cpp:80-87
+                        uint32_t lim = ref_pos < ref_len ? min(len, ref_len - ref_pos) : 0u;
+                        if (lim < len && wl == 0) cv.status[kStatIndexError] = 1u;
+                        uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + col0 + ref_pos;
+                        for (uint32_t t = wl; t < lim; t += G) atomicAdd(ds + t, 1u);
+                        ref_pos = sat_add(ref_pos, len);
+                    }                                                        // S,H,P,B: ignored, count.cpp:92-95
                 }
-            }
-            vc.add(x, cnt);
-            pp += n1;
-            pq += n1;
-            pn -= n1;
-            if (++cnt == kCntMax) {
-                flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
-                cnt = 0;
+                // C: done with the block?
+                const bool active = pn > 0u;
+                if (!__any_sync(kFull, active || cur < cend || !exhausted)) break;
+                // D: which pieces can go into the current window?
+                const bool fits = active && win_valid && pp >= win_lo && (pp - win_lo) < kWin &&
+                                  (pn <= kWin - (pp - win_lo) || pn > kMaxFit);
+                if (__ballot_sync(kFull, fits) == 0u) {
+                    if (__ballot_sync(kFull, active) == 0u) continue;        // still walking ops / fetching
+                    if (cnt) do_flush();
+                    win_lo = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu) & ~31u;
+                    win_valid = true;
+                    continue;
+                }
+                // E: masked words of the fitting pieces, added to the vertical counters
+                uint32_t x[kW][4] = {};
+                uint32_t n1 = 0;
+                if (fits) {
+                    n1 = min(pn, kWin - (pp - win_lo));
+                    piece_words<G, HAS_OK>(x, pp, pq, n1, win_lo, wl, sq, okb, sidx, bv, wbase, nwords);
+                }
+                accumulate(x);
+                pp += n1;
+                pq += n1;
+                pn -= n1;
             }
         }
+
         // ---- stage b is free again: refill it with block j+2, rotate the metadata pipeline
         __syncwarp();
         m0 = m1;
         m1 = m2;
-        rg_cur = rg_nxt;
+        rg = rg_nxt;
         if (j + 2 < nblk) rg_nxt = issue_block(j + 2, m1, b);
         m2 = load_meta(j + 3);
     }
-    if (cnt) flush_counters<G>(vc, cnt, fbuf, (uint64_t)ch.col_base + win_lo, cv.counts, cv.stride, lane);
+    if (cnt) do_flush();
 }
 
 // Cross-check variant: one thread per read, one RED per base.  Same inputs, same planes.

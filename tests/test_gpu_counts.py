@@ -53,10 +53,10 @@ def test_fuzz_vs_oracle(eng, mbq, variant):
         assert np.array_equal(got, oracle_counts(b, 700, mbq)), seed
 
 
-@pytest.mark.parametrize("read_len,n_reads", [(150, 6000), (400, 4000), (1000, 1500), (5000, 300)])
+@pytest.mark.parametrize("read_len,n_reads", [(150, 6000), (400, 4000), (700, 2500), (1000, 1500), (5000, 300)])
 @pytest.mark.parametrize("mbq", [0, 20])
 def test_group_widths_vs_oracle(eng, read_len, n_reads, mbq):
-    """150 bp -> 8-lane groups, 400 bp -> 16, >= 500 bp -> 32; 5 kb reads span several windows."""
+    """150 bp -> 4-lane read slots, 400 bp -> 8, 700 bp -> 16, >= 900 bp -> 32; 5 kb reads span several windows."""
     rec = synth.uniform_short_read_sample(seed=read_len, ref_len=20000, n_reads=n_reads, read_len=read_len, ref_name="x")
     b = select_reads(rec, 0, 0)
     got = gpu_counts(eng, b, [20000], mbq)[0]
