@@ -291,18 +291,50 @@ static int pick_group_width(const bc_batch *b, uint64_t total_words)
     return 32;
 }
 
-// Split every slot's reads into per-warp chunks.  Returns the number of chunks.
-static uint32_t build_chunks(bc_handle *h, const uint32_t *ref_read_off, uint32_t n_reads, std::vector<Chunk> &out)
+template <int G, bool OK>
+static int k1_prepare(size_t *smem, int *ctas_per_sm)
+{
+    *smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<G, OK>();
+    cudaError_t e = cudaFuncSetAttribute(k1_count_tiled<G, OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k1_count_tiled<G, OK>, kK1Threads, *smem);
+}
+
+// Warps of the chosen K1 instance that are resident on the whole GPU at once.
+static int k1_resident_warps(bc_handle *h, int G, bool ok, uint32_t *out)
+{
+    size_t smem = 0;
+    int ctas = 0, e = 0;
+#define K1_PREP(GG) e = ok ? k1_prepare<GG, true>(&smem, &ctas) : k1_prepare<GG, false>(&smem, &ctas)
+    if (G == 4) K1_PREP(4);
+    else if (G == 8) K1_PREP(8);
+    else if (G == 16) K1_PREP(16);
+    else K1_PREP(32);
+#undef K1_PREP
+    if (e != 0) {
+        h->err = std::string("k1 occupancy query: ") + cudaGetErrorString((cudaError_t)e);
+        return BC_ERR_CUDA;
+    }
+    *out = (uint32_t)std::max(1, ctas) * kK1WarpsPerCta * (uint32_t)h->sm_count;
+    return BC_OK;
+}
+
+// Split every slot's reads into per-warp chunks: about one chunk per resident warp (a single
+// full wave), because every chunk pays one counter flush at its end.
+static uint32_t build_chunks(bc_handle *h, const uint32_t *ref_read_off, uint32_t n_reads, uint32_t target_warps,
+                             std::vector<Chunk> &out)
 {
     out.clear();
-    const uint64_t target_warps = (uint64_t)h->sm_count * 32u;
-    uint32_t per = (uint32_t)std::max<uint64_t>(16, (n_reads + target_warps - 1) / target_warps);
-    per = std::min<uint32_t>(per, 4096);
+    uint32_t per = (uint32_t)std::max<uint64_t>(64, ((uint64_t)n_reads + target_warps - 1) / target_warps);
     for (uint32_t r = 0; r < h->n_refs; r++) {
-        for (uint32_t a = ref_read_off[r]; a < ref_read_off[r + 1]; a += per) {
+        const uint32_t n_r = ref_read_off[r + 1] - ref_read_off[r];
+        if (n_r == 0) continue;
+        const uint32_t pieces = (n_r + per - 1) / per;
+        const uint32_t each = (n_r + pieces - 1) / pieces;          // equal shares within the slot
+        for (uint32_t a = ref_read_off[r]; a < ref_read_off[r + 1]; a += each) {
             Chunk c;
             c.read_begin = a;
-            c.read_end = std::min(a + per, ref_read_off[r + 1]);
+            c.read_end = std::min(a + each, ref_read_off[r + 1]);
             c.col_base = h->col_base[r];
             c.ref_len = h->ref_len[r];
             out.push_back(c);
@@ -360,11 +392,9 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     do {                                                                                                       \
         if (ok) {                                                                                              \
             const size_t smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<GG, true>();                       \
-            CU(h, cudaFuncSetAttribute(k1_count_tiled<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             k1_count_tiled<GG, true><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb);  \
         } else {                                                                                               \
             const size_t smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<GG, false>();                      \
-            CU(h, cudaFuncSetAttribute(k1_count_tiled<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             k1_count_tiled<GG, false><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb); \
         }                                                                                                      \
     } while (0)
@@ -421,7 +451,10 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
     mean_words = (uint32_t)((n_words + n - 1) / n);
 
     std::vector<Chunk> chunks;
-    n_chunks = build_chunks(h, b->ref_read_off, n, chunks);
+    uint32_t target_warps = 0;
+    int rc0 = k1_resident_warps(h, G, b->okmask != nullptr, &target_warps);
+    if (rc0) return rc0;
+    n_chunks = build_chunks(h, b->ref_read_off, n, target_warps, chunks);
     if (n_chunks > st.h_chunks_cap) {
         if (st.h_chunks) CU(h, cudaFreeHost(st.h_chunks));
         st.h_chunks = nullptr;

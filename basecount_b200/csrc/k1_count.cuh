@@ -142,7 +142,7 @@ template <int G, bool HAS_OK>
 __host__ __device__ constexpr uint32_t k1_warp_smem_bytes()
 {
     return kStages * (kSeqCap + kSeqPad) * 8u + (HAS_OK ? kStages * (kSeqCap + kSeqPad) * 4u : 0u) +
-           kStages * kCigCap * 4u + /* flush row: 32*W*G columns x u16 */ 64u * kW * G + /* order lists */ 64u +
+           kStages * kCigCap * 4u + /* flush rows: 4 letters x 32*W*G columns x u16 */ 256u * kW * G + /* order lists */ 64u +
            /* mbarriers */ 64u;
 }
 
@@ -156,30 +156,46 @@ struct StagedRange {          // what one pipeline stage holds (warp-uniform)
 
 // Convert the warp's vertical counters to integers and add them to the HBM planes.
 // Byte-packed extraction per slot, widened to 16 bit before the S read slots are summed
-// (so each slot may hold up to 255), staged in shared memory one letter at a time and
-// written with coalesced RED.ADD (128 B per warp instruction).
+// (so each slot may hold up to 255), staged in shared memory and written with coalesced
+// RED.ADD (128 B per warp instruction).  The loop over the shift amount jj is deliberately
+// NOT unrolled: registers stay statically indexed while the code stays a few hundred
+// instructions (a fully unrolled flush inlined at every site made the kernel > 500 KB and
+// instruction-fetch bound).
+//   frow: 4 letters x (32*kW*G columns) uint16
 template <int G>
 __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt, uint16_t *frow, uint64_t win_col,
                                                uint32_t *__restrict__ counts, uint64_t stride, int lane)
 {
     constexpr int S = 32 / G;
+    constexpr int kCols = 32 * kW * G;
     const int slot = lane / G, wl = lane % G;
+    // pendings that hold no carry are zeroed so the loop below needs no cnt tests
 #pragma unroll
-    for (int b = 0; b < 4; b++) {
+    for (int w = 0; w < kW; w++) {
 #pragma unroll
-        for (int w = 0; w < kW; w++) {
-            uint16_t *dst = frow + (kW * wl + w) * 32;
+        for (int b = 0; b < 4; b++) {
+            if (!(cnt & 1u)) vc[w].pend[b][0] = 0u;
+            if (!(cnt & 2u)) vc[w].pend[b][1] = 0u;
+            if (!(cnt & 4u)) vc[w].pend[b][2] = 0u;
+        }
+    }
+    const bool high = cnt >= 16u;                         // planes 4..7 can only be set after 16 inputs
+#pragma unroll 1
+    for (int jj = 0; jj < 8; jj++) {
+        const bool mine = (jj % S) == slot;
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) {
-                uint32_t acc = 0;                     // byte t = count of column jj + 8t (this slot only)
+        for (int b = 0; b < 4; b++) {
 #pragma unroll
-                for (int k = 0; k < kNB; k++) {
-                    if ((cnt >> k) == 0u) break;      // uniform: higher planes are empty
-                    acc += ((vc[w].pl[b][k] >> jj) & 0x01010101u) << k;
+            for (int w = 0; w < kW; w++) {
+                uint32_t acc = 0;                         // byte t = count of column jj + 8t (this slot only)
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc += ((vc[w].pl[b][k] >> jj) & 0x01010101u) << k;
+                if (high) {
+#pragma unroll
+                    for (int k = 4; k < kNB; k++) acc += ((vc[w].pl[b][k] >> jj) & 0x01010101u) << k;
                 }
-                if (cnt & 1u) acc += (vc[w].pend[b][0] >> jj) & 0x01010101u;
-                if (cnt & 2u) acc += ((vc[w].pend[b][1] >> jj) & 0x01010101u) << 1;
-                if (cnt & 4u) acc += ((vc[w].pend[b][2] >> jj) & 0x01010101u) << 2;
+#pragma unroll
+                for (int k = 0; k < 3; k++) acc += ((vc[w].pend[b][k] >> jj) & 0x01010101u) << k;
                 uint32_t ev = acc & 0x00FF00FFu;          // columns jj, jj+16
                 uint32_t od = (acc >> 8) & 0x00FF00FFu;   // columns jj+8, jj+24
 #pragma unroll
@@ -187,22 +203,28 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
                     ev += __shfl_xor_sync(kFull, ev, d);
                     od += __shfl_xor_sync(kFull, od, d);
                 }
-                if ((jj % S) == slot) {
-                    dst[jj] = (uint16_t)ev;
-                    dst[jj + 16] = (uint16_t)(ev >> 16);
-                    dst[jj + 8] = (uint16_t)od;
-                    dst[jj + 24] = (uint16_t)(od >> 16);
+                if (mine) {
+                    uint16_t *dst = frow + b * kCols + (kW * wl + w) * 32 + jj;
+                    dst[0] = (uint16_t)ev;
+                    dst[16] = (uint16_t)(ev >> 16);
+                    dst[8] = (uint16_t)od;
+                    dst[24] = (uint16_t)(od >> 16);
                 }
             }
         }
-        __syncwarp();
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int b = 0; b < 4; b++) {
         uint32_t *plane = counts + (uint64_t)b * stride + win_col;
+        const uint16_t *row = frow + b * kCols;
+#pragma unroll 4
         for (int w = 0; w < kW * G; w++) {
-            const uint32_t val = frow[32 * w + lane];
+            const uint32_t val = row[32 * w + lane];
             if (val) atomicAdd(plane + 32 * w + lane, val);     // RED.ADD, 128 B per warp instruction
         }
-        __syncwarp();
     }
+    __syncwarp();
 #pragma unroll
     for (int w = 0; w < kW; w++) vc[w].clear();
 }
@@ -282,7 +304,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u);
     uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u + (HAS_OK ? kStages * kStageWords * 4u : 0u));
     uint16_t *frow = reinterpret_cast<uint16_t *>(cig_buf + kStages * kCigCap);
-    uint8_t *order1 = reinterpret_cast<uint8_t *>(frow) + 64u * kW * G;
+    uint8_t *order1 = reinterpret_cast<uint8_t *>(frow) + 256u * kW * G;
     uint8_t *order2 = order1 + 32;
     uint64_t *bars = reinterpret_cast<uint64_t *>(order2 + 32);
 
@@ -357,10 +379,10 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         flush_counters<G>(vc, cnt, frow, col0 + win_lo, cv.counts, cv.stride, lane);
         cnt = 0;
     };
-    auto accumulate = [&](uint32_t (&x)[kW][4]) {
+    auto accumulate = [&](uint32_t (&x)[kW][4]) {          // callers flush when cnt reaches kCntMax
 #pragma unroll
         for (int w = 0; w < kW; w++) vc[w].add(x[w], cnt);
-        if (++cnt == kCntMax) do_flush();
+        ++cnt;
     };
 
     for (uint32_t j = 0; j < nblk; j++) {
@@ -405,16 +427,17 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             const bool fits = have && win_valid && pp >= win_lo && (pp - win_lo) <= kWin - pn;
             const uint32_t have_mask = __ballot_sync(kFull, have);
             const uint32_t fit_mask = __ballot_sync(kFull, fits);
-            if (fit_mask != have_mask) {
+            if (fit_mask == 0u || cnt == kCntMax) {                  // the one flush site of this loop
+                if (cnt) do_flush();
                 if (fit_mask == 0u) {                                // nobody fits: move the window
-                    if (cnt) do_flush();
                     win_lo = __reduce_min_sync(kFull, have ? pp : 0xFFFFFFFFu) & ~31u;
                     win_valid = true;
-                    continue;
                 }
-                // reads that do not fit this window are left to the general loop below
-                rest_mask |= __reduce_or_sync(kFull, (have && !fits && wl == 0) ? (1u << src) : 0u);
+                continue;
             }
+            // reads that do not fit this window are left to the general loop below
+            if (fit_mask != have_mask)
+                rest_mask |= __reduce_or_sync(kFull, (have && !fits && wl == 0) ? (1u << src) : 0u);
             uint32_t x[kW][4] = {};
             if (fits) piece_words<G, HAS_OK>(x, pp, 0u, pn, win_lo, wl, sq, okb, sidx, bv, 0u, 0u);
             accumulate(x);
@@ -491,11 +514,14 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 // D: which pieces can go into the current window?
                 const bool fits = active && win_valid && pp >= win_lo && (pp - win_lo) < kWin &&
                                   (pn <= kWin - (pp - win_lo) || pn > kMaxFit);
-                if (__ballot_sync(kFull, fits) == 0u) {
-                    if (__ballot_sync(kFull, active) == 0u) continue;        // still walking ops / fetching
+                const uint32_t fit_any = __ballot_sync(kFull, fits);
+                if (fit_any == 0u || cnt == kCntMax) {                       // the one flush site of this loop
+                    if (fit_any == 0u && __ballot_sync(kFull, active) == 0u) continue;   // still walking ops / fetching
                     if (cnt) do_flush();
-                    win_lo = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu) & ~31u;
-                    win_valid = true;
+                    if (fit_any == 0u) {
+                        win_lo = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu) & ~31u;
+                        win_valid = true;
+                    }
                     continue;
                 }
                 // E: masked words of the fitting pieces, added to the vertical counters
