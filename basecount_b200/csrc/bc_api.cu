@@ -759,6 +759,17 @@ int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, co
     return BC_OK;
 }
 
+int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len)
+{
+    if (!h) return BC_ERR_ARG;
+    if (ref >= h->n_refs || new_len > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "bc_truncate: out of range");
+    CU(h, cudaSetDevice(h->device));
+    h->ref_len[ref] = new_len;
+    CU(h, cudaMemcpyAsync(h->d_ref_len + ref, &h->ref_len[ref], sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
 // ------------------------------------------------------------------ instrumentation
 int bc_timer_start(bc_handle *h)
 {

@@ -137,13 +137,16 @@ constexpr uint32_t kSeqPad = 4;       // guard words so clamped out-of-piece loa
 constexpr uint32_t kCigCap = 256;     // staged CIGAR words per stage (1 KB)
 constexpr int kStages = 2;
 constexpr uint32_t kCntMax = 255u;    // per-slot count limit of the 8-plane counters
+constexpr uint32_t kFlushStride = 34; // uint16 per staged window word (32 + 2 pad: conflict-free stores)
+constexpr uint32_t kRing = 128;       // piece ring entries (uint4 each)
+constexpr uint32_t kLaneSkipMax = 256; // longest D/N run a single lane adds itself
 
 template <int G, bool HAS_OK>
 __host__ __device__ constexpr uint32_t k1_warp_smem_bytes()
 {
     return kStages * (kSeqCap + kSeqPad) * 8u + (HAS_OK ? kStages * (kSeqCap + kSeqPad) * 4u : 0u) +
-           kStages * kCigCap * 4u + /* flush rows: 4 letters x 32*W*G columns x u16 */ 256u * kW * G + /* order lists */ 64u +
-           /* mbarriers */ 64u;
+           kStages * kCigCap * 4u + /* flush rows: 4 letters x (kW*G words x 34) u16 */ 4u * kW * G * kFlushStride * 2u +
+           /* piece ring */ kRing * 16u + /* order list */ 64u + /* mbarriers */ 64u;
 }
 
 struct BlockMeta {            // lane l holds the metadata of read (block_first + l)
@@ -161,13 +164,13 @@ struct StagedRange {          // what one pipeline stage holds (warp-uniform)
 // NOT unrolled: registers stay statically indexed while the code stays a few hundred
 // instructions (a fully unrolled flush inlined at every site made the kernel > 500 KB and
 // instruction-fetch bound).
-//   frow: 4 letters x (32*kW*G columns) uint16
+//   frow: 4 letters x (kW*G window words x kFlushStride) uint16
 template <int G>
 __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt, uint16_t *frow, uint64_t win_col,
                                                uint32_t *__restrict__ counts, uint64_t stride, int lane)
 {
     constexpr int S = 32 / G;
-    constexpr int kCols = 32 * kW * G;
+    constexpr int kCols = (int)kFlushStride * kW * G;
     const int slot = lane / G, wl = lane % G;
     // pendings that hold no carry are zeroed so the loop below needs no cnt tests
 #pragma unroll
@@ -204,7 +207,7 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
                     od += __shfl_xor_sync(kFull, od, d);
                 }
                 if (mine) {
-                    uint16_t *dst = frow + b * kCols + (kW * wl + w) * 32 + jj;
+                    uint16_t *dst = frow + b * kCols + (kW * wl + w) * (int)kFlushStride + jj;
                     dst[0] = (uint16_t)ev;
                     dst[16] = (uint16_t)(ev >> 16);
                     dst[8] = (uint16_t)od;
@@ -220,7 +223,7 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
         const uint16_t *row = frow + b * kCols;
 #pragma unroll 4
         for (int w = 0; w < kW * G; w++) {
-            const uint32_t val = row[32 * w + lane];
+            const uint32_t val = row[(int)kFlushStride * w + lane];
             if (val) atomicAdd(plane + 32 * w + lane, val);     // RED.ADD, 128 B per warp instruction
         }
     }
@@ -230,29 +233,34 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
 }
 
 // Masked one-hot words of one piece for this lane's kW window words.
-//   pp / pq / n1 : reference start, read start and length of the (window-clipped) piece
-//   sidx         : stage index of the read's word 0 (>= kSeqPad) when the read is fully staged, else -1
+//   pp / n1 : reference start and length of the (window-clipped) piece
+//   sbit    : bit index, in the stage buffer, of the piece's first base (fully staged reads);
+//             for unstaged reads pass sbit < 0 and (pq, wbase, nwords) for the global path.
 template <int G, bool HAS_OK>
-__device__ __forceinline__ void piece_words(uint32_t (&x)[kW][4], uint32_t pp, uint32_t pq, uint32_t n1, uint32_t win_lo,
-                                            int wl, const uint2 *__restrict__ sq, const uint32_t *__restrict__ okb,
-                                            int sidx, const BatchView &bv, uint32_t wbase, uint32_t nwords)
+__device__ __forceinline__ void piece_words(uint32_t (&x)[kW][4], uint32_t pp, uint32_t n1, uint32_t win_lo, int wl,
+                                            const uint2 *__restrict__ sq, const uint32_t *__restrict__ okb, int sbit,
+                                            const BatchView &bv, uint32_t pq, uint32_t wbase, uint32_t nwords)
 {
     const int rel = (int)(win_lo + 32u * kW * (uint32_t)wl) - (int)pp;   // piece offset of this lane's column 0
     const int lo_off = max(-rel, 0), hi_off = min((int)n1 - rel, 32 * kW);
     if (lo_off >= hi_off) return;                                      // x stays 0
-    const int bit = (int)pq + rel;                                     // read bit index of the lane's column 0
-    const int k = bit >> 5, sh = bit & 31;
     uint2 r[kW + 1];
     uint32_t o[kW + 1];
-    if (sidx >= 0) {
+    int sh;
+    if (sbit >= 0) {
         // Fully staged: out-of-piece words are masked away below, so only memory safety matters.
-        const int base = min(max(sidx + k, 0), (int)(kSeqCap + kSeqPad) - (kW + 1));
+        const int bit = sbit + rel;
+        sh = bit & 31;
+        const int base = min(max(bit >> 5, 0), (int)(kSeqCap + kSeqPad) - (kW + 1));
 #pragma unroll
         for (int i = 0; i <= kW; i++) {
             r[i] = sq[base + i];
             if (HAS_OK) o[i] = okb[base + i];
         }
     } else {
+        const int bit = (int)pq + rel;                                 // read bit index of the lane's column 0
+        const int k = bit >> 5;
+        sh = bit & 31;
 #pragma unroll
         for (int i = 0; i <= kW; i++) {
             r[i] = make_uint2(0u, 0u);
@@ -304,9 +312,9 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u);
     uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u + (HAS_OK ? kStages * kStageWords * 4u : 0u));
     uint16_t *frow = reinterpret_cast<uint16_t *>(cig_buf + kStages * kCigCap);
-    uint8_t *order1 = reinterpret_cast<uint8_t *>(frow) + 256u * kW * G;
-    uint8_t *order2 = order1 + 32;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(order2 + 32);
+    uint4 *ring = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(frow) + 4u * kW * G * kFlushStride * 2u);
+    uint8_t *order2 = reinterpret_cast<uint8_t *>(ring + kRing);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(order2 + 64);
 
     const int slot = lane / G, wl = lane % G;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -368,7 +376,8 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     if (nblk > 1) rg_nxt = issue_block(1, m1, 1);
     uint32_t parity = 0;                            // bit b: phase to wait for on stage b
 
-    // warp-uniform window + counter state (persist across blocks)
+    // warp-uniform window + counter + piece-ring state (persist across blocks)
+    uint32_t ring_head = 0, ring_tail = 0;
     uint32_t win_lo = 0, cnt = 0;
     bool win_valid = false;
     VCounters vc[kW];
@@ -394,54 +403,123 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         const uint32_t *cg = cig_buf + b * kCigCap;
         const uint32_t nvalid = min(rpb, re - (rb + j * rpb));
 
-        // ---- per-read classification, one read per lane
+        // ---- per-read classification, one read per lane: walk the read's own CIGAR and emit up
+        //      to two M/=/X pieces (adjacent match ops merge) into the piece ring; anything
+        //      bigger (more pieces, long pieces or skips, unstaged reads) goes to the general loop.
         const bool valid = (uint32_t)lane < nvalid;
-        uint32_t cig0 = 0u;
-        if (valid && m0.ncig) {
-            const uint32_t ci = m0.cbase - rg.c_lo;
-            cig0 = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + m0.cbase);
-        }
         const bool staged = valid && (m0.wbase - rg.s_lo) <= rg.s_n && (m0.wbase - rg.s_lo) + m0.nwords <= rg.s_n;
         const int my_sidx = staged ? (int)(m0.wbase - rg.s_lo + kSeqPad) : -1;
-        uint32_t p_len = cig0 >> 4;
-        const bool one_match = valid && m0.ncig == 1u && op_is_match(cig0 & 0xFu);
-        bool simple = one_match && staged && p_len <= kMaxFit;
-        if (simple && p_len && (m0.start >= ref_len || p_len > ref_len - m0.start)) {   // would index past the matrix
-            cv.status[kStatMaybeOverflow] = 1u;                      // exactness decided by k1_check_overflow
-            p_len = m0.start < ref_len ? ref_len - m0.start : 0u;
+        uint32_t pc_pp[2] = {0u, 0u}, pc_pq[2] = {0u, 0u}, pc_pn[2] = {0u, 0u};
+        uint32_t n_pc = 0, sk_pos = 0, sk_len = 0;
+        bool complex_read = valid && m0.ncig && !staged;
+        if (valid && m0.ncig && staged) {
+            uint32_t rpos = m0.start, qpos = 0;
+            bool open = false;                                           // last op was a match op (merge candidates)
+            for (uint32_t c = m0.cbase; c < m0.cbase + m0.ncig; c++) {
+                const uint32_t ci = c - rg.c_lo;
+                const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + c);
+                const uint32_t op = cw & 0xFu, len = cw >> 4;
+                if (op_is_match(op)) {
+                    if (len) {
+                        if (open) {
+                            pc_pn[n_pc - 1] = sat_add(pc_pn[n_pc - 1], len);
+                        } else if (n_pc < 2) {
+                            pc_pp[n_pc] = rpos;
+                            pc_pq[n_pc] = qpos;
+                            pc_pn[n_pc] = len;
+                            n_pc++;
+                            open = true;
+                        } else {
+                            complex_read = true;
+                            break;
+                        }
+                    }
+                    rpos = sat_add(rpos, len);
+                    qpos = sat_add(qpos, len);
+                } else if (op == 1u) {
+                    qpos = sat_add(qpos, len);
+                    open = open && len == 0u;
+                } else if (op_is_refskip(op)) {
+                    if (len) {
+                        if (sk_len || len > kLaneSkipMax) {
+                            complex_read = true;
+                            break;
+                        }
+                        sk_pos = rpos;
+                        sk_len = len;
+                        open = false;
+                    }
+                    rpos = sat_add(rpos, len);
+                }
+            }
+            if (pc_pn[0] > kMaxFit || pc_pn[1] > kMaxFit) complex_read = true;
         }
-        const uint32_t simple_mask = __ballot_sync(kFull, simple && p_len);
-        uint32_t rest_mask = __ballot_sync(kFull, valid && m0.ncig && !simple);
-        if ((simple_mask >> lane) & 1u) order1[__popc(simple_mask & lt_mask)] = (uint8_t)lane;
+        if (complex_read) n_pc = 0;
+        if (valid && !complex_read) {
+            // clip to the reference (count.cpp .at()): exactness decided by k1_check_overflow
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (pc_pn[i] && (pc_pp[i] >= ref_len || pc_pn[i] > ref_len - pc_pp[i])) {
+                    cv.status[kStatMaybeOverflow] = 1u;
+                    pc_pn[i] = pc_pp[i] < ref_len ? ref_len - pc_pp[i] : 0u;
+                }
+            }
+            if (sk_len) {                                                // deletion / skip, count.cpp:80-87
+                const uint32_t lim = sk_pos < ref_len ? min(sk_len, ref_len - sk_pos) : 0u;
+                if (lim < sk_len) cv.status[kStatIndexError] = 1u;
+                uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + col0 + sk_pos;
+                for (uint32_t t = 0; t < lim; t++) atomicAdd(ds + t, 1u);
+            }
+        }
+        const uint32_t has1 = __ballot_sync(kFull, n_pc >= 1u && pc_pn[0]);
+        const uint32_t has2 = __ballot_sync(kFull, n_pc >= 2u && pc_pn[1]);
+        uint32_t rest_mask = __ballot_sync(kFull, complex_read);
+        {
+            uint32_t at = ring_tail + __popc(has1 & lt_mask) + __popc(has2 & lt_mask);
+            if ((has1 >> lane) & 1u) {
+                ring[at & (kRing - 1)] = make_uint4(pc_pp[0], pc_pn[0], (uint32_t)(my_sidx * 32) + pc_pq[0], 0u);
+                at++;
+            }
+            if ((has2 >> lane) & 1u)
+                ring[at & (kRing - 1)] = make_uint4(pc_pp[1], pc_pn[1], (uint32_t)(my_sidx * 32) + pc_pq[1], 0u);
+            ring_tail += __popc(has1) + __popc(has2);
+        }
         __syncwarp();
 
-        // ---- fast loop: S single-run reads per iteration
-        const uint32_t n_simple = __popc(simple_mask);
-        for (uint32_t t = 0; t * S < n_simple;) {
-            const uint32_t kk = t * S + slot;
-            const bool have = kk < n_simple;
-            const int src = have ? (int)order1[kk] : 0;
-            const uint32_t pp = __shfl_sync(kFull, m0.start, src);
-            const uint32_t pn = __shfl_sync(kFull, p_len, src);
-            const int sidx = __shfl_sync(kFull, my_sidx, src);
-            const bool fits = have && win_valid && pp >= win_lo && (pp - win_lo) <= kWin - pn;
-            const uint32_t have_mask = __ballot_sync(kFull, have);
-            const uint32_t fit_mask = __ballot_sync(kFull, fits);
-            if (fit_mask == 0u || cnt == kCntMax) {                  // the one flush site of this loop
-                if (cnt) do_flush();
-                if (fit_mask == 0u) {                                // nobody fits: move the window
-                    win_lo = __reduce_min_sync(kFull, have ? pp : 0xFFFFFFFFu) & ~31u;
-                    win_valid = true;
+        // ---- fast loop: S pieces per iteration straight from the ring; rare events (flush,
+        //      window move) are handled outside the tight inner loop
+        for (;;) {
+            uint32_t have_mask = 0u, fit_mask = 0u, low_pp = 0xFFFFFFFFu;
+            while (ring_head != ring_tail) {
+                const uint32_t kk = ring_head + (uint32_t)slot;
+                const bool have = (int)(ring_tail - kk) > 0;
+                const uint32_t adv = min((uint32_t)S, ring_tail - ring_head);   // entries consumed this iteration
+                uint4 e = make_uint4(0u, 0u, 0u, 0u);
+                if (have) e = ring[kk & (kRing - 1)];
+                const bool fits = have && win_valid && e.x >= win_lo && (e.x - win_lo) <= kWin - e.y;
+                have_mask = __ballot_sync(kFull, have);
+                fit_mask = __ballot_sync(kFull, fits);
+                if (fit_mask == 0u || cnt == kCntMax) {
+                    low_pp = have ? e.x : 0xFFFFFFFFu;
+                    break;
                 }
-                continue;
+                if (fit_mask != have_mask) {                         // re-queue pieces that wait for a window move
+                    const uint32_t unfit = __ballot_sync(kFull, have && !fits && wl == 0);
+                    if (have && !fits && wl == 0) ring[(ring_tail + __popc(unfit & lt_mask)) & (kRing - 1)] = e;
+                    ring_tail += __popc(unfit);
+                    __syncwarp();
+                }
+                ring_head += adv;
+                uint32_t x[kW][4] = {};
+                if (fits) piece_words<G, HAS_OK>(x, e.x, e.y, win_lo, wl, sq, okb, (int)e.z, bv, 0u, 0u, 0u);
+                accumulate(x);
             }
-            // reads that do not fit this window are left to the general loop below
-            if (fit_mask != have_mask)
-                rest_mask |= __reduce_or_sync(kFull, (have && !fits && wl == 0) ? (1u << src) : 0u);
-            uint32_t x[kW][4] = {};
-            if (fits) piece_words<G, HAS_OK>(x, pp, 0u, pn, win_lo, wl, sq, okb, sidx, bv, 0u, 0u);
-            accumulate(x);
-            t++;
+            if (ring_head == ring_tail) break;
+            if (cnt) do_flush();
+            if (fit_mask == 0u) {                                    // nobody fits: move the window
+                win_lo = __reduce_min_sync(kFull, low_pp) & ~31u;
+                win_valid = true;
+            }
         }
 
         // ---- general loop: CIGAR state machine over the remaining reads of the block
@@ -529,7 +607,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 uint32_t n1 = 0;
                 if (fits) {
                     n1 = min(pn, kWin - (pp - win_lo));
-                    piece_words<G, HAS_OK>(x, pp, pq, n1, win_lo, wl, sq, okb, sidx, bv, wbase, nwords);
+                    piece_words<G, HAS_OK>(x, pp, n1, win_lo, wl, sq, okb, sidx >= 0 ? sidx * 32 + (int)pq : -1, bv, pq, wbase, nwords);
                 }
                 accumulate(x);
                 pp += n1;

@@ -141,6 +141,10 @@ class Engine:
     def halo_add(self, ref: int, col_lo: int, n_cols: int, dev_ptr: int):
         _lib.check(self._h, self._L.bc_halo_add(self._h, ref, col_lo, n_cols, ctypes.c_void_p(dev_ptr)))
 
+    def truncate(self, ref: int, new_len: int):
+        _lib.check(self._h, self._L.bc_truncate(self._h, ref, new_len))
+        self.ref_lens[ref] = int(new_len)
+
     # -- instrumentation
     def timer_start(self):
         _lib.check(self._h, self._L.bc_timer_start(self._h))
