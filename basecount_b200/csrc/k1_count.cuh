@@ -36,56 +36,53 @@ __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b)
     return t < a ? 0xFFFFFFFFu : t;
 }
 
-// Vertical counters of one lane: for each of A,C,G,T, kNB bit planes over the lane's
-// 32 columns, plus the not-yet-paired carries of the first three adder levels.
+// Vertical counters of one lane: for each of A,C,G,T, kNB bit planes over the lane's 32
+// columns (Harley-Seal style carry-save adders).  Inputs arrive two at a time, so the
+// weight-1 adder consumes both directly; pend[b][0] / pend[b][1] hold the not-yet-paired
+// carries of weight 2 and 4.
 struct VCounters {
     uint32_t pl[4][kNB];
-    uint32_t pend[4][3];
+    uint32_t pend[4][2];
     __device__ __forceinline__ void clear()
     {
 #pragma unroll
         for (int b = 0; b < 4; b++) {
 #pragma unroll
             for (int k = 0; k < kNB; k++) pl[b][k] = 0;
-#pragma unroll
-            for (int k = 0; k < 3; k++) pend[b][k] = 0;
+            pend[b][0] = 0;
+            pend[b][1] = 0;
         }
     }
-    // Add one 32-column mask per letter.  `cnt` = inputs added so far (warp-uniform), so
-    // every branch below is uniform.
-    __device__ __forceinline__ void add(const uint32_t x[4], uint32_t cnt)
+    // Add two 32-column masks per letter.  `cnt` = inputs added so far (even, warp-uniform),
+    // so every branch below is uniform.
+    __device__ __forceinline__ void add2(const uint32_t xa[4], const uint32_t xb[4], uint32_t cnt)
     {
-        if ((cnt & 1u) == 0u) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) pend[b][0] = x[b];
-            return;
-        }
         uint32_t c1[4];
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            c1[b] = maj3(pl[b][0], pend[b][0], x[b]);
-            pl[b][0] ^= pend[b][0] ^ x[b];
+            c1[b] = maj3(pl[b][0], xa[b], xb[b]);
+            pl[b][0] ^= xa[b] ^ xb[b];
         }
         if ((cnt & 2u) == 0u) {
 #pragma unroll
-            for (int b = 0; b < 4; b++) pend[b][1] = c1[b];
+            for (int b = 0; b < 4; b++) pend[b][0] = c1[b];
             return;
         }
         uint32_t c2[4];
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            c2[b] = maj3(pl[b][1], pend[b][1], c1[b]);
-            pl[b][1] ^= pend[b][1] ^ c1[b];
+            c2[b] = maj3(pl[b][1], pend[b][0], c1[b]);
+            pl[b][1] ^= pend[b][0] ^ c1[b];
         }
         if ((cnt & 4u) == 0u) {
 #pragma unroll
-            for (int b = 0; b < 4; b++) pend[b][2] = c2[b];
+            for (int b = 0; b < 4; b++) pend[b][1] = c2[b];
             return;
         }
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            uint32_t c = maj3(pl[b][2], pend[b][2], c2[b]);
-            pl[b][2] ^= pend[b][2] ^ c2[b];
+            uint32_t c = maj3(pl[b][2], pend[b][1], c2[b]);
+            pl[b][2] ^= pend[b][1] ^ c2[b];
 #pragma unroll
             for (int k = 3; k < kNB; k++) {          // ripple the weight-8 carry upwards
                 uint32_t t = pl[b][k] & c;
@@ -136,7 +133,7 @@ constexpr uint32_t kSeqCap = 512;     // staged 64-bit plane words per stage (4 
 constexpr uint32_t kSeqPad = 4;       // guard words so clamped out-of-piece loads stay inside the stage
 constexpr uint32_t kCigCap = 256;     // staged CIGAR words per stage (1 KB)
 constexpr int kStages = 2;
-constexpr uint32_t kCntMax = 255u;    // per-slot count limit of the 8-plane counters
+constexpr uint32_t kCntMax = 254u;    // per-slot count limit of the 8-plane counters (inputs come in pairs)
 constexpr uint32_t kFlushStride = 34; // uint16 per staged window word (32 + 2 pad: conflict-free stores)
 constexpr uint32_t kRing = 128;       // piece ring entries (uint4 each)
 constexpr uint32_t kLaneSkipMax = 256; // longest D/N run a single lane adds itself
@@ -177,9 +174,8 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
     for (int w = 0; w < kW; w++) {
 #pragma unroll
         for (int b = 0; b < 4; b++) {
-            if (!(cnt & 1u)) vc[w].pend[b][0] = 0u;
-            if (!(cnt & 2u)) vc[w].pend[b][1] = 0u;
-            if (!(cnt & 4u)) vc[w].pend[b][2] = 0u;
+            if (!(cnt & 2u)) vc[w].pend[b][0] = 0u;
+            if (!(cnt & 4u)) vc[w].pend[b][1] = 0u;
         }
     }
     const bool high = cnt >= 16u;                         // planes 4..7 can only be set after 16 inputs
@@ -198,7 +194,7 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
                     for (int k = 4; k < kNB; k++) acc += ((vc[w].pl[b][k] >> jj) & 0x01010101u) << k;
                 }
 #pragma unroll
-                for (int k = 0; k < 3; k++) acc += ((vc[w].pend[b][k] >> jj) & 0x01010101u) << k;
+                for (int k = 0; k < 2; k++) acc += ((vc[w].pend[b][k] >> jj) & 0x01010101u) << (k + 1);
                 uint32_t ev = acc & 0x00FF00FFu;          // columns jj, jj+16
                 uint32_t od = (acc >> 8) & 0x00FF00FFu;   // columns jj+8, jj+24
 #pragma unroll
@@ -232,50 +228,41 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
     for (int w = 0; w < kW; w++) vc[w].clear();
 }
 
-// Masked one-hot words of one piece for this lane's kW window words.
-//   pp / n1 : reference start and length of the (window-clipped) piece
-//   sbit    : bit index, in the stage buffer, of the piece's first base (fully staged reads);
-//             for unstaged reads pass sbit < 0 and (pq, wbase, nwords) for the global path.
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
+{
+    uint32_t r;                                    // PTX shl clamps shift amounts above 31 (result 0)
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+// bits [a, e) of a 32-bit word; a, e may lie outside 0..32 (empty if e <= a)
+__device__ __forceinline__ uint32_t bit_range(int a, int e)
+{
+    return shl_clamp(0xFFFFFFFFu, (uint32_t)max(a, 0)) & ~shl_clamp(0xFFFFFFFFu, (uint32_t)max(e, 0));
+}
+
+// Masked one-hot words of one piece for this lane's kW window words (branch-free).
+//   pp / n1 : reference start and length of the (window-clipped) piece; n1 = 0 gives zeros
+//   sbit    : bit index, in the stage buffer, of the piece's first base (read fully staged)
 template <int G, bool HAS_OK>
 __device__ __forceinline__ void piece_words(uint32_t (&x)[kW][4], uint32_t pp, uint32_t n1, uint32_t win_lo, int wl,
-                                            const uint2 *__restrict__ sq, const uint32_t *__restrict__ okb, int sbit,
-                                            const BatchView &bv, uint32_t pq, uint32_t wbase, uint32_t nwords)
+                                            const uint2 *__restrict__ sq, const uint32_t *__restrict__ okb, int sbit)
 {
     const int rel = (int)(win_lo + 32u * kW * (uint32_t)wl) - (int)pp;   // piece offset of this lane's column 0
-    const int lo_off = max(-rel, 0), hi_off = min((int)n1 - rel, 32 * kW);
-    if (lo_off >= hi_off) return;                                      // x stays 0
+    const int bit = sbit + rel;
+    const int sh = bit & 31;
+    // Out-of-piece words are masked away below, so only memory safety matters for the index.
+    const int base = min(max(bit >> 5, 0), (int)(kSeqCap + kSeqPad) - (kW + 1));
     uint2 r[kW + 1];
     uint32_t o[kW + 1];
-    int sh;
-    if (sbit >= 0) {
-        // Fully staged: out-of-piece words are masked away below, so only memory safety matters.
-        const int bit = sbit + rel;
-        sh = bit & 31;
-        const int base = min(max(bit >> 5, 0), (int)(kSeqCap + kSeqPad) - (kW + 1));
 #pragma unroll
-        for (int i = 0; i <= kW; i++) {
-            r[i] = sq[base + i];
-            if (HAS_OK) o[i] = okb[base + i];
-        }
-    } else {
-        const int bit = (int)pq + rel;                                 // read bit index of the lane's column 0
-        const int k = bit >> 5;
-        sh = bit & 31;
-#pragma unroll
-        for (int i = 0; i <= kW; i++) {
-            r[i] = make_uint2(0u, 0u);
-            o[i] = 0u;
-            if (k + i >= 0 && (uint32_t)(k + i) < nwords) {
-                r[i] = __ldg(bv.planes + wbase + (uint32_t)(k + i));
-                if (HAS_OK) o[i] = __ldg(bv.okmask + wbase + (uint32_t)(k + i));
-            }
-        }
+    for (int i = 0; i <= kW; i++) {
+        r[i] = sq[base + i];
+        if (HAS_OK) o[i] = okb[base + i];
     }
 #pragma unroll
     for (int w = 0; w < kW; w++) {
-        const int a = min(max(lo_off - 32 * w, 0), 32), e = min(max(hi_off - 32 * w, 0), 32);
-        uint32_t m = 0u;
-        if (a < e) m = (e >= 32 ? 0xFFFFFFFFu : ((1u << e) - 1u)) & (0xFFFFFFFFu << a);
+        // columns of word w cover piece offsets rel + 32w .. rel + 32w + 31; valid offsets are [0, n1)
+        uint32_t m = bit_range(-rel - 32 * w, (int)n1 - rel - 32 * w);
         if (HAS_OK) m &= __funnelshift_r(o[w], o[w + 1], sh);
         const uint32_t lo = __funnelshift_r(r[w].x, r[w + 1].x, sh);
         const uint32_t hi = __funnelshift_r(r[w].y, r[w + 1].y, sh);
@@ -283,6 +270,38 @@ __device__ __forceinline__ void piece_words(uint32_t (&x)[kW][4], uint32_t pp, u
         x[w][1] = ~hi & lo & m;                                        // C
         x[w][2] = hi & ~lo & m;                                        // G
         x[w][3] = hi & lo & m;                                         // T
+    }
+}
+
+// Same, for reads that are not (fully) staged: bounds-checked loads from HBM.
+template <int G, bool HAS_OK>
+__device__ __forceinline__ void piece_words_global(uint32_t (&x)[kW][4], uint32_t pp, uint32_t n1, uint32_t win_lo, int wl,
+                                                   const BatchView &bv, uint32_t pq, uint32_t wbase, uint32_t nwords)
+{
+    const int rel = (int)(win_lo + 32u * kW * (uint32_t)wl) - (int)pp;
+    const int bit = (int)pq + rel;                                     // read bit index of the lane's column 0
+    const int k = bit >> 5, sh = bit & 31;
+    uint2 r[kW + 1];
+    uint32_t o[kW + 1];
+#pragma unroll
+    for (int i = 0; i <= kW; i++) {
+        r[i] = make_uint2(0u, 0u);
+        o[i] = 0u;
+        if (n1 && k + i >= 0 && (uint32_t)(k + i) < nwords) {
+            r[i] = __ldg(bv.planes + wbase + (uint32_t)(k + i));
+            if (HAS_OK) o[i] = __ldg(bv.okmask + wbase + (uint32_t)(k + i));
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+        uint32_t m = bit_range(-rel - 32 * w, (int)n1 - rel - 32 * w);
+        if (HAS_OK) m &= __funnelshift_r(o[w], o[w + 1], sh);
+        const uint32_t lo = __funnelshift_r(r[w].x, r[w + 1].x, sh);
+        const uint32_t hi = __funnelshift_r(r[w].y, r[w + 1].y, sh);
+        x[w][0] = ~hi & ~lo & m;
+        x[w][1] = ~hi & lo & m;
+        x[w][2] = hi & ~lo & m;
+        x[w][3] = hi & lo & m;
     }
 }
 
@@ -388,10 +407,10 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         flush_counters<G>(vc, cnt, frow, col0 + win_lo, cv.counts, cv.stride, lane);
         cnt = 0;
     };
-    auto accumulate = [&](uint32_t (&x)[kW][4]) {          // callers flush when cnt reaches kCntMax
+    auto accumulate2 = [&](uint32_t (&xa)[kW][4], uint32_t (&xb)[kW][4]) {   // callers flush at kCntMax
 #pragma unroll
-        for (int w = 0; w < kW; w++) vc[w].add(x[w], cnt);
-        ++cnt;
+        for (int w = 0; w < kW; w++) vc[w].add2(xa[w], xb[w], cnt);
+        cnt += 2;
     };
 
     for (uint32_t j = 0; j < nblk; j++) {
@@ -486,37 +505,42 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         }
         __syncwarp();
 
-        // ---- fast loop: S pieces per iteration straight from the ring; rare events (flush,
-        //      window move) are handled outside the tight inner loop
+        // ---- fast loop: 2*S pieces per trip straight from the ring (two per read slot, so the
+        //      weight-1 adder needs no pending register); straight-line body; rare events
+        //      (flush, window move) are handled outside the tight inner loop
         for (;;) {
-            uint32_t have_mask = 0u, fit_mask = 0u, low_pp = 0xFFFFFFFFu;
+            uint32_t fit_any = 0u, low_pp = 0xFFFFFFFFu;
             while (ring_head != ring_tail) {
-                const uint32_t kk = ring_head + (uint32_t)slot;
-                const bool have = (int)(ring_tail - kk) > 0;
-                const uint32_t adv = min((uint32_t)S, ring_tail - ring_head);   // entries consumed this iteration
-                uint4 e = make_uint4(0u, 0u, 0u, 0u);
-                if (have) e = ring[kk & (kRing - 1)];
-                const bool fits = have && win_valid && e.x >= win_lo && (e.x - win_lo) <= kWin - e.y;
-                have_mask = __ballot_sync(kFull, have);
-                fit_mask = __ballot_sync(kFull, fits);
-                if (fit_mask == 0u || cnt == kCntMax) {
-                    low_pp = have ? e.x : 0xFFFFFFFFu;
+                const uint32_t avail = ring_tail - ring_head;
+                const uint32_t adv = min((uint32_t)(2 * S), avail);     // entries consumed this trip
+                const bool have_a = (uint32_t)slot < avail, have_b = (uint32_t)(slot + S) < avail;
+                uint4 ea = ring[(ring_head + (uint32_t)slot) & (kRing - 1)];
+                uint4 eb = ring[(ring_head + (uint32_t)(slot + S)) & (kRing - 1)];
+                const bool fit_a = have_a && win_valid && ea.x >= win_lo && (ea.x - win_lo) <= kWin - ea.y;
+                const bool fit_b = have_b && win_valid && eb.x >= win_lo && (eb.x - win_lo) <= kWin - eb.y;
+                fit_any = __ballot_sync(kFull, fit_a || fit_b);
+                if (fit_any == 0u || cnt >= kCntMax) {
+                    low_pp = min(have_a ? ea.x : 0xFFFFFFFFu, have_b ? eb.x : 0xFFFFFFFFu);
                     break;
                 }
-                if (fit_mask != have_mask) {                         // re-queue pieces that wait for a window move
-                    const uint32_t unfit = __ballot_sync(kFull, have && !fits && wl == 0);
-                    if (have && !fits && wl == 0) ring[(ring_tail + __popc(unfit & lt_mask)) & (kRing - 1)] = e;
-                    ring_tail += __popc(unfit);
+                const uint32_t unfit_a = __ballot_sync(kFull, have_a && !fit_a && wl == 0);
+                const uint32_t unfit_b = __ballot_sync(kFull, have_b && !fit_b && wl == 0);
+                if (unfit_a | unfit_b) {                                 // re-queue pieces that wait for a window move
+                    if (have_a && !fit_a && wl == 0) ring[(ring_tail + __popc(unfit_a & lt_mask)) & (kRing - 1)] = ea;
+                    if (have_b && !fit_b && wl == 0)
+                        ring[(ring_tail + __popc(unfit_a) + __popc(unfit_b & lt_mask)) & (kRing - 1)] = eb;
+                    ring_tail += __popc(unfit_a) + __popc(unfit_b);
                     __syncwarp();
                 }
                 ring_head += adv;
-                uint32_t x[kW][4] = {};
-                if (fits) piece_words<G, HAS_OK>(x, e.x, e.y, win_lo, wl, sq, okb, (int)e.z, bv, 0u, 0u, 0u);
-                accumulate(x);
+                uint32_t xa[kW][4], xb[kW][4];
+                piece_words<G, HAS_OK>(xa, ea.x, fit_a ? ea.y : 0u, win_lo, wl, sq, okb, (int)ea.z);
+                piece_words<G, HAS_OK>(xb, eb.x, fit_b ? eb.y : 0u, win_lo, wl, sq, okb, (int)eb.z);
+                accumulate2(xa, xb);
             }
             if (ring_head == ring_tail) break;
             if (cnt) do_flush();
-            if (fit_mask == 0u) {                                    // nobody fits: move the window
+            if (fit_any == 0u) {                                         // nobody fits: move the window
                 win_lo = __reduce_min_sync(kFull, low_pp) & ~31u;
                 win_valid = true;
             }
@@ -593,7 +617,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 const bool fits = active && win_valid && pp >= win_lo && (pp - win_lo) < kWin &&
                                   (pn <= kWin - (pp - win_lo) || pn > kMaxFit);
                 const uint32_t fit_any = __ballot_sync(kFull, fits);
-                if (fit_any == 0u || cnt == kCntMax) {                       // the one flush site of this loop
+                if (fit_any == 0u || cnt >= kCntMax) {                       // the one flush site of this loop
                     if (fit_any == 0u && __ballot_sync(kFull, active) == 0u) continue;   // still walking ops / fetching
                     if (cnt) do_flush();
                     if (fit_any == 0u) {
@@ -603,13 +627,11 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                     continue;
                 }
                 // E: masked words of the fitting pieces, added to the vertical counters
-                uint32_t x[kW][4] = {};
-                uint32_t n1 = 0;
-                if (fits) {
-                    n1 = min(pn, kWin - (pp - win_lo));
-                    piece_words<G, HAS_OK>(x, pp, n1, win_lo, wl, sq, okb, sidx >= 0 ? sidx * 32 + (int)pq : -1, bv, pq, wbase, nwords);
-                }
-                accumulate(x);
+                uint32_t x[kW][4], zero[kW][4] = {};
+                const uint32_t n1 = fits ? min(pn, kWin - (pp - win_lo)) : 0u;
+                if (sidx >= 0) piece_words<G, HAS_OK>(x, pp, n1, win_lo, wl, sq, okb, sidx * 32 + (int)pq);
+                else piece_words_global<G, HAS_OK>(x, pp, n1, win_lo, wl, bv, pq, wbase, nwords);
+                accumulate2(x, zero);
                 pp += n1;
                 pq += n1;
                 pn -= n1;
