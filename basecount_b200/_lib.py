@@ -54,6 +54,8 @@ _SIGNATURES = {
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bc_summary": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bc_summary_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bc_amplicons": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                     ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bc_halo_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]),
@@ -67,6 +69,7 @@ _SIGNATURES = {
     "bc_timer_start": (ctypes.c_int, [ctypes.c_void_p]),
     "bc_timer_stop": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "bc_last_count_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
+    "bc_count_kernel_ms_history": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
     "bc_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
     "bc_set_count_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
 }

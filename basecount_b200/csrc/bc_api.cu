@@ -50,7 +50,8 @@ struct Resident {                // a batch kept in HBM by bc_batch_upload
 struct bc_handle {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t copy = nullptr, compute = nullptr;
+    cudaStream_t copy = nullptr, compute = nullptr, side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
     std::string err;
 
     uint32_t n_refs = 0;
@@ -71,8 +72,10 @@ struct bc_handle {
     SummaryPartial *d_partials = nullptr;
     size_t partials_cap = 0;
 
-    cudaEvent_t t0 = nullptr, t1 = nullptr, k0 = nullptr, k1 = nullptr;
-    bool k_timed = false;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    static constexpr int kHist = 256;           // ring of (start, stop) events around the counting kernel
+    cudaEvent_t k0[kHist] = {}, k1[kHist] = {};
+    uint64_t k_count = 0;
     uint64_t launches = 0;
     int variant = 0;
 };
@@ -165,8 +168,15 @@ int bc_create(int device, bc_handle **out)
     h->sm_count = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
     if ((e = cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
-    for (cudaEvent_t *ev : {&h->t0, &h->t1, &h->k0, &h->k1})
+    if ((e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
+    if ((e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    for (cudaEvent_t *ev : {&h->t0, &h->t1})
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail(e, "event");
+    for (int i = 0; i < bc_handle::kHist; i++) {
+        if ((e = cudaEventCreate(&h->k0[i])) != cudaSuccess) return bail(e, "event");
+        if ((e = cudaEventCreate(&h->k1[i])) != cudaSuccess) return bail(e, "event");
+    }
     for (Staging &s : h->stage) {
         if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
         if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
@@ -201,10 +211,17 @@ void bc_destroy(bc_handle *h)
     if (h->d_ref_len) cudaFree(h->d_ref_len);
     if (h->d_status) cudaFree(h->d_status);
     if (h->h_status) cudaFreeHost(h->h_status);
-    for (cudaEvent_t ev : {h->t0, h->t1, h->k0, h->k1})
+    for (cudaEvent_t ev : {h->t0, h->t1})
         if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < bc_handle::kHist; i++) {
+        if (h->k0[i]) cudaEventDestroy(h->k0[i]);
+        if (h->k1[i]) cudaEventDestroy(h->k1[i]);
+    }
+    if (h->fork) cudaEventDestroy(h->fork);
+    if (h->join) cudaEventDestroy(h->join);
     if (h->copy) cudaStreamDestroy(h->copy);
     if (h->compute) cudaStreamDestroy(h->compute);
+    if (h->side) cudaStreamDestroy(h->side);
     delete h;
 }
 
@@ -379,7 +396,17 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     cv.ref_len = h->d_ref_len;
     cv.status = h->d_status;
 
-    CU(h, cudaEventRecord(h->k0, h->compute));
+    // The sparse corrections only add to planes A and N with atomics, so they commute with K1:
+    // run them on a forked stream, concurrently with the counting kernel.
+    if (v.n_exc) {
+        CU(h, cudaEventRecord(h->fork, h->compute));
+        CU(h, cudaStreamWaitEvent(h->side, h->fork, 0));
+        k1_exceptions<<<(v.n_exc + 127) / 128, 128, 0, h->side>>>(v, cv);
+        CU(h, cudaEventRecord(h->join, h->side));
+        h->launches++;
+    }
+    const int ki = (int)(h->k_count % bc_handle::kHist);
+    CU(h, cudaEventRecord(h->k0[ki], h->compute));
     if (h->variant == 1) {
         k1_count_per_base<<<(v.n_reads + 127) / 128, 128, 0, h->compute>>>(v, cv);
     } else {
@@ -404,14 +431,11 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
         else K1_LAUNCH(32);
 #undef K1_LAUNCH
     }
-    CU(h, cudaEventRecord(h->k1, h->compute));
-    h->k_timed = true;
+    CU(h, cudaEventRecord(h->k1[ki], h->compute));
+    h->k_count++;
     h->launches++;
-    if (v.n_exc) {
-        k1_exceptions<<<(v.n_exc + 127) / 128, 128, 0, h->compute>>>(v, cv);
-        h->launches++;
-    }
-    k1_check_overflow<<<(v.n_reads + 127) / 128, 128, 0, h->compute>>>(v, cv);
+    if (v.n_exc) CU(h, cudaStreamWaitEvent(h->compute, h->join, 0));
+    k1_check_overflow<<<std::min<unsigned>((v.n_reads + 255) / 256, (unsigned)h->sm_count * 2), 256, 0, h->compute>>>(v, cv);
     h->launches++;
     CU(h, cudaGetLastError());
     return BC_OK;
@@ -646,8 +670,23 @@ int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, 
     return BC_OK;
 }
 
+static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
+                        double *entropy_sum, bool sync);
+
 int bc_summary(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
                double *entropy_sum)
+{
+    return summary_impl(h, show_n, norm, norm2, nonzero, cov_sum, entropy_sum, true);
+}
+
+int bc_summary_async(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
+                     double *entropy_sum)
+{
+    return summary_impl(h, show_n, norm, norm2, nonzero, cov_sum, entropy_sum, false);
+}
+
+static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
+                        double *entropy_sum, bool sync)
 {
     if (!h || !nonzero || !cov_sum || !entropy_sum) return BC_ERR_ARG;
     if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
@@ -678,7 +717,7 @@ int bc_summary(bc_handle *h, int show_n, double norm, double norm2, int64_t *non
     CU(h, cudaMemcpyAsync(nonzero, d_nz, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
     CU(h, cudaMemcpyAsync(cov_sum, d_cs, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
     CU(h, cudaMemcpyAsync(entropy_sum, d_es, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
-    CU(h, cudaStreamSynchronize(h->compute));
+    if (sync) CU(h, cudaStreamSynchronize(h->compute));
     return BC_OK;
 }
 
@@ -789,11 +828,20 @@ int bc_timer_stop(bc_handle *h, float *ms)
 
 int bc_last_count_kernel_ms(bc_handle *h, float *ms)
 {
-    if (!h || !ms) return BC_ERR_ARG;
-    if (!h->k_timed) return fail(h, BC_ERR_STATE, "no counting kernel has run");
-    CU(h, cudaEventSynchronize(h->k1));
-    CU(h, cudaEventElapsedTime(ms, h->k0, h->k1));
-    return BC_OK;
+    return bc_count_kernel_ms_history(h, ms, 1) == 1 ? BC_OK : BC_ERR_STATE;
+}
+
+int bc_count_kernel_ms_history(bc_handle *h, float *ms, int n)
+{
+    if (!h || !ms || n <= 0) return -1;
+    const int have = (int)std::min<uint64_t>(h->k_count, (uint64_t)bc_handle::kHist);
+    n = std::min(n, have);
+    for (int i = 0; i < n; i++) {                 // ms[0] = most recent launch
+        const int ki = (int)((h->k_count - 1 - (uint64_t)i) % bc_handle::kHist);
+        if (cudaEventSynchronize(h->k1[ki]) != cudaSuccess) return -1;
+        if (cudaEventElapsedTime(&ms[i], h->k0[ki], h->k1[ki]) != cudaSuccess) return -1;
+    }
+    return n;
 }
 
 uint64_t bc_kernel_launches(bc_handle *h) { return h ? h->launches : 0; }

@@ -752,8 +752,7 @@ __device__ __forceinline__ uint32_t find_exception(const BatchView &bv, uint32_t
 __global__ void k1_check_overflow(BatchView bv, CountView cv)
 {
     if (cv.status[kStatMaybeOverflow] == 0u) return;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= bv.n_reads) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < bv.n_reads; i += gridDim.x * blockDim.x) {
     const uint32_t r = slot_of_read(bv.ref_read_off, bv.n_refs, i);
     const uint32_t ref_len = cv.ref_len[r];
     uint32_t ref_pos = bv.starts[i], read_pos = 0;
@@ -783,6 +782,7 @@ __global__ void k1_check_overflow(BatchView bv, CountView cv)
         } else if (op_is_refskip(op)) {
             ref_pos = sat_add(ref_pos, len);
         }
+    }
     }
 }
 

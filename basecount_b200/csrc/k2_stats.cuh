@@ -40,6 +40,16 @@ __device__ __forceinline__ double neumaier_entropy(const long long *c, int n, lo
     return hi;
 }
 
+// Coverage and entropy only (what the --summarise reductions need, main.py:479-485).
+__device__ __forceinline__ void position_cov_entropy(const long long *c, int K, double norm, long long &cov_out,
+                                                     double &ent_out)
+{
+    long long cov = 0;
+    for (int i = 0; i < K; i++) cov += c[i];
+    cov_out = cov;
+    ent_out = cov == 0 ? 1.0 : norm * neumaier_entropy(c, K, cov, -1);
+}
+
 __device__ __forceinline__ void position_stats(const long long *c, int K, double norm, double norm2, PosStats &o)
 {
     long long cov = 0;
@@ -121,11 +131,12 @@ k2_summary_partials(const uint32_t *__restrict__ c32, const unsigned long long *
     for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < L; pos += gridDim.x * blockDim.x) {
         long long c[6];
         load_counts(c32, c64, stride, base + pos, K, c);
-        PosStats s;
-        position_stats(c, K, norm, norm2, s);
-        nz += (s.cov != 0);
-        cs += s.cov;
-        es += s.ent;
+        long long cov;
+        double ent;
+        position_cov_entropy(c, K, norm, cov, ent);
+        nz += (cov != 0);
+        cs += cov;
+        es += ent;
     }
     __shared__ long long s_nz[256], s_cs[256];
     __shared__ double s_es[256];

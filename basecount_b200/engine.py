@@ -123,6 +123,13 @@ class Engine:
         _lib.check(self._h, self._L.bc_summary(self._h, int(show_n_bases), n1, n2, _lib.ptr(nz), _lib.ptr(cs), _lib.ptr(es)))
         return nz, cs, es
 
+    def summary_async(self, out, show_n_bases: bool = False):
+        """Queue the summarise reductions; `out` = (nonzero, cov_sum, ent_sum) pinned arrays
+        (see _lib.pinned_empty), valid after sync()."""
+        n1, n2 = norm_factors(show_n_bases)
+        _lib.check(self._h, self._L.bc_summary_async(self._h, int(show_n_bases), n1, n2, _lib.ptr(out[0]),
+                                                     _lib.ptr(out[1]), _lib.ptr(out[2])))
+
     def amplicons(self, ref: int, lo, hi, show_n_bases: bool = False):
         lo = np.ascontiguousarray(lo, dtype=np.int32)
         hi = np.ascontiguousarray(hi, dtype=np.int32)
@@ -158,6 +165,14 @@ class Engine:
         ms = ctypes.c_float()
         _lib.check(self._h, self._L.bc_last_count_kernel_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+    def count_kernel_ms_history(self, n: int):
+        """Device times (ms) of the last n counting-kernel launches, most recent first."""
+        buf = (ctypes.c_float * n)()
+        got = self._L.bc_count_kernel_ms_history(self._h, buf, n)
+        if got < 0:
+            raise RuntimeError("bc_count_kernel_ms_history failed")
+        return [float(buf[i]) for i in range(got)]
 
     def kernel_launches(self) -> int:
         return int(self._L.bc_kernel_launches(self._h))

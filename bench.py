@@ -270,57 +270,83 @@ def main():
     alg_bytes = [p.algorithmic_bytes(ref_lens) for p in packed]
     d2h_bytes = len(ref_lens) * 24
 
-    def step_resident(i):
+    from basecount_b200 import _lib as bclib
+    n_slots = len(ref_lens)
+
+    def pinned_out():
+        return (bclib.pinned_empty(n_slots, np.int64), bclib.pinned_empty(n_slots, np.int64),
+                bclib.pinned_empty(n_slots, np.float64))
+
+    outs = [pinned_out() for _ in range(max(args.steps, args.warmup, 1))]
+
+    def step_resident(i, out):
+        """Queue one step; results land in the pinned `out` arrays (valid after eng.sync())."""
         eng.reset()
         eng.push(resident[i % len(resident)])
-        return eng.summary(False)                 # K2 + K3, D2H of the per-sample scalars, sync
+        eng.summary_async(out, False)             # K2 + K3, D2H of the per-sample scalars
 
-    def step_e2e(i):
+    def step_e2e(i, out):
         eng.reset()
         eng.push(packed[i % len(packed)])         # pinned host SoA -> H2D -> K1
-        out = eng.summary(False)
-        eng.sync()
-        return out
+        eng.summary_async(out, False)
 
     # ---- correctness guard: the timed configuration must produce the oracle's summary
     # (size-independent property: the synthetic reads hold only A,C,G,T,N, so every aligned base
     # lands in exactly one cell of its sample's matrix)
-    nz, cs, _ = step_resident(0)
+    step_resident(0, outs[0])
     eng.sync()
+    nz, cs = outs[0][0].copy(), outs[0][1].copy()
     c0 = eng.counts(0)
     assert int(c0.sum()) == sets[0][0].aligned_bases(), "cells do not add up to the aligned bases"
     assert int(cs[0]) == int(c0[:, :5].sum()) and int(nz[0]) == int((c0[:, :5].sum(axis=1) != 0).sum())
 
-    # ---- value: inputs resident in HBM
+    # ---- value: inputs resident in HBM; the K steps are queued back to back (each step's
+    #      summary is copied to its own pinned slot) and the stream is drained at the end
     for i in range(args.warmup):
-        step_resident(i)
+        step_resident(i, outs[i])
     eng.sync()
     clocks = ClockSampler(local)
-    barrier()
     clocks.start()
-    k1_ms = []
+    barrier()
     launches0 = eng.kernel_launches()
     eng.timer_start()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
-        step_resident(i)
-        k1_ms.append((eng.last_count_kernel_ms(), i % len(resident)))
+        step_resident(i, outs[i])
     ms_dev = eng.timer_stop()
+    eng.sync()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
     launches = eng.kernel_launches() - launches0
+    hist = eng.count_kernel_ms_history(min(args.steps, 256))          # most recent first
+    k1_ms = [(m, (args.steps - 1 - k) % len(resident)) for k, m in enumerate(hist)]
+    for i in range(args.steps):                                        # every step must have produced its summary
+        assert int(outs[i][1].sum()) > 0
     ms_dev = max_over_ranks(ms_dev)
     total_bases = sum_over_ranks(float(sum(bases_per_step[i % len(resident)] for i in range(args.steps))))
     value = total_bases / (ms_dev * 1e-3)
+    # clocks: the timed region is only milliseconds long, so keep the same steps running until
+    # nvidia-smi (100 ms period) has seen ~1.5 s of this load
+    t_end = time.perf_counter() + 1.5
+    i = 0
+    while time.perf_counter() < t_end:
+        step_resident(i, outs[i % len(outs)])
+        i += 1
+        if i % 64 == 0:
+            eng.sync()
+    eng.sync()
+    clk = clocks.stop()
+    clk["window"] = "timed region plus the same steps repeated for 1.5 s"
 
     # ---- e2e: pinned host buffers through the C ABI, copies inside the timed region
     for i in range(args.warmup):
-        step_e2e(i)
+        step_e2e(i, outs[i])
+    eng.sync()
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step_e2e(i)
+        step_e2e(i, outs[i])
+        eng.sync()                                # the caller reads this step's result before the next
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_bases / e2e_s

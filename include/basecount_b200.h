@@ -135,6 +135,10 @@ int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
  * (entropy = 1 at zero coverage). */
 int bc_summary(bc_handle *h, int show_n, double norm, double norm2,
                int64_t *nonzero, int64_t *cov_sum, double *entropy_sum);
+/* Same, without waiting: the three outputs must be pinned host buffers (bc_host_alloc) and are
+ * valid after the next bc_sync.  Lets a stream of batches pipeline without a host sync each. */
+int bc_summary_async(bc_handle *h, int show_n, double norm, double norm2,
+                     int64_t *nonzero, int64_t *cov_sum, double *entropy_sum);
 
 /* --summarise-with-bed amplicon vectors (main.py:519-551) for one slot.
  * Window t covers 0-based positions lo[t]..hi[t] inclusive, clipped to the reference.
@@ -171,6 +175,9 @@ int bc_timer_start(bc_handle *h);
 int bc_timer_stop(bc_handle *h, float *ms);
 /* Device time of the last counting-kernel launch alone (events around K1), and launches so far. */
 int bc_last_count_kernel_ms(bc_handle *h, float *ms);
+/* Device times of the last n counting-kernel launches (ms[0] = most recent; ring of 256).
+ * Returns how many were written, or -1. */
+int bc_count_kernel_ms_history(bc_handle *h, float *ms, int n);
 uint64_t bc_kernel_launches(bc_handle *h);
 /* Debug / cross-check: 0 = tiled bit-sliced kernel (default), 1 = one-thread-per-read
  * per-base atomics.  Both are CUDA; there is no host path. */
