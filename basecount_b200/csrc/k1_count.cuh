@@ -146,8 +146,10 @@ __host__ __device__ constexpr uint32_t k1_warp_smem_bytes()
            /* piece ring */ kRing * 16u + /* order list */ 64u + /* mbarriers */ 64u;
 }
 
-struct BlockMeta {            // lane l holds the metadata of read (block_first + l)
-    uint32_t start, cbase, ncig, wbase, nwords;
+struct BlockMeta {            // lane l holds the metadata of read (block_first + l); raw loaded values only,
+    uint32_t start, cbase, cend, wbase, wend;   // so nothing waits on the loads until the block is used
+    __device__ __forceinline__ uint32_t ncig() const { return cend - cbase; }
+    __device__ __forceinline__ uint32_t nwords() const { return wend - wbase; }
 };
 struct StagedRange {          // what one pipeline stage holds (warp-uniform)
     uint32_t s_lo, s_n;       // plane / okmask words [s_lo, s_lo + s_n)
@@ -358,9 +360,9 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         if ((uint32_t)lane < rpb && idx < re) {
             m.start = __ldg(bv.starts + idx);
             m.cbase = __ldg(bv.cigar_off + idx);
-            m.ncig = __ldg(bv.cigar_off + idx + 1) - m.cbase;
+            m.cend = __ldg(bv.cigar_off + idx + 1);
             m.wbase = __ldg(bv.seq_woff + idx);
-            m.nwords = __ldg(bv.seq_woff + idx + 1) - m.wbase;
+            m.wend = __ldg(bv.seq_woff + idx + 1);
         }
         return m;
     };
@@ -368,9 +370,9 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     auto issue_block = [&](uint32_t blk, const BlockMeta &m, int b) {
         const uint32_t nvalid = min(rpb, re - (rb + blk * rpb));
         const uint32_t s0 = __shfl_sync(kFull, m.wbase, 0);
-        const uint32_t s1 = __shfl_sync(kFull, m.wbase + m.nwords, (int)nvalid - 1);
+        const uint32_t s1 = __shfl_sync(kFull, m.wend, (int)nvalid - 1);
         const uint32_t c0 = __shfl_sync(kFull, m.cbase, 0);
-        const uint32_t c1 = __shfl_sync(kFull, m.cbase + m.ncig, (int)nvalid - 1);
+        const uint32_t c1 = __shfl_sync(kFull, m.cend, (int)nvalid - 1);
         StagedRange r;
         r.s_lo = s0 & ~3u;                                           // 32 B / 16 B aligned sources
         r.s_n = min(((s1 + 3u) & ~3u) - r.s_lo, kSeqCap);
@@ -426,15 +428,15 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         //      to two M/=/X pieces (adjacent match ops merge) into the piece ring; anything
         //      bigger (more pieces, long pieces or skips, unstaged reads) goes to the general loop.
         const bool valid = (uint32_t)lane < nvalid;
-        const bool staged = valid && (m0.wbase - rg.s_lo) <= rg.s_n && (m0.wbase - rg.s_lo) + m0.nwords <= rg.s_n;
+        const bool staged = valid && (m0.wbase - rg.s_lo) <= rg.s_n && (m0.wbase - rg.s_lo) + m0.nwords() <= rg.s_n;
         const int my_sidx = staged ? (int)(m0.wbase - rg.s_lo + kSeqPad) : -1;
         uint32_t pc_pp[2] = {0u, 0u}, pc_pq[2] = {0u, 0u}, pc_pn[2] = {0u, 0u};
         uint32_t n_pc = 0, sk_pos = 0, sk_len = 0;
-        bool complex_read = valid && m0.ncig && !staged;
-        if (valid && m0.ncig && staged) {
+        bool complex_read = valid && m0.ncig() && !staged;
+        if (valid && m0.ncig() && staged) {
             uint32_t rpos = m0.start, qpos = 0;
             bool open = false;                                           // last op was a match op (merge candidates)
-            for (uint32_t c = m0.cbase; c < m0.cbase + m0.ncig; c++) {
+            for (uint32_t c = m0.cbase; c < m0.cbase + m0.ncig(); c++) {
                 const uint32_t ci = c - rg.c_lo;
                 const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + c);
                 const uint32_t op = cw & 0xFu, len = cw >> 4;
@@ -567,9 +569,9 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                     const int src = take ? (int)order2[idx] : 0;
                     const uint32_t t_start = __shfl_sync(kFull, m0.start, src);
                     const uint32_t t_cbase = __shfl_sync(kFull, m0.cbase, src);
-                    const uint32_t t_ncig = __shfl_sync(kFull, m0.ncig, src);
+                    const uint32_t t_ncig = __shfl_sync(kFull, m0.ncig(), src);
                     const uint32_t t_wbase = __shfl_sync(kFull, m0.wbase, src);
-                    const uint32_t t_nwords = __shfl_sync(kFull, m0.nwords, src);
+                    const uint32_t t_nwords = __shfl_sync(kFull, m0.nwords(), src);
                     const int t_sidx = __shfl_sync(kFull, my_sidx, src);
                     if (take) {
                         ref_pos = t_start;
