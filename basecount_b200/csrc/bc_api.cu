@@ -311,7 +311,7 @@ static int pick_group_width(const bc_batch *b, uint64_t total_words)
 template <int G, bool OK>
 static int k1_prepare(size_t *smem, int *ctas_per_sm)
 {
-    *smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<G, OK>();
+    *smem = (size_t)k1_cta_smem_bytes<G, OK>();
     cudaError_t e = cudaFuncSetAttribute(k1_count_tiled<G, OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k1_count_tiled<G, OK>, kK1Threads, *smem);
@@ -414,14 +414,14 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
         const bool ok = v.okmask != nullptr;
         // reads per staging block: a block's plane words must fit one pipeline stage
         const uint32_t words_per_read = std::max<uint32_t>(1, mean_words);
-        const uint32_t rpb = std::max<uint32_t>(2, std::min<uint32_t>(32, (kSeqCap * 9 / 10) / words_per_read));
+        const uint32_t rpb = std::max<uint32_t>(1, std::min<uint32_t>(kMaxRpb, (kSeqCap - 8) / words_per_read));
 #define K1_LAUNCH(GG)                                                                                          \
     do {                                                                                                       \
         if (ok) {                                                                                              \
-            const size_t smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<GG, true>();                       \
+            const size_t smem = (size_t)k1_cta_smem_bytes<GG, true>();                      \
             k1_count_tiled<GG, true><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb);  \
         } else {                                                                                               \
-            const size_t smem = (size_t)kK1WarpsPerCta * k1_warp_smem_bytes<GG, false>();                      \
+            const size_t smem = (size_t)k1_cta_smem_bytes<GG, false>();                      \
             k1_count_tiled<GG, false><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb); \
         }                                                                                                      \
     } while (0)

@@ -2,22 +2,34 @@
 //
 // Replaces the loop nest of the reference operator (basecount/count.cpp:22-97).
 //
-// Design (B200-first, nothing here mirrors the reference's scalar loop):
-//   * A warp owns a chunk of consecutive reads of one reference slot.  Its 32 lanes
-//     form S = 32/G "read slots" of G lanes; lane (slot, w) covers the 32 reference
-//     columns of window word w.  All slots share ONE window of 32*G columns, so window
-//     moves and flushes are warp-uniform (no divergence between slots).
-//   * Sequence data is 2-bit, bit-planar (lo/hi plane): one 64-bit load + a funnel
-//     shift aligns 32 bases of a read onto a 32-column window word; three LOP3 build
-//     the masked one-hot words for A/C/G/T.  No per-base work anywhere.
-//   * Counts are accumulated VERTICALLY in registers as bit-sliced counters
-//     (carry-save adders, Harley-Seal style): ~3 LOP3 per 32 bases per base letter.
-//   * A flush converts the bit-sliced counters to integers (byte-packed extraction,
-//     PRMT transposes, shared-memory staging) and adds them to the HBM count planes
-//     with coalesced 128-byte RED.ADD -- one atomic per column per flush instead of
+// Design (B200-first, nothing here mirrors the reference's scalar loop).  The kernel is bound by
+// the ALU pipe (LOP3 / SHF issue at one warp instruction per two cycles per SM sub-partition), so
+// everything is arranged to spend as few logic instructions per aligned base as possible:
+//   * A warp owns a chunk of consecutive reads of one reference slot.  Its 32 lanes form
+//     S = 32/G "read slots" of G lanes; a lane covers kW = 2 consecutive 32-column window words,
+//     so all slots share ONE window of 64*G reference columns and window moves / flushes are
+//     warp-uniform.
+//   * Sequence data is 2-bit, bit-planar (lo / hi plane), staged in shared memory by 1-D TMA bulk
+//     copies three blocks of reads ahead.  A funnel shift aligns 32 bases of a read onto a window
+//     word; no per-base work anywhere.
+//   * CIGAR walk: one read per lane, all lanes step through their own CIGAR in lock step
+//     (count.cpp:40-96).  Every M/=/X run that fits the window becomes a 16-byte *piece* entry
+//     {first column, end column, bit offset of the data} in a shared-memory ring; D/N runs add to
+//     the DS plane directly; I advances the read.  Runs that do not fit wait (their lane stalls)
+//     until the window moves; runs longer than a window are pushed window by window.
+//   * Counting: the ring is consumed four pieces per read slot at a time, straight-line code with
+//     no votes or branches inside.  Per window word four quantities are counted VERTICALLY in
+//     bit-sliced carry-save counters (Harley-Seal): n(lo), n(hi), n(lo & hi), n(valid), each masked
+//     with the piece's column range (a 64-bit mask looked up in shared memory).  That is ~2.1
+//     LOP3 per counted quantity per 32 bases; letters follow at flush time:
+//     T = n(lo&hi), C = n(lo) - T, G = n(hi) - T, A = n(valid) - n(lo) - n(hi) + T.
+//   * A flush (every 252 pieces per slot, or on a window move) converts the counters to integers
+//     (byte-packed extraction, 16-bit slot sums, shared-memory staging) and adds them to the HBM
+//     count planes with coalesced 128-byte RED.ADD -- one atomic per column per flush instead of
 //     one per base.
-//   * D / N ops add to the DS plane directly (rare); letters the 2-bit code cannot
-//     express (N, IUPAC, lower case) are a sparse correction pass (k1_exceptions).
+//   * Letters the 2-bit code cannot express (N, IUPAC, lower case) are a sparse correction pass
+//     (k1_exceptions); reads whose data was not staged (far longer than the batch mean) are copied
+//     into a free stage segment by segment and take the same path.
 #pragma once
 #include "bc_common.cuh"
 
@@ -26,8 +38,21 @@ namespace bc {
 constexpr int kK1WarpsPerCta = 4;
 constexpr int kK1MinCtas = 3;
 constexpr int kK1Threads = kK1WarpsPerCta * 32;
-constexpr int kNB = 8;                       // bit planes per vertical counter (counts to 255)
+constexpr int kNB = 8;                        // bit planes per vertical counter (counts to 255)
+constexpr int kNC = 4;                        // counted quantities per window word: lo, hi, lo&hi, valid
+constexpr int kW = 2;                         // window words per lane
+constexpr int kStages = 3;                    // TMA pipeline depth (blocks of reads)
 constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr uint32_t kSeqCap = 448;             // staged 64-bit plane words per stage (31 reads x 13 words + slack)
+constexpr uint32_t kCigCap = 96;              // staged CIGAR words per stage; the rest is read from HBM
+constexpr uint32_t kRing = 64;                // piece ring entries (uint4 each)
+constexpr uint32_t kCntMax = 252;             // pieces per slot between flushes (8-plane counters, 4 per trip)
+constexpr uint32_t kFlushStride = 34;         // uint16 per staged window word (32 + 2 pad: conflict-free stores)
+constexpr uint32_t kMaxRpb = 31;              // reads per block: lane i+1 holds the end offsets of read i
+constexpr uint32_t kLaneSkipMax = 32;         // longest D/N run a single lane adds itself
+constexpr uint32_t kOpClass = 0x140F9u;       // 2 bits per CIGAR op: 1 = M/=/X, 2 = I, 3 = D/N, 0 = S/H/P/B/other
+
+static_assert(kW == 2, "the piece masks are 64-bit (uint2)");
 
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
 __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b)
@@ -35,63 +60,6 @@ __device__ __forceinline__ uint32_t sat_add(uint32_t a, uint32_t b)
     uint32_t t = a + b;
     return t < a ? 0xFFFFFFFFu : t;
 }
-
-// Vertical counters of one lane: for each of A,C,G,T, kNB bit planes over the lane's 32
-// columns (Harley-Seal style carry-save adders).  Inputs arrive two at a time, so the
-// weight-1 adder consumes both directly; pend[b][0] / pend[b][1] hold the not-yet-paired
-// carries of weight 2 and 4.
-struct VCounters {
-    uint32_t pl[4][kNB];
-    uint32_t pend[4][2];
-    __device__ __forceinline__ void clear()
-    {
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-#pragma unroll
-            for (int k = 0; k < kNB; k++) pl[b][k] = 0;
-            pend[b][0] = 0;
-            pend[b][1] = 0;
-        }
-    }
-    // Add two 32-column masks per letter.  `cnt` = inputs added so far (even, warp-uniform),
-    // so every branch below is uniform.
-    __device__ __forceinline__ void add2(const uint32_t xa[4], const uint32_t xb[4], uint32_t cnt)
-    {
-        uint32_t c1[4];
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            c1[b] = maj3(pl[b][0], xa[b], xb[b]);
-            pl[b][0] ^= xa[b] ^ xb[b];
-        }
-        if ((cnt & 2u) == 0u) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) pend[b][0] = c1[b];
-            return;
-        }
-        uint32_t c2[4];
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            c2[b] = maj3(pl[b][1], pend[b][0], c1[b]);
-            pl[b][1] ^= pend[b][0] ^ c1[b];
-        }
-        if ((cnt & 4u) == 0u) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) pend[b][1] = c2[b];
-            return;
-        }
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            uint32_t c = maj3(pl[b][2], pend[b][1], c2[b]);
-            pl[b][2] ^= pend[b][1] ^ c2[b];
-#pragma unroll
-            for (int k = 3; k < kNB; k++) {          // ripple the weight-8 carry upwards
-                uint32_t t = pl[b][k] & c;
-                pl[b][k] ^= c;
-                c = t;
-            }
-        }
-    }
-};
 
 // ---- TMA (1-D bulk async copy) + mbarrier helpers -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,59 +93,76 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         : "memory");
 }
 
-// ---- geometry -----------------------------------------------------------------------------
-// A warp's 32 lanes form S = 32/G read slots of G lanes; every lane covers W consecutive
-// 32-column window words, so the (warp-shared) window spans 32*W*G reference columns.
-constexpr int kW = 2;
-constexpr uint32_t kSeqCap = 512;     // staged 64-bit plane words per stage (4 KB): 32 reads x 400 bp = 416 words
-constexpr uint32_t kSeqPad = 4;       // guard words so clamped out-of-piece loads stay inside the stage
-constexpr uint32_t kCigCap = 256;     // staged CIGAR words per stage (1 KB)
-constexpr int kStages = 2;
-constexpr uint32_t kCntMax = 254u;    // per-slot count limit of the 8-plane counters (inputs come in pairs)
-constexpr uint32_t kFlushStride = 34; // uint16 per staged window word (32 + 2 pad: conflict-free stores)
-constexpr uint32_t kRing = 128;       // piece ring entries (uint4 each)
-constexpr uint32_t kLaneSkipMax = 256; // longest D/N run a single lane adds itself
-
+// ---- geometry + shared-memory layout --------------------------------------------------------
+// Per CTA: the 65-entry mask table, then one region per warp.  Inside a warp's region the
+// sequence stages sit between the ring / flush rows (below) and the CIGAR stages (above), so the
+// unclamped word index of a piece (up to 64*G columns before or after its data) always lands in
+// the CTA's own shared memory; whatever it reads there is masked away.
 template <int G, bool HAS_OK>
-__host__ __device__ constexpr uint32_t k1_warp_smem_bytes()
+struct K1Cfg {
+    static constexpr int S = 32 / G;                        // read slots per warp
+    static constexpr int Q = 4 * S;                         // ring entries consumed per trip
+    static constexpr uint32_t kWin = 32u * kW * G;          // window columns
+    static constexpr uint32_t kCols = kFlushStride * kW * G;   // uint16 per flush row
+    static constexpr uint32_t lut_bytes = 528;              // 65 x uint2, padded to 16 B
+    static constexpr uint32_t ring_off = 0;
+    static constexpr uint32_t frow_off = ring_off + kRing * 16u;
+    static constexpr uint32_t seq_off = frow_off + kNC * kCols * 2u;
+    static constexpr uint32_t ok_off = seq_off + kStages * kSeqCap * 8u;
+    static constexpr uint32_t cig_off = ok_off + (HAS_OK ? kStages * kSeqCap * 4u : 0u);
+    static constexpr uint32_t bar_off = cig_off + kStages * kCigCap * 4u;
+    static constexpr uint32_t warp_bytes = bar_off + 32u;
+    static constexpr uint32_t cta_bytes = lut_bytes + kK1WarpsPerCta * warp_bytes;
+    static_assert(seq_off % 16 == 0 && ok_off % 16 == 0 && cig_off % 16 == 0 && bar_off % 8 == 0 && warp_bytes % 16 == 0,
+                  "TMA destinations are 16-byte aligned");
+    static_assert(seq_off >= (kWin / 32 + 4) * 8 && kStages * kCigCap * 4u >= (kWin / 32 + 4) * 8,
+                  "guard bands around the sequence stages");
+};
+template <int G, bool HAS_OK>
+__host__ __device__ constexpr uint32_t k1_cta_smem_bytes()
 {
-    return kStages * (kSeqCap + kSeqPad) * 8u + (HAS_OK ? kStages * (kSeqCap + kSeqPad) * 4u : 0u) +
-           kStages * kCigCap * 4u + /* flush rows: 4 letters x (kW*G words x 34) u16 */ 4u * kW * G * kFlushStride * 2u +
-           /* piece ring */ kRing * 16u + /* order list */ 64u + /* mbarriers */ 64u;
+    return K1Cfg<G, HAS_OK>::cta_bytes;
 }
 
-struct BlockMeta {            // lane l holds the metadata of read (block_first + l); raw loaded values only,
-    uint32_t start, cbase, cend, wbase, wend;   // so nothing waits on the loads until the block is used
-    __device__ __forceinline__ uint32_t ncig() const { return cend - cbase; }
-    __device__ __forceinline__ uint32_t nwords() const { return wend - wbase; }
-};
-struct StagedRange {          // what one pipeline stage holds (warp-uniform)
-    uint32_t s_lo, s_n;       // plane / okmask words [s_lo, s_lo + s_n)
-    uint32_t c_lo, c_n;       // CIGAR words        [c_lo, c_lo + c_n)
-};
-
 // Convert the warp's vertical counters to integers and add them to the HBM planes.
-// Byte-packed extraction per slot, widened to 16 bit before the S read slots are summed
-// (so each slot may hold up to 255), staged in shared memory and written with coalesced
-// RED.ADD (128 B per warp instruction).  The loop over the shift amount jj is deliberately
-// NOT unrolled: registers stay statically indexed while the code stays a few hundred
-// instructions (a fully unrolled flush inlined at every site made the kernel > 500 KB and
-// instruction-fetch bound).
-//   frow: 4 letters x (kW*G window words x kFlushStride) uint16
+// Pending carries are folded in first; then byte-packed extraction per slot, widened to 16 bit
+// before the S read slots are summed (each slot holds at most 252), staged in shared memory,
+// turned into letter counts and written with coalesced RED.ADD (128 B per warp instruction).
+// The loop over the shift amount jj is deliberately NOT unrolled: registers stay statically
+// indexed while the code stays a few hundred instructions.
+//   frow: kNC rows x (kW*G window words x kFlushStride) uint16;  counts: plane A at window column 0
 template <int G>
-__device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt, uint16_t *frow, uint64_t win_col,
-                                               uint32_t *__restrict__ counts, uint64_t stride, int lane)
+__device__ __forceinline__ void flush_counters(uint32_t (&pl)[kW][kNC][kNB], uint32_t (&pa)[kW][kNC],
+                                               uint32_t (&pb)[kW][kNC], uint32_t (&pc)[kW][kNC], uint32_t cnt,
+                                               uint16_t *frow, uint32_t *__restrict__ counts, uint64_t stride, int lane)
 {
     constexpr int S = 32 / G;
     constexpr int kCols = (int)kFlushStride * kW * G;
     const int slot = lane / G, wl = lane % G;
-    // pendings that hold no carry are zeroed so the loop below needs no cnt tests
 #pragma unroll
     for (int w = 0; w < kW; w++) {
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            if (!(cnt & 2u)) vc[w].pend[b][0] = 0u;
-            if (!(cnt & 4u)) vc[w].pend[b][1] = 0u;
+        for (int k = 0; k < kNC; k++) {
+            // pending carries of weight 4 / 8 / 16 are live iff that bit of cnt is set
+            uint32_t c = (cnt & 4u) ? pa[w][k] : 0u;
+#pragma unroll
+            for (int p = 2; p < kNB; p++) {
+                if (p == 3) {
+                    const uint32_t d = (cnt & 8u) ? pb[w][k] : 0u;    // two carries into plane 3: full adder
+                    const uint32_t t = maj3(pl[w][k][p], c, d);
+                    pl[w][k][p] ^= c ^ d;
+                    c = t;
+                } else if (p == 4) {
+                    const uint32_t d = (cnt & 16u) ? pc[w][k] : 0u;
+                    const uint32_t t = maj3(pl[w][k][p], c, d);
+                    pl[w][k][p] ^= c ^ d;
+                    c = t;
+                } else {
+                    const uint32_t t = pl[w][k][p] & c;
+                    pl[w][k][p] ^= c;
+                    c = t;
+                }
+            }
         }
     }
     const bool high = cnt >= 16u;                         // planes 4..7 can only be set after 16 inputs
@@ -185,27 +170,25 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
     for (int jj = 0; jj < 8; jj++) {
         const bool mine = (jj % S) == slot;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
+        for (int k = 0; k < kNC; k++) {
 #pragma unroll
             for (int w = 0; w < kW; w++) {
                 uint32_t acc = 0;                         // byte t = count of column jj + 8t (this slot only)
 #pragma unroll
-                for (int k = 0; k < 4; k++) acc += ((vc[w].pl[b][k] >> jj) & 0x01010101u) << k;
+                for (int p = 0; p < 4; p++) acc += ((pl[w][k][p] >> jj) & 0x01010101u) << p;
                 if (high) {
 #pragma unroll
-                    for (int k = 4; k < kNB; k++) acc += ((vc[w].pl[b][k] >> jj) & 0x01010101u) << k;
+                    for (int p = 4; p < kNB; p++) acc += ((pl[w][k][p] >> jj) & 0x01010101u) << p;
                 }
-#pragma unroll
-                for (int k = 0; k < 2; k++) acc += ((vc[w].pend[b][k] >> jj) & 0x01010101u) << (k + 1);
                 uint32_t ev = acc & 0x00FF00FFu;          // columns jj, jj+16
                 uint32_t od = (acc >> 8) & 0x00FF00FFu;   // columns jj+8, jj+24
 #pragma unroll
-                for (int d = G; d < 32; d <<= 1) {        // sum the read slots (<= 8 * 255 fits 16 bit)
+                for (int d = G; d < 32; d <<= 1) {        // sum the read slots (<= 8 * 252 fits 16 bit)
                     ev += __shfl_xor_sync(kFull, ev, d);
                     od += __shfl_xor_sync(kFull, od, d);
                 }
                 if (mine) {
-                    uint16_t *dst = frow + b * kCols + (kW * wl + w) * (int)kFlushStride + jj;
+                    uint16_t *dst = frow + k * kCols + (kW * wl + w) * (int)kFlushStride + jj;
                     dst[0] = (uint16_t)ev;
                     dst[16] = (uint16_t)(ev >> 16);
                     dst[8] = (uint16_t)od;
@@ -215,440 +198,431 @@ __device__ __forceinline__ void flush_counters(VCounters (&vc)[kW], uint32_t cnt
         }
     }
     __syncwarp();
-#pragma unroll 1
-    for (int b = 0; b < 4; b++) {
-        uint32_t *plane = counts + (uint64_t)b * stride + win_col;
-        const uint16_t *row = frow + b * kCols;
-#pragma unroll 4
-        for (int w = 0; w < kW * G; w++) {
-            const uint32_t val = row[(int)kFlushStride * w + lane];
-            if (val) atomicAdd(plane + 32 * w + lane, val);     // RED.ADD, 128 B per warp instruction
-        }
+#pragma unroll 2
+    for (int w = 0; w < kW * G; w++) {
+        const int at = (int)kFlushStride * w + lane;
+        const uint32_t nlo = frow[at], nhi = frow[kCols + at], nb = frow[2 * kCols + at], nv = frow[3 * kCols + at];
+        uint32_t *p = counts + 32 * w + lane;
+        const uint32_t a = nv + nb - nlo - nhi, c = nlo - nb, g = nhi - nb;
+        if (a) atomicAdd(p, a);                                 // RED.ADD, 128 B per warp instruction
+        if (c) atomicAdd(p + stride, c);
+        if (g) atomicAdd(p + 2 * stride, g);
+        if (nb) atomicAdd(p + 3 * stride, nb);
     }
     __syncwarp();
 #pragma unroll
-    for (int w = 0; w < kW; w++) vc[w].clear();
-}
-
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n)
-{
-    uint32_t r;                                    // PTX shl clamps shift amounts above 31 (result 0)
-    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
-    return r;
-}
-// bits [a, e) of a 32-bit word; a, e may lie outside 0..32 (empty if e <= a)
-__device__ __forceinline__ uint32_t bit_range(int a, int e)
-{
-    return shl_clamp(0xFFFFFFFFu, (uint32_t)max(a, 0)) & ~shl_clamp(0xFFFFFFFFu, (uint32_t)max(e, 0));
-}
-
-// Masked one-hot words of one piece for this lane's kW window words (branch-free).
-//   pp / n1 : reference start and length of the (window-clipped) piece; n1 = 0 gives zeros
-//   sbit    : bit index, in the stage buffer, of the piece's first base (read fully staged)
-template <int G, bool HAS_OK>
-__device__ __forceinline__ void piece_words(uint32_t (&x)[kW][4], uint32_t pp, uint32_t n1, uint32_t win_lo, int wl,
-                                            const uint2 *__restrict__ sq, const uint32_t *__restrict__ okb, int sbit)
-{
-    const int rel = (int)(win_lo + 32u * kW * (uint32_t)wl) - (int)pp;   // piece offset of this lane's column 0
-    const int bit = sbit + rel;
-    const int sh = bit & 31;
-    // Out-of-piece words are masked away below, so only memory safety matters for the index.
-    const int base = min(max(bit >> 5, 0), (int)(kSeqCap + kSeqPad) - (kW + 1));
-    uint2 r[kW + 1];
-    uint32_t o[kW + 1];
-#pragma unroll
-    for (int i = 0; i <= kW; i++) {
-        r[i] = sq[base + i];
-        if (HAS_OK) o[i] = okb[base + i];
-    }
-#pragma unroll
     for (int w = 0; w < kW; w++) {
-        // columns of word w cover piece offsets rel + 32w .. rel + 32w + 31; valid offsets are [0, n1)
-        uint32_t m = bit_range(-rel - 32 * w, (int)n1 - rel - 32 * w);
-        if (HAS_OK) m &= __funnelshift_r(o[w], o[w + 1], sh);
-        const uint32_t lo = __funnelshift_r(r[w].x, r[w + 1].x, sh);
-        const uint32_t hi = __funnelshift_r(r[w].y, r[w + 1].y, sh);
-        x[w][0] = ~hi & ~lo & m;                                       // A
-        x[w][1] = ~hi & lo & m;                                        // C
-        x[w][2] = hi & ~lo & m;                                        // G
-        x[w][3] = hi & lo & m;                                         // T
-    }
-}
-
-// Same, for reads that are not (fully) staged: bounds-checked loads from HBM.
-template <int G, bool HAS_OK>
-__device__ __forceinline__ void piece_words_global(uint32_t (&x)[kW][4], uint32_t pp, uint32_t n1, uint32_t win_lo, int wl,
-                                                   const BatchView &bv, uint32_t pq, uint32_t wbase, uint32_t nwords)
-{
-    const int rel = (int)(win_lo + 32u * kW * (uint32_t)wl) - (int)pp;
-    const int bit = (int)pq + rel;                                     // read bit index of the lane's column 0
-    const int k = bit >> 5, sh = bit & 31;
-    uint2 r[kW + 1];
-    uint32_t o[kW + 1];
 #pragma unroll
-    for (int i = 0; i <= kW; i++) {
-        r[i] = make_uint2(0u, 0u);
-        o[i] = 0u;
-        if (n1 && k + i >= 0 && (uint32_t)(k + i) < nwords) {
-            r[i] = __ldg(bv.planes + wbase + (uint32_t)(k + i));
-            if (HAS_OK) o[i] = __ldg(bv.okmask + wbase + (uint32_t)(k + i));
+        for (int k = 0; k < kNC; k++) {
+#pragma unroll
+            for (int p = 0; p < kNB; p++) pl[w][k][p] = 0u;
+            pa[w][k] = 0u;
+            pb[w][k] = 0u;
+            pc[w][k] = 0u;
         }
-    }
-#pragma unroll
-    for (int w = 0; w < kW; w++) {
-        uint32_t m = bit_range(-rel - 32 * w, (int)n1 - rel - 32 * w);
-        if (HAS_OK) m &= __funnelshift_r(o[w], o[w + 1], sh);
-        const uint32_t lo = __funnelshift_r(r[w].x, r[w + 1].x, sh);
-        const uint32_t hi = __funnelshift_r(r[w].y, r[w + 1].y, sh);
-        x[w][0] = ~hi & ~lo & m;
-        x[w][1] = ~hi & lo & m;
-        x[w][2] = hi & ~lo & m;
-        x[w][3] = hi & lo & m;
     }
 }
 
 // The counting kernel.  One warp = one chunk of consecutive reads, processed in blocks of
-// `rpb` <= 32 reads.  Per block: metadata sits in registers (one read per lane, handed to the
-// read slots by shuffle); sequence / CIGAR words were staged in shared memory by TMA bulk
-// copies two blocks ahead.  Reads that are a single M/=/X run (the common case) go through a
-// branch-free fast loop, S reads per iteration; the rest (indels, clips, long or unstaged
-// reads, reads deferred by a window move) go through the general CIGAR state machine.
+// `rpb` <= 31 reads, one read per lane.
 template <int G, bool HAS_OK>
 __global__ void __launch_bounds__(kK1Threads, kK1MinCtas)
 k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb)
 {
-    constexpr int S = 32 / G;
-    constexpr uint32_t kWin = 32u * kW * G;         // window columns
-    constexpr uint32_t kMaxFit = kWin - 31u;        // a piece this long fits a fresh window at any alignment
-    constexpr uint32_t kStageWords = kSeqCap + kSeqPad;
+    using C = K1Cfg<G, HAS_OK>;
+    constexpr int S = C::S, Q = C::Q;
+    constexpr uint32_t kWin = C::kWin;
     extern __shared__ __align__(128) unsigned char k1_smem[];
 
     const int lane = threadIdx.x & 31;
     const int warp_in_cta = threadIdx.x >> 5;
-    const uint32_t warp_id = blockIdx.x * kK1WarpsPerCta + warp_in_cta;
-    if (warp_id >= n_chunks) return;                // warps are independent: no CTA-wide barrier anywhere
 
-    unsigned char *wsm = k1_smem + (size_t)warp_in_cta * k1_warp_smem_bytes<G, HAS_OK>();
-    uint2 *seq_buf = reinterpret_cast<uint2 *>(wsm);
-    uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u);
-    uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + kStages * kStageWords * 8u + (HAS_OK ? kStages * kStageWords * 4u : 0u));
-    uint16_t *frow = reinterpret_cast<uint16_t *>(cig_buf + kStages * kCigCap);
-    uint4 *ring = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(frow) + 4u * kW * G * kFlushStride * 2u);
-    uint8_t *order2 = reinterpret_cast<uint8_t *>(ring + kRing);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(order2 + 64);
+    // lut[v] = the 64 window columns of a lane at or above column v (v in [0, 64])
+    uint2 *lut = reinterpret_cast<uint2 *>(k1_smem);
+    for (int v = threadIdx.x; v <= 64; v += kK1Threads)
+        lut[v] = make_uint2(v < 32 ? 0xFFFFFFFFu << v : 0u, v <= 32 ? 0xFFFFFFFFu : (v < 64 ? 0xFFFFFFFFu << (v - 32) : 0u));
+    __syncthreads();                                // the only CTA-wide barrier: warps are independent from here on
+
+    const uint32_t warp_id = blockIdx.x * kK1WarpsPerCta + warp_in_cta;
+    if (warp_id >= n_chunks) return;
+
+    unsigned char *wsm = k1_smem + C::lut_bytes + (size_t)warp_in_cta * C::warp_bytes;
+    uint4 *ring = reinterpret_cast<uint4 *>(wsm + C::ring_off);
+    uint16_t *frow = reinterpret_cast<uint16_t *>(wsm + C::frow_off);
+    uint2 *seq_buf = reinterpret_cast<uint2 *>(wsm + C::seq_off);
+    uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + C::ok_off);
+    uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + C::cig_off);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + C::bar_off);
+    const uint2 *wsm2 = reinterpret_cast<const uint2 *>(wsm);       // word views of the whole warp region:
+    const uint32_t *wsm1 = reinterpret_cast<const uint32_t *>(wsm); // piece word indices are offsets into these
 
     const int slot = lane / G, wl = lane % G;
+    const int L0 = 32 * kW * wl;                    // window column of this lane's bit 0
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t slot_lead_below = (slot == 0) ? 0u : ((1u << (slot * G)) - 1u);
 
     const Chunk ch = chunks[warp_id];
     const uint32_t ref_len = ch.ref_len;
     const uint32_t rb = ch.read_begin, re = ch.read_end;
+    if (re <= rb) return;
     const uint32_t nblk = (re - rb + rpb - 1) / rpb;
-    const uint64_t col0 = ch.col_base;
+    uint32_t *const plane0 = cv.counts + ch.col_base;                       // plane A, column 0 of this slot
+    uint32_t *const ds_plane = plane0 + (uint64_t)kPlaneDS * cv.stride;
 
     if (lane == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+#pragma unroll
+        for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
+    // ---- block metadata: lane l holds read (block_first + l); lane l+1's offsets are read l's ends
+    struct Meta { uint32_t start, cbase, wbase; };
+    struct Range { uint32_t s_lo, s_n, c_lo, c_n; };     // what a stage holds: plane / okmask words, CIGAR words
     auto load_meta = [&](uint32_t blk) {
-        BlockMeta m = {0u, 0u, 0u, 0u, 0u};
+        Meta m = {0u, 0u, 0u};
         const uint64_t idx = (uint64_t)rb + (uint64_t)blk * rpb + lane;
-        if ((uint32_t)lane < rpb && idx < re) {
-            m.start = __ldg(bv.starts + idx);
+        if (blk < nblk && idx <= re) {
             m.cbase = __ldg(bv.cigar_off + idx);
-            m.cend = __ldg(bv.cigar_off + idx + 1);
             m.wbase = __ldg(bv.seq_woff + idx);
-            m.wend = __ldg(bv.seq_woff + idx + 1);
+            if (idx < re) m.start = __ldg(bv.starts + idx);
         }
         return m;
     };
-    // Stage the words of block `blk` (metadata m) into pipeline stage b.
-    auto issue_block = [&](uint32_t blk, const BlockMeta &m, int b) {
-        const uint32_t nvalid = min(rpb, re - (rb + blk * rpb));
-        const uint32_t s0 = __shfl_sync(kFull, m.wbase, 0);
-        const uint32_t s1 = __shfl_sync(kFull, m.wend, (int)nvalid - 1);
-        const uint32_t c0 = __shfl_sync(kFull, m.cbase, 0);
-        const uint32_t c1 = __shfl_sync(kFull, m.cend, (int)nvalid - 1);
-        StagedRange r;
+    auto block_range = [&](const Meta &m, uint32_t nvalid) {
+        const uint32_t s0 = __shfl_sync(kFull, m.wbase, 0), s1 = __shfl_sync(kFull, m.wbase, (int)nvalid);
+        const uint32_t c0 = __shfl_sync(kFull, m.cbase, 0), c1 = __shfl_sync(kFull, m.cbase, (int)nvalid);
+        Range r;
         r.s_lo = s0 & ~3u;                                           // 32 B / 16 B aligned sources
         r.s_n = min(((s1 + 3u) & ~3u) - r.s_lo, kSeqCap);
         r.c_lo = c0 & ~3u;
         r.c_n = min(((c1 + 3u) & ~3u) - r.c_lo, kCigCap);
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage
-            const uint32_t bytes = r.s_n * 8u + (HAS_OK ? r.s_n * 4u : 0u) + r.c_n * 4u;
-            mbar_expect_tx(&bars[b], bytes);
-            if (r.s_n) {
-                bulk_g2s(seq_buf + b * kStageWords + kSeqPad, bv.planes + r.s_lo, r.s_n * 8u, &bars[b]);
-                if (HAS_OK) bulk_g2s(ok_buf + b * kStageWords + kSeqPad, bv.okmask + r.s_lo, r.s_n * 4u, &bars[b]);
-            }
-            if (r.c_n) bulk_g2s(cig_buf + b * kCigCap, bv.cigar + r.c_lo, r.c_n * 4u, &bars[b]);
-        }
         return r;
     };
+    auto issue_block = [&](uint32_t blk, const Meta &m, uint32_t stg) {
+        const uint32_t nvalid = min(rpb, re - (rb + blk * rpb));
+        const Range r = block_range(m, nvalid);
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this stage
+            const uint32_t bytes = r.s_n * 8u + (HAS_OK ? r.s_n * 4u : 0u) + r.c_n * 4u;
+            mbar_expect_tx(&bars[stg], bytes);
+            if (r.s_n) {
+                bulk_g2s(seq_buf + stg * kSeqCap, bv.planes + r.s_lo, r.s_n * 8u, &bars[stg]);
+                if (HAS_OK) bulk_g2s(ok_buf + stg * kSeqCap, bv.okmask + r.s_lo, r.s_n * 4u, &bars[stg]);
+            }
+            if (r.c_n) bulk_g2s(cig_buf + stg * kCigCap, bv.cigar + r.c_lo, r.c_n * 4u, &bars[stg]);
+        }
+    };
 
-    BlockMeta m0 = load_meta(0), m1 = load_meta(1), m2 = load_meta(2);
-    StagedRange rg = issue_block(0, m0, 0);
-    StagedRange rg_nxt = {0u, 0u, 0u, 0u};
-    if (nblk > 1) rg_nxt = issue_block(1, m1, 1);
-    uint32_t parity = 0;                            // bit b: phase to wait for on stage b
+    Meta m0 = load_meta(0), m1 = load_meta(1), m2 = load_meta(2), m3 = load_meta(3);
+    issue_block(0, m0, 0);
+    if (nblk > 1) issue_block(1, m1, 1);
+    if (nblk > 2) issue_block(2, m2, 2);
+    uint32_t phases = 0;                            // bit s: parity to wait for on stage s
+    uint32_t st = 0;                                // stage of the current block
 
-    // warp-uniform window + counter + piece-ring state (persist across blocks)
-    uint32_t ring_head = 0, ring_tail = 0;
+    // ---- warp-uniform state that persists across blocks
+    uint32_t ring_head = 0, ring_tail = 0, mark = 0;      // mark: entries before it come from earlier blocks
     uint32_t win_lo = 0, cnt = 0;
     bool win_valid = false;
-    VCounters vc[kW];
+    uint32_t pl[kW][kNC][kNB], pa[kW][kNC], pb[kW][kNC], pc[kW][kNC];
 #pragma unroll
-    for (int w = 0; w < kW; w++) vc[w].clear();
-
-    auto do_flush = [&]() {
-        flush_counters<G>(vc, cnt, frow, col0 + win_lo, cv.counts, cv.stride, lane);
-        cnt = 0;
-    };
-    auto accumulate2 = [&](uint32_t (&xa)[kW][4], uint32_t (&xb)[kW][4]) {   // callers flush at kCntMax
+    for (int w = 0; w < kW; w++) {
 #pragma unroll
-        for (int w = 0; w < kW; w++) vc[w].add2(xa[w], xb[w], cnt);
-        cnt += 2;
+        for (int k = 0; k < kNC; k++) {
+#pragma unroll
+            for (int p = 0; p < kNB; p++) pl[w][k][p] = 0u;
+            pa[w][k] = 0u;
+            pb[w][k] = 0u;
+            pc[w][k] = 0u;
+        }
+    }
+
+    // Masked words of one piece for this lane's two window words.
+    //   e.x / e.y : first / end column of the piece, relative to the window
+    //   e.z       : bit index (in this warp's shared-memory region) of window column 0
+    auto piece = [&](const uint4 e, uint32_t (&x)[kW][kNC]) {
+        const int a_c = __viaddmin_s32_relu((int)e.x, -L0, 64);      // clamp(first - L0, 0, 64), one VIADDMNMX
+        const int e_c = __viaddmin_s32_relu((int)e.y, -L0, 64);
+        const uint2 ga = lut[a_c], ge = lut[e_c];
+        uint32_t m[kW] = {ga.x & ~ge.x, ga.y & ~ge.y};
+        const int bit = (int)e.z + L0;
+        const int wi = bit >> 5;
+        const uint2 r0 = wsm2[(int)(C::seq_off / 8u) + wi], r1 = wsm2[(int)(C::seq_off / 8u) + wi + 1],
+                    r2 = wsm2[(int)(C::seq_off / 8u) + wi + 2];
+        const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, (uint32_t)bit), __funnelshift_r(r1.x, r2.x, (uint32_t)bit)};
+        const uint32_t hi[kW] = {__funnelshift_r(r0.y, r1.y, (uint32_t)bit), __funnelshift_r(r1.y, r2.y, (uint32_t)bit)};
+        if (HAS_OK) {
+            const uint32_t o0 = wsm1[(int)(C::ok_off / 4u) + wi], o1 = wsm1[(int)(C::ok_off / 4u) + wi + 1],
+                           o2 = wsm1[(int)(C::ok_off / 4u) + wi + 2];
+            m[0] &= __funnelshift_r(o0, o1, (uint32_t)bit);
+            m[1] &= __funnelshift_r(o1, o2, (uint32_t)bit);
+        }
+#pragma unroll
+        for (int w = 0; w < kW; w++) {
+            x[w][0] = lo[w] & m[w];
+            x[w][1] = hi[w] & m[w];
+            x[w][2] = lo[w] & hi[w] & m[w];
+            x[w][3] = m[w];
+        }
     };
 
-    for (uint32_t j = 0; j < nblk; j++) {
-        const int b = (int)(j & 1u);
-        mbar_wait(&bars[b], (parity >> b) & 1u);
-        parity ^= 1u << b;
-        const uint2 *sq = seq_buf + b * kStageWords;
-        const uint32_t *okb = ok_buf + b * kStageWords;
-        const uint32_t *cg = cig_buf + b * kCigCap;
-        const uint32_t nvalid = min(rpb, re - (rb + j * rpb));
+    // j == nblk is a virtual empty block: it drains the ring and does the final flush in the
+    // same (single) trip / flush code as everything else.
+    for (uint32_t j = 0; j <= nblk; j++) {
+        const bool last = (j == nblk);
+        uint32_t nvalid = 0;
+        Range rg = {0u, 0u, 0u, 0u};
+        if (!last) {
+            mbar_wait(&bars[st], (phases >> st) & 1u);
+            phases ^= 1u << st;
+            nvalid = min(rpb, re - (rb + j * rpb));
+            rg = block_range(m0, nvalid);
+        }
+        const uint32_t *cg = cig_buf + st * kCigCap;
+        const int seg_bit0 = (int)(st * kSeqCap * 32u);              // bit index of the stage's first word
 
-        // ---- per-read classification, one read per lane: walk the read's own CIGAR and emit up
-        //      to two M/=/X pieces (adjacent match ops merge) into the piece ring; anything
-        //      bigger (more pieces, long pieces or skips, unstaged reads) goes to the general loop.
+        // ---- per-lane read state (count.cpp:35-38)
         const bool valid = (uint32_t)lane < nvalid;
-        const bool staged = valid && (m0.wbase - rg.s_lo) <= rg.s_n && (m0.wbase - rg.s_lo) + m0.nwords() <= rg.s_n;
-        const int my_sidx = staged ? (int)(m0.wbase - rg.s_lo + kSeqPad) : -1;
-        uint32_t pc_pp[2] = {0u, 0u}, pc_pq[2] = {0u, 0u}, pc_pn[2] = {0u, 0u};
-        uint32_t n_pc = 0, sk_pos = 0, sk_len = 0;
-        bool complex_read = valid && m0.ncig() && !staged;
-        if (valid && m0.ncig() && staged) {
-            uint32_t rpos = m0.start, qpos = 0;
-            bool open = false;                                           // last op was a match op (merge candidates)
-            for (uint32_t c = m0.cbase; c < m0.cbase + m0.ncig(); c++) {
-                const uint32_t ci = c - rg.c_lo;
-                const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + c);
-                const uint32_t op = cw & 0xFu, len = cw >> 4;
-                if (op_is_match(op)) {
-                    if (len) {
-                        if (open) {
-                            pc_pn[n_pc - 1] = sat_add(pc_pn[n_pc - 1], len);
-                        } else if (n_pc < 2) {
-                            pc_pp[n_pc] = rpos;
-                            pc_pq[n_pc] = qpos;
-                            pc_pn[n_pc] = len;
-                            n_pc++;
-                            open = true;
-                        } else {
-                            complex_read = true;
-                            break;
-                        }
-                    }
-                    rpos = sat_add(rpos, len);
-                    qpos = sat_add(qpos, len);
-                } else if (op == 1u) {
-                    qpos = sat_add(qpos, len);
-                    open = open && len == 0u;
-                } else if (op_is_refskip(op)) {
-                    if (len) {
-                        if (sk_len || len > kLaneSkipMax) {
-                            complex_read = true;
-                            break;
-                        }
-                        sk_pos = rpos;
-                        sk_len = len;
-                        open = false;
-                    }
-                    rpos = sat_add(rpos, len);
-                }
-            }
-            if (pc_pn[0] > kMaxFit || pc_pn[1] > kMaxFit) complex_read = true;
-        }
-        if (complex_read) n_pc = 0;
-        if (valid && !complex_read) {
-            // clip to the reference (count.cpp .at()): exactness decided by k1_check_overflow
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                if (pc_pn[i] && (pc_pp[i] >= ref_len || pc_pn[i] > ref_len - pc_pp[i])) {
-                    cv.status[kStatMaybeOverflow] = 1u;
-                    pc_pn[i] = pc_pp[i] < ref_len ? ref_len - pc_pp[i] : 0u;
-                }
-            }
-            if (sk_len) {                                                // deletion / skip, count.cpp:80-87
-                const uint32_t lim = sk_pos < ref_len ? min(sk_len, ref_len - sk_pos) : 0u;
-                if (lim < sk_len) cv.status[kStatIndexError] = 1u;
-                uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + col0 + sk_pos;
-                for (uint32_t t = 0; t < lim; t++) atomicAdd(ds + t, 1u);
-            }
-        }
-        const uint32_t has1 = __ballot_sync(kFull, n_pc >= 1u && pc_pn[0]);
-        const uint32_t has2 = __ballot_sync(kFull, n_pc >= 2u && pc_pn[1]);
-        uint32_t rest_mask = __ballot_sync(kFull, complex_read);
-        {
-            uint32_t at = ring_tail + __popc(has1 & lt_mask) + __popc(has2 & lt_mask);
-            if ((has1 >> lane) & 1u) {
-                ring[at & (kRing - 1)] = make_uint4(pc_pp[0], pc_pn[0], (uint32_t)(my_sidx * 32) + pc_pq[0], 0u);
-                at++;
-            }
-            if ((has2 >> lane) & 1u)
-                ring[at & (kRing - 1)] = make_uint4(pc_pp[1], pc_pn[1], (uint32_t)(my_sidx * 32) + pc_pq[1], 0u);
-            ring_tail += __popc(has1) + __popc(has2);
-        }
-        __syncwarp();
+        const uint32_t cbase = m0.cbase, cend_all = __shfl_down_sync(kFull, m0.cbase, 1);
+        const uint32_t wbase = m0.wbase, wend = __shfl_down_sync(kFull, m0.wbase, 1);
+        const bool staged = valid && (wend - rg.s_lo) <= rg.s_n;
+        uint32_t unst = __ballot_sync(kFull, valid && !staged && cend_all > cbase);   // reads to stage by hand
+        uint32_t cur = cbase, cend = staged ? cend_all : cbase;
+        uint32_t rpos = min(m0.start, ref_len), rem = 0u, ds_pos = 0u, ds_n = 0u;
+        int qb = seg_bit0 + (int)((wbase - rg.s_lo) * 32u);          // bit index of the next read base
+        int qend = qb + (int)((wend - wbase) * 32u);                 // end of the staged data of this read
+        bool issue_pending = (j >= 1u) && (j + 2u < nblk);           // block j+2 goes into block j-1's stage
+        int slow_lane = -1;                                          // lane whose read is staged by hand right now
+        uint32_t seg_w = 0u, seg_end = 0u;                           // its current segment / end (plane word indices)
 
-        // ---- fast loop: 2*S pieces per trip straight from the ring (two per read slot, so the
-        //      weight-1 adder needs no pending register); straight-line body; rare events
-        //      (flush, window move) are handled outside the tight inner loop
         for (;;) {
-            uint32_t fit_any = 0u, low_pp = 0xFFFFFFFFu;
-            while (ring_head != ring_tail) {
-                const uint32_t avail = ring_tail - ring_head;
-                const uint32_t adv = min((uint32_t)(2 * S), avail);     // entries consumed this trip
-                const bool have_a = (uint32_t)slot < avail, have_b = (uint32_t)(slot + S) < avail;
-                uint4 ea = ring[(ring_head + (uint32_t)slot) & (kRing - 1)];
-                uint4 eb = ring[(ring_head + (uint32_t)(slot + S)) & (kRing - 1)];
-                const bool fit_a = have_a && win_valid && ea.x >= win_lo && (ea.x - win_lo) <= kWin - ea.y;
-                const bool fit_b = have_b && win_valid && eb.x >= win_lo && (eb.x - win_lo) <= kWin - eb.y;
-                fit_any = __ballot_sync(kFull, fit_a || fit_b);
-                if (fit_any == 0u || cnt >= kCntMax) {
-                    low_pp = min(have_a ? ea.x : 0xFFFFFFFFu, have_b ? eb.x : 0xFFFFFFFFu);
-                    break;
-                }
-                const uint32_t unfit_a = __ballot_sync(kFull, have_a && !fit_a && wl == 0);
-                const uint32_t unfit_b = __ballot_sync(kFull, have_b && !fit_b && wl == 0);
-                if (unfit_a | unfit_b) {                                 // re-queue pieces that wait for a window move
-                    if (have_a && !fit_a && wl == 0) ring[(ring_tail + __popc(unfit_a & lt_mask)) & (kRing - 1)] = ea;
-                    if (have_b && !fit_b && wl == 0)
-                        ring[(ring_tail + __popc(unfit_a) + __popc(unfit_b & lt_mask)) & (kRing - 1)] = eb;
-                    ring_tail += __popc(unfit_a) + __popc(unfit_b);
-                    __syncwarp();
-                }
-                ring_head += adv;
-                uint32_t xa[kW][4], xb[kW][4];
-                piece_words<G, HAS_OK>(xa, ea.x, fit_a ? ea.y : 0u, win_lo, wl, sq, okb, (int)ea.z);
-                piece_words<G, HAS_OK>(xb, eb.x, fit_b ? eb.y : 0u, win_lo, wl, sq, okb, (int)eb.z);
-                accumulate2(xa, xb);
+            // ---- F: fetch CIGAR ops until an M/=/X run is open (count.cpp:40-96)
+            bool moved = false;
+            while (rem == 0u && ds_n == 0u && cur < cend) {
+                const uint32_t ci = cur - rg.c_lo;
+                const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + cur);
+                cur++;
+                moved = true;
+                const uint32_t op = cw & 15u, len = cw >> 4;
+                const uint32_t cls = (kOpClass >> (2u * op)) & 3u;
+                if (cls == 1u) {                                     // M / = / X, count.cpp:51
+                    const uint32_t lim = ref_len - rpos;
+                    if (len > lim) cv.status[kStatMaybeOverflow] = 1u;   // would index past the matrix: exact check later
+                    rem = min(len, lim);
+                } else if (cls == 2u) {                              // insertion, count.cpp:74
+                    qb = (int)min((uint32_t)qb + len, 1u << 30);
+                } else if (cls == 3u) {                              // deletion / skip, count.cpp:80-87
+                    const uint32_t lim = ref_len - rpos, n = min(len, lim);
+                    if (len > lim) cv.status[kStatIndexError] = 1u;
+                    if (n <= kLaneSkipMax) {
+                        for (uint32_t t = 0; t < n; t++) atomicAdd(ds_plane + rpos + t, 1u);
+                    } else {
+                        ds_pos = rpos;
+                        ds_n = n;
+                    }
+                    rpos += n;
+                }                                                    // S, H, P, B: ignored, count.cpp:92-95
             }
-            if (ring_head == ring_tail) break;
-            if (cnt) do_flush();
-            if (fit_any == 0u) {                                         // nobody fits: move the window
-                win_lo = __reduce_min_sync(kFull, low_pp) & ~31u;
-                win_valid = true;
+            // ---- D: long D/N runs, all lanes help
+            uint32_t dsm = __ballot_sync(kFull, ds_n != 0u);
+            while (dsm) {
+                const int src = __ffs((int)dsm) - 1;
+                dsm &= dsm - 1u;
+                const uint32_t p = __shfl_sync(kFull, ds_pos, src), n = __shfl_sync(kFull, ds_n, src);
+                for (uint32_t t = lane; t < n; t += 32u) atomicAdd(ds_plane + p + t, 1u);
             }
-        }
-
-        // ---- general loop: CIGAR state machine over the remaining reads of the block
-        if (rest_mask) {
-            if ((rest_mask >> lane) & 1u) order2[__popc(rest_mask & lt_mask)] = (uint8_t)lane;
-            __syncwarp();
-            const uint32_t n_rest = __popc(rest_mask);
-            uint32_t cursor = 0;
-            // per read-slot state (replicated over the slot's G lanes)
-            uint32_t cur = 0, cend = 0, ref_pos = 0, read_pos = 0, wbase = 0, nwords = 0;
-            int sidx = -1;
-            bool exhausted = false;
-            uint32_t pp = 0, pq = 0, pn = 0;        // pending M/=/X piece: ref pos, read pos, length
+            ds_n = 0u;
+            // ---- P: the part of the open run that fits the window becomes a piece
+            const uint32_t relp = rpos - win_lo;
+            uint32_t n1 = 0u;
+            if (rem != 0u && win_valid && relp < kWin && qb < qend)
+                n1 = min(min(rem, kWin - relp), (uint32_t)(qend - qb));
+            const uint32_t pm = __ballot_sync(kFull, n1 != 0u);
+            if (pm) {
+                __syncwarp();                                        // earlier ring reads are done
+                if (n1) {
+                    ring[(ring_tail + __popc(pm & lt_mask)) & (kRing - 1u)] =
+                        make_uint4(relp, relp + n1, (uint32_t)(qb - (int)relp), 0u);
+                    rpos += n1;
+                    qb += (int)n1;
+                    rem -= n1;
+                    moved = true;
+                }
+                ring_tail += __popc(pm);
+                __syncwarp();
+            }
+            // ---- what next?  0: keep walking, 1: everyone waits for a window move, 2: this pass is over
+            int action = 0;
+            uint32_t new_lo = 0u;
+            if (!__any_sync(kFull, cur < cend || rem != 0u)) {
+                action = 2;
+            } else if (!__any_sync(kFull, moved)) {
+                const bool wst = rem != 0u && qb < qend;             // waits for the window (not for data)
+                if (__any_sync(kFull, wst)) {
+                    action = 1;
+                    new_lo = __reduce_min_sync(kFull, wst ? rpos : 0xFFFFFFFFu) & ~31u;
+                } else {
+                    action = 2;
+                }
+            }
+            // ---- the one trip site and the one flush site
             for (;;) {
-                // A: read slots that finished their read pull the next ones, in order
-                const bool need = (pn == 0u) && (cur == cend) && !exhausted;
-                const uint32_t need_mask = __ballot_sync(kFull, need && wl == 0);
-                if (need_mask) {
-                    const uint32_t idx = cursor + __popc(need_mask & slot_lead_below);
-                    const bool take = need && idx < n_rest;
-                    const int src = take ? (int)order2[idx] : 0;
-                    const uint32_t t_start = __shfl_sync(kFull, m0.start, src);
-                    const uint32_t t_cbase = __shfl_sync(kFull, m0.cbase, src);
-                    const uint32_t t_ncig = __shfl_sync(kFull, m0.ncig(), src);
-                    const uint32_t t_wbase = __shfl_sync(kFull, m0.wbase, src);
-                    const uint32_t t_nwords = __shfl_sync(kFull, m0.nwords(), src);
-                    const int t_sidx = __shfl_sync(kFull, my_sidx, src);
-                    if (take) {
-                        ref_pos = t_start;
-                        cur = t_cbase;
-                        cend = t_cbase + t_ncig;
-                        wbase = t_wbase;
-                        nwords = t_nwords;
-                        sidx = t_sidx;
-                        read_pos = 0;
-                    } else if (need) {
-                        exhausted = true;
+                const uint32_t avail = ring_tail - ring_head;
+                bool want_flush;
+                if (avail >= (uint32_t)Q) {
+                    want_flush = (cnt == kCntMax);
+                } else {
+                    const bool drain = action == 1 || (action == 2 && (last || unst != 0u || slow_lane >= 0 ||
+                                                                       (issue_pending && (int)(ring_head - mark) < 0)));
+                    if (avail != 0u && drain) {                      // pad the ring with empty pieces to a full trip
+                        if ((uint32_t)lane < (uint32_t)Q - avail) ring[(ring_tail + lane) & (kRing - 1u)] = make_uint4(0u, 0u, 0u, 0u);
+                        ring_tail += (uint32_t)Q - avail;
+                        __syncwarp();
+                        continue;
                     }
-                    cursor += __popc(need_mask);
+                    want_flush = cnt != 0u && (action == 1 || (action == 2 && last));
+                    if (!want_flush) break;
                 }
-                // B: no piece pending -> consume one CIGAR op (count.cpp:40-96)
-                if (pn == 0u && cur < cend) {
-                    const uint32_t ci = cur - rg.c_lo;
-                    const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + cur);
-                    cur++;
-                    const uint32_t op = cw & 0xFu, len = cw >> 4;
-                    if (op_is_match(op)) {                                   // count.cpp:51
-                        pp = ref_pos;
-                        pq = read_pos;
-                        pn = len;
-                        ref_pos = sat_add(ref_pos, len);
-                        read_pos = sat_add(read_pos, len);
-                        if (pn && (pp >= ref_len || pn > ref_len - pp)) {    // would index past the matrix
-                            if (wl == 0) cv.status[kStatMaybeOverflow] = 1u;
-                            pn = pp < ref_len ? ref_len - pp : 0u;
-                        }
-                    } else if (op == 1u) {                                   // insertion, count.cpp:74
-                        read_pos = sat_add(read_pos, len);
-                    } else if (op_is_refskip(op)) {                          // deletion / skip, count.cpp:80-87
-                        uint32_t lim = ref_pos < ref_len ? min(len, ref_len - ref_pos) : 0u;
-                        if (lim < len && wl == 0) cv.status[kStatIndexError] = 1u;
-                        uint32_t *ds = cv.counts + (uint64_t)kPlaneDS * cv.stride + col0 + ref_pos;
-                        for (uint32_t t = wl; t < lim; t += G) atomicAdd(ds + t, 1u);
-                        ref_pos = sat_add(ref_pos, len);
-                    }                                                        // S,H,P,B: ignored, count.cpp:92-95
-                }
-                // C: done with the block?
-                const bool active = pn > 0u;
-                if (!__any_sync(kFull, active || cur < cend || !exhausted)) break;
-                // D: which pieces can go into the current window?
-                const bool fits = active && win_valid && pp >= win_lo && (pp - win_lo) < kWin &&
-                                  (pn <= kWin - (pp - win_lo) || pn > kMaxFit);
-                const uint32_t fit_any = __ballot_sync(kFull, fits);
-                if (fit_any == 0u || cnt >= kCntMax) {                       // the one flush site of this loop
-                    if (fit_any == 0u && __ballot_sync(kFull, active) == 0u) continue;   // still walking ops / fetching
-                    if (cnt) do_flush();
-                    if (fit_any == 0u) {
-                        win_lo = __reduce_min_sync(kFull, active ? pp : 0xFFFFFFFFu) & ~31u;
-                        win_valid = true;
-                    }
+                if (want_flush) {
+                    flush_counters<G>(pl, pa, pb, pc, cnt, frow, plane0 + win_lo, cv.stride, lane);
+                    cnt = 0u;
                     continue;
                 }
-                // E: masked words of the fitting pieces, added to the vertical counters
-                uint32_t x[kW][4], zero[kW][4] = {};
-                const uint32_t n1 = fits ? min(pn, kWin - (pp - win_lo)) : 0u;
-                if (sidx >= 0) piece_words<G, HAS_OK>(x, pp, n1, win_lo, wl, sq, okb, sidx * 32 + (int)pq);
-                else piece_words_global<G, HAS_OK>(x, pp, n1, win_lo, wl, bv, pq, wbase, nwords);
-                accumulate2(x, zero);
-                pp += n1;
-                pq += n1;
-                pn -= n1;
+                // -- trip: four pieces per read slot, straight-line
+                uint4 e[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) e[q] = ring[(ring_head + (uint32_t)(q * S + slot)) & (kRing - 1u)];
+                ring_head += (uint32_t)Q;
+                uint32_t x[4][kW][kNC];
+#pragma unroll
+                for (int q = 0; q < 4; q++) piece(e[q], x[q]);
+                uint32_t c2[kW][kNC];
+#pragma unroll
+                for (int w = 0; w < kW; w++) {
+#pragma unroll
+                    for (int k = 0; k < kNC; k++) {
+                        const uint32_t c1a = maj3(pl[w][k][0], x[0][w][k], x[1][w][k]);
+                        const uint32_t t = pl[w][k][0] ^ x[0][w][k] ^ x[1][w][k];
+                        const uint32_t c1b = maj3(t, x[2][w][k], x[3][w][k]);
+                        pl[w][k][0] = t ^ x[2][w][k] ^ x[3][w][k];
+                        c2[w][k] = maj3(pl[w][k][1], c1a, c1b);
+                        pl[w][k][1] ^= c1a ^ c1b;
+                    }
+                }
+                if (!(cnt & 4u)) {
+#pragma unroll
+                    for (int w = 0; w < kW; w++)
+#pragma unroll
+                        for (int k = 0; k < kNC; k++) pa[w][k] = c2[w][k];
+                } else {
+                    uint32_t c3[kW][kNC];
+#pragma unroll
+                    for (int w = 0; w < kW; w++) {
+#pragma unroll
+                        for (int k = 0; k < kNC; k++) {
+                            c3[w][k] = maj3(pl[w][k][2], pa[w][k], c2[w][k]);
+                            pl[w][k][2] ^= pa[w][k] ^ c2[w][k];
+                        }
+                    }
+                    if (!(cnt & 8u)) {
+#pragma unroll
+                        for (int w = 0; w < kW; w++)
+#pragma unroll
+                            for (int k = 0; k < kNC; k++) pb[w][k] = c3[w][k];
+                    } else {
+                        uint32_t c4[kW][kNC];
+#pragma unroll
+                        for (int w = 0; w < kW; w++) {
+#pragma unroll
+                            for (int k = 0; k < kNC; k++) {
+                                c4[w][k] = maj3(pl[w][k][3], pb[w][k], c3[w][k]);
+                                pl[w][k][3] ^= pb[w][k] ^ c3[w][k];
+                            }
+                        }
+                        if (!(cnt & 16u)) {
+#pragma unroll
+                            for (int w = 0; w < kW; w++)
+#pragma unroll
+                                for (int k = 0; k < kNC; k++) pc[w][k] = c4[w][k];
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < kW; w++) {
+#pragma unroll
+                                for (int k = 0; k < kNC; k++) {
+                                    uint32_t c = maj3(pl[w][k][4], pc[w][k], c4[w][k]);
+                                    pl[w][k][4] ^= pc[w][k] ^ c4[w][k];
+#pragma unroll
+                                    for (int p = 5; p < kNB; p++) {  // ripple the weight-32 carry upwards
+                                        const uint32_t t = pl[w][k][p] & c;
+                                        pl[w][k][p] ^= c;
+                                        c = t;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                cnt += 4u;
+            }
+            if (issue_pending && (int)(ring_head - mark) >= 0) {     // block j-1's pieces are all counted
+                issue_block(j + 2u, m2, st == 0u ? 2u : st - 1u);
+                issue_pending = false;
+            }
+            if (action == 1) {
+                win_lo = new_lo;
+                win_valid = true;
+            }
+            if (action != 2) continue;
+
+            // ---- pass over: reads that were not staged are copied into this stage segment by segment
+            if (slow_lane >= 0) {
+                const int done = __shfl_sync(kFull, (int)(cur >= cend && rem == 0u), slow_lane);
+                const int qb_u = __shfl_sync(kFull, qb, slow_lane);
+                const uint32_t adv = (uint32_t)(qb_u - seg_bit0) >> 5;      // whole words already consumed
+                if (done || adv == 0u || adv >= seg_end - seg_w) {          // finished (or the CIGAR overruns the read)
+                    if (lane == slow_lane) {
+                        cur = cend;
+                        rem = 0u;
+                    }
+                    slow_lane = -1;
+                } else {
+                    seg_w += adv;
+                    if (lane == slow_lane) qb -= (int)(adv * 32u);
+                }
+            }
+            if (slow_lane < 0) {
+                if (unst == 0u) break;
+                slow_lane = __ffs((int)unst) - 1;
+                unst &= unst - 1u;
+                seg_w = __shfl_sync(kFull, wbase, slow_lane);
+                seg_end = __shfl_sync(kFull, wend, slow_lane);
+                if (lane == slow_lane) {
+                    cur = cbase;
+                    cend = cend_all;
+                    rpos = min(m0.start, ref_len);
+                    rem = 0u;
+                    qb = seg_bit0;
+                }
+            }
+            {
+                const uint32_t nw = min(seg_end - seg_w, kSeqCap);
+                for (uint32_t i = lane; i < nw; i += 32u) {
+                    seq_buf[st * kSeqCap + i] = __ldg(bv.planes + seg_w + i);
+                    if (HAS_OK) ok_buf[st * kSeqCap + i] = __ldg(bv.okmask + seg_w + i);
+                }
+                if (lane == slow_lane) qend = seg_bit0 + (int)(nw * 32u);
+                __syncwarp();
             }
         }
 
-        // ---- stage b is free again: refill it with block j+2, rotate the metadata pipeline
-        __syncwarp();
+        // ---- rotate the pipelines
+        mark = ring_tail;
+        st = (st == (uint32_t)kStages - 1u) ? 0u : st + 1u;
         m0 = m1;
         m1 = m2;
-        rg = rg_nxt;
-        if (j + 2 < nblk) rg_nxt = issue_block(j + 2, m1, b);
-        m2 = load_meta(j + 3);
+        m2 = m3;
+        m3 = load_meta(j + 4u);
     }
-    if (cnt) do_flush();
 }
 
 // Cross-check variant: one thread per read, one RED per base.  Same inputs, same planes.
