@@ -39,13 +39,15 @@ constexpr int kK1WarpsPerCta = 4;
 constexpr int kK1MinCtas = 3;
 constexpr int kK1Threads = kK1WarpsPerCta * 32;
 constexpr int kNB = 8;                        // bit planes per vertical counter (counts to 255)
+constexpr int kNR = 5;                        // planes 0..4 live in registers; planes 5..7 and the weight-16 pending
+                                              // carry are touched every 8th / 4th trip only and live in shared memory
+constexpr uint32_t kSpillWords = 32;          // per lane: 8 counters x (pending + 3 planes); aliases the flush rows
 constexpr int kNC = 4;                        // counted quantities per window word: lo, hi, lo&hi, valid
 constexpr int kW = 2;                         // window words per lane
 constexpr int kStages = 3;                    // TMA pipeline depth (blocks of reads)
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr uint32_t kSeqCap = 448;             // staged 64-bit plane words per stage (31 reads x 13 words + slack)
 constexpr uint32_t kCigCap = 96;              // staged CIGAR words per stage; the rest is read from HBM
-constexpr uint32_t kRing = 64;                // piece ring entries (uint4 each)
 constexpr uint32_t kCntMax = 252;             // pieces per slot between flushes (8-plane counters, 4 per trip)
 constexpr uint32_t kFlushStride = 34;         // uint16 per staged window word (32 + 2 pad: conflict-free stores)
 constexpr uint32_t kMaxRpb = 31;              // reads per block: lane i+1 holds the end offsets of read i
@@ -102,12 +104,15 @@ template <int G, bool HAS_OK>
 struct K1Cfg {
     static constexpr int S = 32 / G;                        // read slots per warp
     static constexpr int Q = 4 * S;                         // ring entries consumed per trip
+    static constexpr uint32_t kRing = Q >= 32 ? 128u : 64u; // piece ring entries (uint4 each): a leftover + one block
     static constexpr uint32_t kWin = 32u * kW * G;          // window columns
+    static constexpr uint32_t kMaxFit = kWin - 31u;         // a piece this long fits a fresh window at any alignment
     static constexpr uint32_t kCols = kFlushStride * kW * G;   // uint16 per flush row
     static constexpr uint32_t lut_bytes = 528;              // 65 x uint2, padded to 16 B
     static constexpr uint32_t ring_off = 0;
     static constexpr uint32_t frow_off = ring_off + kRing * 16u;
-    static constexpr uint32_t seq_off = frow_off + kNC * kCols * 2u;
+    static constexpr uint32_t frow_bytes = kNC * kCols * 2u > kSpillWords * 128u ? kNC * kCols * 2u : kSpillWords * 128u;
+    static constexpr uint32_t seq_off = frow_off + frow_bytes;
     static constexpr uint32_t ok_off = seq_off + kStages * kSeqCap * 8u;
     static constexpr uint32_t cig_off = ok_off + (HAS_OK ? kStages * kSeqCap * 4u : 0u);
     static constexpr uint32_t bar_off = cig_off + kStages * kCigCap * 4u;
@@ -124,90 +129,132 @@ __host__ __device__ constexpr uint32_t k1_cta_smem_bytes()
     return K1Cfg<G, HAS_OK>::cta_bytes;
 }
 
+__device__ __forceinline__ void red_add_nz(uint32_t *p, uint32_t v)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %1, 0;\n@q red.global.add.u32 [%0], %1;\n}\n" ::"l"(p), "r"(v) : "memory");
+}
+
 // Convert the warp's vertical counters to integers and add them to the HBM planes.
-// Pending carries are folded in first; then byte-packed extraction per slot, widened to 16 bit
-// before the S read slots are summed (each slot holds at most 252), staged in shared memory,
-// turned into letter counts and written with coalesced RED.ADD (128 B per warp instruction).
-// The loop over the shift amount jj is deliberately NOT unrolled: registers stay statically
-// indexed while the code stays a few hundred instructions.
-//   frow: kNC rows x (kW*G window words x kFlushStride) uint16;  counts: plane A at window column 0
+//   1. every lane rebuilds its eight full 8-plane counters (planes 5..7 and the weight-16 pending
+//      carry come back from shared memory; pending carries are folded in);
+//   2. the S read slots that cover the same window words add their counters IN BIT-SLICED FORM
+//      (a ripple-carry adder over the planes, operands exchanged by shuffle), each keeping half
+//      of the counters per round, so after log2(S) rounds a lane holds 8/S counters of the
+//      window totals and only those are extracted;
+//   3. byte-packed extraction (the loop over the shift amount jj is deliberately NOT unrolled:
+//      registers stay statically indexed while the code stays small), staged as uint16 rows;
+//   4. letters from the four counted quantities, written with coalesced RED.ADD (128 B per
+//      warp instruction), zeros skipped.
+//   frow: kNC rows x (kW*G window words x kFlushStride) uint16, aliasing the spill words
+//   counts: plane A at window column 0
 template <int G>
-__device__ __forceinline__ void flush_counters(uint32_t (&pl)[kW][kNC][kNB], uint32_t (&pa)[kW][kNC],
-                                               uint32_t (&pb)[kW][kNC], uint32_t (&pc)[kW][kNC], uint32_t cnt,
-                                               uint16_t *frow, uint32_t *__restrict__ counts, uint64_t stride, int lane)
+__device__ __forceinline__ void flush_counters(uint32_t (&pl)[kW][kNC][kNR], uint32_t (&pa)[kW][kNC],
+                                               uint32_t (&pb)[kW][kNC], uint32_t cnt, uint16_t *frow,
+                                               uint32_t *__restrict__ counts, uint64_t stride, int lane)
 {
     constexpr int S = 32 / G;
+    constexpr int R = S == 8 ? 3 : (S == 4 ? 2 : (S == 2 ? 1 : 0));      // combine rounds
     constexpr int kCols = (int)kFlushStride * kW * G;
+    constexpr int kN = kW * kNC;                                          // counters per lane (8)
     const int slot = lane / G, wl = lane % G;
+    const uint32_t *sp = reinterpret_cast<const uint32_t *>(frow);
+    uint32_t A[kN][kNB + 3];
 #pragma unroll
     for (int w = 0; w < kW; w++) {
 #pragma unroll
         for (int k = 0; k < kNC; k++) {
+            const int i = w * kNC + k;
+#pragma unroll
+            for (int p = 0; p < kNR; p++) A[i][p] = pl[w][k][p];
+#pragma unroll
+            for (int p = kNR; p < kNB; p++) A[i][p] = cnt >= 32u ? sp[(i * 4 + (p - kNR + 1)) * 32 + lane] : 0u;
             // pending carries of weight 4 / 8 / 16 are live iff that bit of cnt is set
             uint32_t c = (cnt & 4u) ? pa[w][k] : 0u;
-#pragma unroll
-            for (int p = 2; p < kNB; p++) {
-                if (p == 3) {
-                    const uint32_t d = (cnt & 8u) ? pb[w][k] : 0u;    // two carries into plane 3: full adder
-                    const uint32_t t = maj3(pl[w][k][p], c, d);
-                    pl[w][k][p] ^= c ^ d;
-                    c = t;
-                } else if (p == 4) {
-                    const uint32_t d = (cnt & 16u) ? pc[w][k] : 0u;
-                    const uint32_t t = maj3(pl[w][k][p], c, d);
-                    pl[w][k][p] ^= c ^ d;
-                    c = t;
-                } else {
-                    const uint32_t t = pl[w][k][p] & c;
-                    pl[w][k][p] ^= c;
-                    c = t;
-                }
+            {
+                const uint32_t t = A[i][2] & c;
+                A[i][2] ^= c;
+                c = t;
             }
+            {
+                const uint32_t d = (cnt & 8u) ? pb[w][k] : 0u;            // two carries into plane 3: full adder
+                const uint32_t t = maj3(A[i][3], c, d);
+                A[i][3] ^= c ^ d;
+                c = t;
+            }
+            {
+                const uint32_t d = (cnt & 16u) ? sp[(i * 4) * 32 + lane] : 0u;
+                const uint32_t t = maj3(A[i][4], c, d);
+                A[i][4] ^= c ^ d;
+                c = t;
+            }
+#pragma unroll
+            for (int p = 5; p < kNB; p++) {
+                const uint32_t t = A[i][p] & c;
+                A[i][p] ^= c;
+                c = t;
+            }
+#pragma unroll
+            for (int p = kNB; p < kNB + 3; p++) A[i][p] = 0u;
         }
     }
-    const bool high = cnt >= 16u;                         // planes 4..7 can only be set after 16 inputs
+    __syncwarp();                                     // all spill words are read before the rows are written
+    // ---- bit-sliced sum over the read slots
+    int first = 0;                                    // counter index (w * kNC + k) of A[0] after the rounds
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int d = G << r;
+        const int h = kN >> (r + 1);
+        const bool up = (slot >> r) & 1;
+        if (up) first += h;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            uint32_t carry = 0u;
+#pragma unroll
+            for (int p = 0; p < kNB + r; p++) {
+                const uint32_t mine = up ? A[h + i][p] : A[i][p];
+                const uint32_t give = up ? A[i][p] : A[h + i][p];
+                const uint32_t got = __shfl_xor_sync(kFull, give, d);
+                A[i][p] = mine ^ got ^ carry;
+                carry = maj3(mine, got, carry);
+            }
+            A[i][kNB + r] = carry;
+        }
+    }
+    constexpr int kLeft = kN >> R;                    // counters this lane extracts
+    const bool high = cnt * (uint32_t)S >= 16u;       // planes 4.. can only be set once 16 inputs went in
 #pragma unroll 1
     for (int jj = 0; jj < 8; jj++) {
-        const bool mine = (jj % S) == slot;
 #pragma unroll
-        for (int k = 0; k < kNC; k++) {
+        for (int i = 0; i < kLeft; i++) {
+            uint32_t acc = 0u, acc2 = 0u;             // byte t = count of column jj + 8t: low 8 bits / bits 8..
 #pragma unroll
-            for (int w = 0; w < kW; w++) {
-                uint32_t acc = 0;                         // byte t = count of column jj + 8t (this slot only)
+            for (int p = 0; p < 4; p++) acc += ((A[i][p] >> jj) & 0x01010101u) << p;
+            if (high) {
 #pragma unroll
-                for (int p = 0; p < 4; p++) acc += ((pl[w][k][p] >> jj) & 0x01010101u) << p;
-                if (high) {
+                for (int p = 4; p < kNB; p++) acc += ((A[i][p] >> jj) & 0x01010101u) << p;
 #pragma unroll
-                    for (int p = 4; p < kNB; p++) acc += ((pl[w][k][p] >> jj) & 0x01010101u) << p;
-                }
-                uint32_t ev = acc & 0x00FF00FFu;          // columns jj, jj+16
-                uint32_t od = (acc >> 8) & 0x00FF00FFu;   // columns jj+8, jj+24
-#pragma unroll
-                for (int d = G; d < 32; d <<= 1) {        // sum the read slots (<= 8 * 252 fits 16 bit)
-                    ev += __shfl_xor_sync(kFull, ev, d);
-                    od += __shfl_xor_sync(kFull, od, d);
-                }
-                if (mine) {
-                    uint16_t *dst = frow + k * kCols + (kW * wl + w) * (int)kFlushStride + jj;
-                    dst[0] = (uint16_t)ev;
-                    dst[16] = (uint16_t)(ev >> 16);
-                    dst[8] = (uint16_t)od;
-                    dst[24] = (uint16_t)(od >> 16);
-                }
+                for (int p = 0; p < R; p++) acc2 += ((A[i][kNB + p] >> jj) & 0x01010101u) << p;
             }
+            const uint32_t ev = (acc & 0x00FF00FFu) + ((acc2 & 0x00FF00FFu) << 8);               // columns jj, jj+16
+            const uint32_t od = ((acc >> 8) & 0x00FF00FFu) + (((acc2 >> 8) & 0x00FF00FFu) << 8);  // columns jj+8, jj+24
+            const int ci = first + i, w = ci / kNC, k = ci % kNC;
+            uint16_t *dst = frow + k * kCols + (kW * wl + w) * (int)kFlushStride + jj;
+            dst[0] = (uint16_t)ev;
+            dst[16] = (uint16_t)(ev >> 16);
+            dst[8] = (uint16_t)od;
+            dst[24] = (uint16_t)(od >> 16);
         }
     }
     __syncwarp();
-#pragma unroll 2
+    uint32_t *const pA = counts + lane, *const pC = pA + stride, *const pG = pC + stride, *const pT = pG + stride;
+#pragma unroll
     for (int w = 0; w < kW * G; w++) {
         const int at = (int)kFlushStride * w + lane;
         const uint32_t nlo = frow[at], nhi = frow[kCols + at], nb = frow[2 * kCols + at], nv = frow[3 * kCols + at];
-        uint32_t *p = counts + 32 * w + lane;
-        const uint32_t a = nv + nb - nlo - nhi, c = nlo - nb, g = nhi - nb;
-        if (a) atomicAdd(p, a);                                 // RED.ADD, 128 B per warp instruction
-        if (c) atomicAdd(p + stride, c);
-        if (g) atomicAdd(p + 2 * stride, g);
-        if (nb) atomicAdd(p + 3 * stride, nb);
+        red_add_nz(pA + 32 * w, nv + nb - nlo - nhi);           // RED.ADD, 128 B per warp instruction
+        red_add_nz(pC + 32 * w, nlo - nb);
+        red_add_nz(pG + 32 * w, nhi - nb);
+        red_add_nz(pT + 32 * w, nb);
     }
     __syncwarp();
 #pragma unroll
@@ -215,10 +262,9 @@ __device__ __forceinline__ void flush_counters(uint32_t (&pl)[kW][kNC][kNB], uin
 #pragma unroll
         for (int k = 0; k < kNC; k++) {
 #pragma unroll
-            for (int p = 0; p < kNB; p++) pl[w][k][p] = 0u;
+            for (int p = 0; p < kNR; p++) pl[w][k][p] = 0u;
             pa[w][k] = 0u;
             pb[w][k] = 0u;
-            pc[w][k] = 0u;
         }
     }
 }
@@ -231,7 +277,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
 {
     using C = K1Cfg<G, HAS_OK>;
     constexpr int S = C::S, Q = C::Q;
-    constexpr uint32_t kWin = C::kWin;
+    constexpr uint32_t kWin = C::kWin, kRing = C::kRing;
     extern __shared__ __align__(128) unsigned char k1_smem[];
 
     const int lane = threadIdx.x & 31;
@@ -324,18 +370,18 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     uint32_t ring_head = 0, ring_tail = 0, mark = 0;      // mark: entries before it come from earlier blocks
     uint32_t win_lo = 0, cnt = 0;
     bool win_valid = false;
-    uint32_t pl[kW][kNC][kNB], pa[kW][kNC], pb[kW][kNC], pc[kW][kNC];
+    uint32_t pl[kW][kNC][kNR], pa[kW][kNC], pb[kW][kNC];
 #pragma unroll
     for (int w = 0; w < kW; w++) {
 #pragma unroll
         for (int k = 0; k < kNC; k++) {
 #pragma unroll
-            for (int p = 0; p < kNB; p++) pl[w][k][p] = 0u;
+            for (int p = 0; p < kNR; p++) pl[w][k][p] = 0u;
             pa[w][k] = 0u;
             pb[w][k] = 0u;
-            pc[w][k] = 0u;
         }
     }
+    uint32_t *const sp = reinterpret_cast<uint32_t *>(frow) + lane;   // this lane's spill words, 32 apart
 
     // Masked words of one piece for this lane's two window words.
     //   e.x / e.y : first / end column of the piece, relative to the window
@@ -370,6 +416,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     // same (single) trip / flush code as everything else.
     for (uint32_t j = 0; j <= nblk; j++) {
         const bool last = (j == nblk);
+        const Meta m4 = load_meta(j + 4u);                           // rotated in at the end of this block
         uint32_t nvalid = 0;
         Range rg = {0u, 0u, 0u, 0u};
         if (!last) {
@@ -395,9 +442,96 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         int slow_lane = -1;                                          // lane whose read is staged by hand right now
         uint32_t seg_w = 0u, seg_end = 0u;                           // its current segment / end (plane word indices)
 
+        // ---- fast path: every lane walks its whole CIGAR privately (no votes inside); if every read
+        //      has at most two M/=/X runs (adjacent ones merge) and one short D/N run, and all of them
+        //      fit the current window, the pieces are committed in one go.  Anything else (window
+        //      moves, long or many runs, hand-staged reads) takes the lock-step walker below, which
+        //      starts the block from scratch: nothing here has side effects before the commit
+        //      (the status flags are idempotent).
+        bool prewalked = false;
+        if (!last) {
+            uint32_t fpp0 = 0u, fpp1 = 0u, fpn0 = 0u, fpn1 = 0u, n_pc = 0u, sk_pos = 0u, sk_n = 0u;
+            int fpq0 = 0, fpq1 = 0;
+            bool bad = unst != 0u;
+            if (staged) {
+                uint32_t r = rpos;
+                int q = qb;
+                bool open = false;                                   // the previous run was a match run: merge
+                for (uint32_t c = cbase; c < cend_all; c++) {
+                    const uint32_t ci = c - rg.c_lo;
+                    const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + c);
+                    const uint32_t op = cw & 15u, len = cw >> 4;
+                    const uint32_t cls = (kOpClass >> (2u * op)) & 3u;
+                    if (cls == 1u) {
+                        const uint32_t lim = ref_len - r, n = min(len, lim);
+                        if (len > lim) cv.status[kStatMaybeOverflow] = 1u;
+                        if (n) {
+                            if (open) {
+                                if (n_pc == 1u) fpn0 += n; else fpn1 += n;
+                            } else if (n_pc == 0u) {
+                                fpp0 = r;
+                                fpq0 = q;
+                                fpn0 = n;
+                                n_pc = 1u;
+                                open = true;
+                            } else if (n_pc == 1u) {
+                                fpp1 = r;
+                                fpq1 = q;
+                                fpn1 = n;
+                                n_pc = 2u;
+                                open = true;
+                            } else {
+                                bad = true;
+                            }
+                        }
+                        r += n;
+                        q = (int)min((uint32_t)q + len, 1u << 30);
+                    } else if (cls == 2u) {
+                        q = (int)min((uint32_t)q + len, 1u << 30);
+                        open = open && len == 0u;
+                    } else if (cls == 3u) {
+                        const uint32_t lim = ref_len - r, n = min(len, lim);
+                        if (len > lim) cv.status[kStatIndexError] = 1u;
+                        if (n) {
+                            if (sk_n || n > kLaneSkipMax) bad = true;
+                            sk_pos = r;
+                            sk_n = n;
+                            open = false;
+                        }
+                        r += n;
+                    }
+                }
+                bad = bad || q > qend || fpn0 > C::kMaxFit || fpn1 > C::kMaxFit;
+                // window fit: rel + n <= kWin, with rel = pp - win_lo as unsigned (pp below the window wraps)
+                bad = bad || !win_valid || (n_pc >= 1u && fpp0 - win_lo > kWin - fpn0) ||
+                      (n_pc >= 2u && fpp1 - win_lo > kWin - fpn1);
+            }
+            const uint32_t has0 = __ballot_sync(kFull, n_pc >= 1u), has1 = __ballot_sync(kFull, n_pc >= 2u);
+            const uint32_t np = __popc(has0) + __popc(has1);
+            if (!__any_sync(kFull, bad) && (ring_tail - ring_head) + np <= kRing) {
+                __syncwarp();                                        // earlier ring reads are done
+                uint32_t at = ring_tail + __popc(has0 & lt_mask) + __popc(has1 & lt_mask);
+                if (n_pc >= 1u) {
+                    const uint32_t rel = fpp0 - win_lo;
+                    ring[at & (kRing - 1u)] = make_uint4(rel, rel + fpn0, (uint32_t)(fpq0 - (int)rel), 0u);
+                    at++;
+                }
+                if (n_pc >= 2u) {
+                    const uint32_t rel = fpp1 - win_lo;
+                    ring[at & (kRing - 1u)] = make_uint4(rel, rel + fpn1, (uint32_t)(fpq1 - (int)rel), 0u);
+                }
+                ring_tail += np;
+                for (uint32_t t = 0; t < sk_n; t++) atomicAdd(ds_plane + sk_pos + t, 1u);     // count.cpp:80-87
+                __syncwarp();
+                cur = cend;                                          // every read of the block is done
+                prewalked = true;
+            }
+        }
+
         for (;;) {
             // ---- F: fetch CIGAR ops until an M/=/X run is open (count.cpp:40-96)
             bool moved = false;
+            if (!prewalked) {
             while (rem == 0u && ds_n == 0u && cur < cend) {
                 const uint32_t ci = cur - rg.c_lo;
                 const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + cur);
@@ -451,6 +585,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 ring_tail += __popc(pm);
                 __syncwarp();
             }
+            }                                                        // !prewalked
             // ---- what next?  0: keep walking, 1: everyone waits for a window move, 2: this pass is over
             int action = 0;
             uint32_t new_lo = 0u;
@@ -484,7 +619,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                     if (!want_flush) break;
                 }
                 if (want_flush) {
-                    flush_counters<G>(pl, pa, pb, pc, cnt, frow, plane0 + win_lo, cv.stride, lane);
+                    flush_counters<G>(pl, pa, pb, cnt, frow, plane0 + win_lo, cv.stride, lane);
                     cnt = 0u;
                     continue;
                 }
@@ -539,23 +674,26 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                                 pl[w][k][3] ^= pb[w][k] ^ c3[w][k];
                             }
                         }
-                        if (!(cnt & 16u)) {
+                        if (!(cnt & 16u)) {                           // every 8th trip: park the weight-16 carry
 #pragma unroll
                             for (int w = 0; w < kW; w++)
 #pragma unroll
-                                for (int k = 0; k < kNC; k++) pc[w][k] = c4[w][k];
-                        } else {
+                                for (int k = 0; k < kNC; k++) sp[((w * kNC + k) * 4) * 32] = c4[w][k];
+                        } else {                                      // every 8th trip: planes 5..7 in shared memory
+                            const bool have = cnt >= 32u;             // (they were never written before trip 8)
 #pragma unroll
                             for (int w = 0; w < kW; w++) {
 #pragma unroll
                                 for (int k = 0; k < kNC; k++) {
-                                    uint32_t c = maj3(pl[w][k][4], pc[w][k], c4[w][k]);
-                                    pl[w][k][4] ^= pc[w][k] ^ c4[w][k];
+                                    uint32_t *q = sp + ((w * kNC + k) * 4) * 32;
+                                    const uint32_t pcv = q[0];
+                                    uint32_t c = maj3(pl[w][k][4], pcv, c4[w][k]);
+                                    pl[w][k][4] ^= pcv ^ c4[w][k];
 #pragma unroll
-                                    for (int p = 5; p < kNB; p++) {  // ripple the weight-32 carry upwards
-                                        const uint32_t t = pl[w][k][p] & c;
-                                        pl[w][k][p] ^= c;
-                                        c = t;
+                                    for (int p = 1; p < 4; p++) {     // ripple the weight-32 carry upwards
+                                        const uint32_t v = have ? q[p * 32] : 0u;
+                                        q[p * 32] = v ^ c;
+                                        c &= v;
                                     }
                                 }
                             }
@@ -621,7 +759,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         m0 = m1;
         m1 = m2;
         m2 = m3;
-        m3 = load_meta(j + 4u);
+        m3 = m4;
     }
 }
 
