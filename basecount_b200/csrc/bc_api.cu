@@ -463,6 +463,7 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
     G = 32;
     mean_words = 1;
     if (n == 0) return BC_OK;
+    if (n > 0xFFFFFFFFu - 64u) return fail(h, BC_ERR_ARG, "too many reads in one batch");
     if (b->ref_read_off[0] != 0 || b->ref_read_off[b->n_refs] != n)
         return fail(h, BC_ERR_ARG, "ref_read_off must start at 0 and end at n_reads");
     for (uint32_t r = 0; r < b->n_refs; r++)

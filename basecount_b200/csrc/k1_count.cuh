@@ -116,9 +116,10 @@ struct K1Cfg {
     static constexpr uint32_t ok_off = seq_off + kStages * kSeqCap * 8u;
     static constexpr uint32_t cig_off = ok_off + (HAS_OK ? kStages * kSeqCap * 4u : 0u);
     static constexpr uint32_t bar_off = cig_off + kStages * kCigCap * 4u;
-    static constexpr uint32_t warp_bytes = bar_off + 32u;
+    static constexpr uint32_t rng_off = bar_off + 32u;      // per stage: what it holds (uint4)
+    static constexpr uint32_t warp_bytes = rng_off + kStages * 16u;
     static constexpr uint32_t cta_bytes = lut_bytes + kK1WarpsPerCta * warp_bytes;
-    static_assert(seq_off % 16 == 0 && ok_off % 16 == 0 && cig_off % 16 == 0 && bar_off % 8 == 0 && warp_bytes % 16 == 0,
+    static_assert(seq_off % 16 == 0 && ok_off % 16 == 0 && cig_off % 16 == 0 && bar_off % 16 == 0 && warp_bytes % 16 == 0,
                   "TMA destinations are 16-byte aligned");
     static_assert(seq_off >= (kWin / 32 + 4) * 8 && kStages * kCigCap * 4u >= (kWin / 32 + 4) * 8,
                   "guard bands around the sequence stages");
@@ -269,6 +270,74 @@ __device__ __forceinline__ void flush_counters(uint32_t (&pl)[kW][kNC][kNR], uin
     }
 }
 
+// ---- shared-memory accessors on 32-bit shared addresses.  The warp's base address is made
+//      opaque to the compiler once (so it lives in a register instead of being recomputed from
+//      special registers in every loop) and all hot accesses are base + immediate.
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
 // The counting kernel.  One warp = one chunk of consecutive reads, processed in blocks of
 // `rpb` <= 31 reads, one read per lane.
 template <int G, bool HAS_OK>
@@ -280,7 +349,9 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     constexpr uint32_t kWin = C::kWin, kRing = C::kRing;
     extern __shared__ __align__(128) unsigned char k1_smem[];
 
-    const int lane = threadIdx.x & 31;
+    uint32_t lane_u;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_u));
+    const int lane = (int)lane_u;
     const int warp_in_cta = threadIdx.x >> 5;
 
     // lut[v] = the 64 window columns of a lane at or above column v (v in [0, 64])
@@ -293,18 +364,18 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     if (warp_id >= n_chunks) return;
 
     unsigned char *wsm = k1_smem + C::lut_bytes + (size_t)warp_in_cta * C::warp_bytes;
-    uint4 *ring = reinterpret_cast<uint4 *>(wsm + C::ring_off);
-    uint16_t *frow = reinterpret_cast<uint16_t *>(wsm + C::frow_off);
-    uint2 *seq_buf = reinterpret_cast<uint2 *>(wsm + C::seq_off);
-    uint32_t *ok_buf = reinterpret_cast<uint32_t *>(wsm + C::ok_off);
-    uint32_t *cig_buf = reinterpret_cast<uint32_t *>(wsm + C::cig_off);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(wsm + C::bar_off);
-    const uint2 *wsm2 = reinterpret_cast<const uint2 *>(wsm);       // word views of the whole warp region:
-    const uint32_t *wsm1 = reinterpret_cast<const uint32_t *>(wsm); // piece word indices are offsets into these
+    uint16_t *frow = reinterpret_cast<uint16_t *>(wsm + C::frow_off);          // flush only
+    const uint32_t lutb = opaque(smem_u32(k1_smem));
+    const uint32_t wb = opaque(smem_u32(wsm));                                 // the warp's region
+    const uint32_t ringb = wb + C::ring_off, seqb = wb + C::seq_off, okb = wb + C::ok_off, cigb = wb + C::cig_off,
+                   barb = wb + C::bar_off, rngb = wb + C::rng_off;
 
     const int slot = lane / G, wl = lane % G;
     const int L0 = 32 * kW * wl;                    // window column of this lane's bit 0
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t lt_mask = opaque((1u << lane) - 1u);
+    const uint32_t spb = opaque(wb + C::frow_off + 4u * (uint32_t)lane);       // this lane's spill words, 128 B apart
+    const uint32_t trip_ringb = opaque(ringb + 16u * (uint32_t)slot);          // ring entry of this slot in a trip
+    const uint32_t lane_seq_off = 8u * kW * (uint32_t)wl;                      // byte offset of this lane's window words
 
     const Chunk ch = chunks[warp_id];
     const uint32_t ref_len = ch.ref_len;
@@ -316,17 +387,16 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < kStages; s++) mbar_init_s(barb + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
     // ---- block metadata: lane l holds read (block_first + l); lane l+1's offsets are read l's ends
     struct Meta { uint32_t start, cbase, wbase; };
-    struct Range { uint32_t s_lo, s_n, c_lo, c_n; };     // what a stage holds: plane / okmask words, CIGAR words
     auto load_meta = [&](uint32_t blk) {
         Meta m = {0u, 0u, 0u};
-        const uint64_t idx = (uint64_t)rb + (uint64_t)blk * rpb + lane;
+        const uint32_t idx = rb + blk * rpb + (uint32_t)lane;         // (the host keeps n_reads < 2^32 - 64)
         if (blk < nblk && idx <= re) {
             m.cbase = __ldg(bv.cigar_off + idx);
             m.wbase = __ldg(bv.seq_woff + idx);
@@ -334,28 +404,24 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         }
         return m;
     };
-    auto block_range = [&](const Meta &m, uint32_t nvalid) {
-        const uint32_t s0 = __shfl_sync(kFull, m.wbase, 0), s1 = __shfl_sync(kFull, m.wbase, (int)nvalid);
-        const uint32_t c0 = __shfl_sync(kFull, m.cbase, 0), c1 = __shfl_sync(kFull, m.cbase, (int)nvalid);
-        Range r;
-        r.s_lo = s0 & ~3u;                                           // 32 B / 16 B aligned sources
-        r.s_n = min(((s1 + 3u) & ~3u) - r.s_lo, kSeqCap);
-        r.c_lo = c0 & ~3u;
-        r.c_n = min(((c1 + 3u) & ~3u) - r.c_lo, kCigCap);
-        return r;
-    };
+    // Stage block `blk` (metadata m) into pipeline stage stg; what the stage holds
+    // {first plane word, plane words, first CIGAR word, CIGAR words} is left in shared memory for the block's turn.
     auto issue_block = [&](uint32_t blk, const Meta &m, uint32_t stg) {
         const uint32_t nvalid = min(rpb, re - (rb + blk * rpb));
-        const Range r = block_range(m, nvalid);
+        const uint32_t s0 = __shfl_sync(kFull, m.wbase, 0), s1 = __shfl_sync(kFull, m.wbase, (int)nvalid);
+        const uint32_t c0 = __shfl_sync(kFull, m.cbase, 0), c1 = __shfl_sync(kFull, m.cbase, (int)nvalid);
         if (lane == 0) {
+            const uint32_t s_lo = s0 & ~3u, s_n = min(((s1 + 3u) & ~3u) - s_lo, kSeqCap);     // 32 B / 16 B aligned sources
+            const uint32_t c_lo = c0 & ~3u, c_n = min(((c1 + 3u) & ~3u) - c_lo, kCigCap);
+            sts128(rngb + 16u * stg, make_uint4(s_lo, s_n, c_lo, c_n));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this stage
-            const uint32_t bytes = r.s_n * 8u + (HAS_OK ? r.s_n * 4u : 0u) + r.c_n * 4u;
-            mbar_expect_tx(&bars[stg], bytes);
-            if (r.s_n) {
-                bulk_g2s(seq_buf + stg * kSeqCap, bv.planes + r.s_lo, r.s_n * 8u, &bars[stg]);
-                if (HAS_OK) bulk_g2s(ok_buf + stg * kSeqCap, bv.okmask + r.s_lo, r.s_n * 4u, &bars[stg]);
+            const uint32_t bar = barb + 8u * stg;
+            mbar_expect_tx_s(bar, s_n * 8u + (HAS_OK ? s_n * 4u : 0u) + c_n * 4u);
+            if (s_n) {
+                bulk_g2s_s(seqb + stg * (kSeqCap * 8u), bv.planes + s_lo, s_n * 8u, bar);
+                if (HAS_OK) bulk_g2s_s(okb + stg * (kSeqCap * 4u), bv.okmask + s_lo, s_n * 4u, bar);
             }
-            if (r.c_n) bulk_g2s(cig_buf + stg * kCigCap, bv.cigar + r.c_lo, r.c_n * 4u, &bars[stg]);
+            if (c_n) bulk_g2s_s(cigb + stg * (kCigCap * 4u), bv.cigar + c_lo, c_n * 4u, bar);
         }
     };
 
@@ -381,27 +447,29 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             pb[w][k] = 0u;
         }
     }
-    uint32_t *const sp = reinterpret_cast<uint32_t *>(frow) + lane;   // this lane's spill words, 32 apart
 
+    // A ring entry: x / y = first / end column of the piece relative to the window, z = bit index
+    // of window column 0 in the staged data (only its low 5 bits, the funnel-shift amount, are
+    // used), w = shared address of the plane word that holds window column 0.
+    auto make_entry = [&](uint32_t rel, uint32_t n, int qbit) {
+        const int z = qbit - (int)rel;
+        return make_uint4(rel, rel + n, (uint32_t)z, seqb + (uint32_t)((z >> 5) * 8));
+    };
     // Masked words of one piece for this lane's two window words.
-    //   e.x / e.y : first / end column of the piece, relative to the window
-    //   e.z       : bit index (in this warp's shared-memory region) of window column 0
     auto piece = [&](const uint4 e, uint32_t (&x)[kW][kNC]) {
         const int a_c = __viaddmin_s32_relu((int)e.x, -L0, 64);      // clamp(first - L0, 0, 64), one VIADDMNMX
         const int e_c = __viaddmin_s32_relu((int)e.y, -L0, 64);
-        const uint2 ga = lut[a_c], ge = lut[e_c];
+        const uint2 ga = lds64(lutb + 8u * (uint32_t)a_c), ge = lds64(lutb + 8u * (uint32_t)e_c);
         uint32_t m[kW] = {ga.x & ~ge.x, ga.y & ~ge.y};
-        const int bit = (int)e.z + L0;
-        const int wi = bit >> 5;
-        const uint2 r0 = wsm2[(int)(C::seq_off / 8u) + wi], r1 = wsm2[(int)(C::seq_off / 8u) + wi + 1],
-                    r2 = wsm2[(int)(C::seq_off / 8u) + wi + 2];
-        const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, (uint32_t)bit), __funnelshift_r(r1.x, r2.x, (uint32_t)bit)};
-        const uint32_t hi[kW] = {__funnelshift_r(r0.y, r1.y, (uint32_t)bit), __funnelshift_r(r1.y, r2.y, (uint32_t)bit)};
+        const uint32_t wa = e.w + lane_seq_off;
+        const uint2 r0 = lds64(wa), r1 = lds64(wa + 8u), r2 = lds64(wa + 16u);
+        const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, e.z), __funnelshift_r(r1.x, r2.x, e.z)};
+        const uint32_t hi[kW] = {__funnelshift_r(r0.y, r1.y, e.z), __funnelshift_r(r1.y, r2.y, e.z)};
         if (HAS_OK) {
-            const uint32_t o0 = wsm1[(int)(C::ok_off / 4u) + wi], o1 = wsm1[(int)(C::ok_off / 4u) + wi + 1],
-                           o2 = wsm1[(int)(C::ok_off / 4u) + wi + 2];
-            m[0] &= __funnelshift_r(o0, o1, (uint32_t)bit);
-            m[1] &= __funnelshift_r(o1, o2, (uint32_t)bit);
+            const uint32_t oa = okb + (uint32_t)((int)(wa - seqb) >> 1);
+            const uint32_t o0 = lds32(oa), o1 = lds32(oa + 4u), o2 = lds32(oa + 8u);
+            m[0] &= __funnelshift_r(o0, o1, e.z);
+            m[1] &= __funnelshift_r(o1, o2, e.z);
         }
 #pragma unroll
         for (int w = 0; w < kW; w++) {
@@ -418,108 +486,92 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         const bool last = (j == nblk);
         const Meta m4 = load_meta(j + 4u);                           // rotated in at the end of this block
         uint32_t nvalid = 0;
-        Range rg = {0u, 0u, 0u, 0u};
+        uint4 rg = make_uint4(0u, 0u, 0u, 0u);                       // s_lo, s_n, c_lo, c_n of this stage
         if (!last) {
-            mbar_wait(&bars[st], (phases >> st) & 1u);
+            mbar_wait_s(barb + 8u * st, (phases >> st) & 1u);
             phases ^= 1u << st;
             nvalid = min(rpb, re - (rb + j * rpb));
-            rg = block_range(m0, nvalid);
+            __syncwarp();                                            // lane 0 wrote the range when it issued the block
+            rg = lds128(rngb + 16u * st);
         }
-        const uint32_t *cg = cig_buf + st * kCigCap;
+        const uint32_t cg = cigb + st * (kCigCap * 4u) - rg.z * 4u;  // shared address of CIGAR word 0
         const int seg_bit0 = (int)(st * kSeqCap * 32u);              // bit index of the stage's first word
 
         // ---- per-lane read state (count.cpp:35-38)
         const bool valid = (uint32_t)lane < nvalid;
         const uint32_t cbase = m0.cbase, cend_all = __shfl_down_sync(kFull, m0.cbase, 1);
         const uint32_t wbase = m0.wbase, wend = __shfl_down_sync(kFull, m0.wbase, 1);
-        const bool staged = valid && (wend - rg.s_lo) <= rg.s_n;
+        const bool staged = valid && (wend - rg.x) <= rg.y;
+        const bool cig_staged = (cend_all - rg.z) <= rg.w;           // this read's CIGAR words are in shared memory
         uint32_t unst = __ballot_sync(kFull, valid && !staged && cend_all > cbase);   // reads to stage by hand
         uint32_t cur = cbase, cend = staged ? cend_all : cbase;
         uint32_t rpos = min(m0.start, ref_len), rem = 0u, ds_pos = 0u, ds_n = 0u;
-        int qb = seg_bit0 + (int)((wbase - rg.s_lo) * 32u);          // bit index of the next read base
+        int qb = seg_bit0 + (int)((wbase - rg.x) * 32u);             // bit index of the next read base
         int qend = qb + (int)((wend - wbase) * 32u);                 // end of the staged data of this read
         bool issue_pending = (j >= 1u) && (j + 2u < nblk);           // block j+2 goes into block j-1's stage
         int slow_lane = -1;                                          // lane whose read is staged by hand right now
         uint32_t seg_w = 0u, seg_end = 0u;                           // its current segment / end (plane word indices)
 
-        // ---- fast path: every lane walks its whole CIGAR privately (no votes inside); if every read
-        //      has at most two M/=/X runs (adjacent ones merge) and one short D/N run, and all of them
-        //      fit the current window, the pieces are committed in one go.  Anything else (window
-        //      moves, long or many runs, hand-staged reads) takes the lock-step walker below, which
-        //      starts the block from scratch: nothing here has side effects before the commit
-        //      (the status flags are idempotent).
+        // ---- fast path: reads with at most three CIGAR ops (which is nearly all short reads: M, M-I-M,
+        //      M-D-M, clipped or =/X spellings) are decoded in straight-line code, no loop and no
+        //      votes: a missing op reads as a zero-length M, which changes nothing.  Ops of one match
+        //      run (nothing but zero-length or S/H/P ops between them) merge into one piece; a run
+        //      starts at the read start (run A) or right after the first non-empty I/D/N (run B).
+        //      If every read of the block qualifies and every piece fits the current window, the
+        //      pieces are committed in one go.  Anything else (more ops, window moves, clipping at
+        //      the reference end, long D/N runs, hand-staged reads) takes the lock-step walker
+        //      below, which starts the block from scratch: nothing here has side effects before
+        //      the commit.
         bool prewalked = false;
         if (!last) {
-            uint32_t fpp0 = 0u, fpp1 = 0u, fpn0 = 0u, fpn1 = 0u, n_pc = 0u, sk_pos = 0u, sk_n = 0u;
-            int fpq0 = 0, fpq1 = 0;
-            bool bad = unst != 0u;
+            const uint32_t ncig = cend_all - cbase;
+            bool bad = unst != 0u || !win_valid || (valid && (!cig_staged || ncig > 3u));
+            uint32_t nA = 0u, nB = 0u, ppB = 0u, sk_pos = 0u, sk_n = 0u;
+            int pqB = 0;
             if (staged) {
-                uint32_t r = rpos;
-                int q = qb;
-                bool open = false;                                   // the previous run was a match run: merge
-                for (uint32_t c = cbase; c < cend_all; c++) {
-                    const uint32_t ci = c - rg.c_lo;
-                    const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + c);
-                    const uint32_t op = cw & 15u, len = cw >> 4;
-                    const uint32_t cls = (kOpClass >> (2u * op)) & 3u;
-                    if (cls == 1u) {
-                        const uint32_t lim = ref_len - r, n = min(len, lim);
-                        if (len > lim) cv.status[kStatMaybeOverflow] = 1u;
-                        if (n) {
-                            if (open) {
-                                if (n_pc == 1u) fpn0 += n; else fpn1 += n;
-                            } else if (n_pc == 0u) {
-                                fpp0 = r;
-                                fpq0 = q;
-                                fpn0 = n;
-                                n_pc = 1u;
-                                open = true;
-                            } else if (n_pc == 1u) {
-                                fpp1 = r;
-                                fpq1 = q;
-                                fpn1 = n;
-                                n_pc = 2u;
-                                open = true;
-                            } else {
-                                bad = true;
-                            }
-                        }
-                        r += n;
-                        q = (int)min((uint32_t)q + len, 1u << 30);
-                    } else if (cls == 2u) {
-                        q = (int)min((uint32_t)q + len, 1u << 30);
-                        open = open && len == 0u;
-                    } else if (cls == 3u) {
-                        const uint32_t lim = ref_len - r, n = min(len, lim);
-                        if (len > lim) cv.status[kStatIndexError] = 1u;
-                        if (n) {
-                            if (sk_n || n > kLaneSkipMax) bad = true;
-                            sk_pos = r;
-                            sk_n = n;
-                            open = false;
-                        }
-                        r += n;
-                    }
+                const uint32_t ca = cg + cbase * 4u;
+                uint32_t cw[3];
+                cw[0] = ncig > 0u ? lds32(ca) : 0u;
+                cw[1] = ncig > 1u ? lds32(ca + 4u) : 0u;
+                cw[2] = ncig > 2u ? lds32(ca + 8u) : 0u;
+                uint32_t r[4], q[4], mlen[3], dlen[3];
+                bool brk[3];
+                r[0] = rpos;
+                q[0] = (uint32_t)qb;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const uint32_t len = cw[k] >> 4;
+                    const uint32_t cls = (kOpClass >> ((cw[k] << 1) & 30u)) & 3u;
+                    r[k + 1] = r[k] + ((cls & 1u) ? len : 0u);               // M/=/X (1), D/N (3): count.cpp:67-68, 87
+                    q[k + 1] = q[k] + (((cls + 1u) & 2u) ? len : 0u);        // M/=/X (1), I (2): count.cpp:67, 75
+                    mlen[k] = cls == 1u ? len : 0u;
+                    dlen[k] = cls == 3u ? len : 0u;
+                    brk[k] = cls >= 2u && len != 0u;                         // a non-empty I/D/N ends the match run
                 }
-                bad = bad || q > qend || fpn0 > C::kMaxFit || fpn1 > C::kMaxFit;
-                // window fit: rel + n <= kWin, with rel = pp - win_lo as unsigned (pp below the window wraps)
-                bad = bad || !win_valid || (n_pc >= 1u && fpp0 - win_lo > kWin - fpn0) ||
-                      (n_pc >= 2u && fpp1 - win_lo > kWin - fpn1);
+                // run of op 1: brk0; run of op 2: brk0 + brk1; an M in a third run is left to the walker
+                nA = mlen[0] + (brk[0] ? 0u : mlen[1]) + ((brk[0] || brk[1]) ? 0u : mlen[2]);
+                nB = (brk[0] ? mlen[1] : 0u) + ((brk[0] != brk[1]) ? mlen[2] : 0u);
+                ppB = brk[0] ? r[1] : r[2];
+                pqB = (int)(brk[0] ? q[1] : q[2]);
+                sk_n = dlen[0] + dlen[1] + dlen[2];
+                sk_pos = dlen[0] ? r[0] : (dlen[1] ? r[1] : r[2]);
+                const uint32_t nsk = (dlen[0] ? 1u : 0u) + (dlen[1] ? 1u : 0u) + (dlen[2] ? 1u : 0u);
+                // reference end, data bounds, piece lengths, window fit: rel + n <= kWin with
+                // rel = pp - win_lo as unsigned (pp below the window wraps)
+                bad = bad || r[3] > ref_len || q[3] > (uint32_t)qend || (brk[0] && brk[1] && mlen[2] != 0u) || nsk > 1u ||
+                      sk_n > kLaneSkipMax || nA > C::kMaxFit || nB > C::kMaxFit ||
+                      (nA != 0u && rpos - win_lo > kWin - nA) || (nB != 0u && ppB - win_lo > kWin - nB);
             }
-            const uint32_t has0 = __ballot_sync(kFull, n_pc >= 1u), has1 = __ballot_sync(kFull, n_pc >= 2u);
+            const uint32_t has0 = __ballot_sync(kFull, nA != 0u), has1 = __ballot_sync(kFull, nB != 0u);
             const uint32_t np = __popc(has0) + __popc(has1);
             if (!__any_sync(kFull, bad) && (ring_tail - ring_head) + np <= kRing) {
                 __syncwarp();                                        // earlier ring reads are done
                 uint32_t at = ring_tail + __popc(has0 & lt_mask) + __popc(has1 & lt_mask);
-                if (n_pc >= 1u) {
-                    const uint32_t rel = fpp0 - win_lo;
-                    ring[at & (kRing - 1u)] = make_uint4(rel, rel + fpn0, (uint32_t)(fpq0 - (int)rel), 0u);
+                if (nA != 0u) {
+                    sts128(ringb + 16u * (at & (kRing - 1u)), make_entry(rpos - win_lo, nA, qb));
                     at++;
                 }
-                if (n_pc >= 2u) {
-                    const uint32_t rel = fpp1 - win_lo;
-                    ring[at & (kRing - 1u)] = make_uint4(rel, rel + fpn1, (uint32_t)(fpq1 - (int)rel), 0u);
-                }
+                if (nB != 0u) sts128(ringb + 16u * (at & (kRing - 1u)), make_entry(ppB - win_lo, nB, pqB));
                 ring_tail += np;
                 for (uint32_t t = 0; t < sk_n; t++) atomicAdd(ds_plane + sk_pos + t, 1u);     // count.cpp:80-87
                 __syncwarp();
@@ -529,104 +581,103 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         }
 
         for (;;) {
-            // ---- F: fetch CIGAR ops until an M/=/X run is open (count.cpp:40-96)
-            bool moved = false;
-            if (!prewalked) {
-            while (rem == 0u && ds_n == 0u && cur < cend) {
-                const uint32_t ci = cur - rg.c_lo;
-                const uint32_t cw = ci < rg.c_n ? cg[ci] : __ldg(bv.cigar + cur);
-                cur++;
-                moved = true;
-                const uint32_t op = cw & 15u, len = cw >> 4;
-                const uint32_t cls = (kOpClass >> (2u * op)) & 3u;
-                if (cls == 1u) {                                     // M / = / X, count.cpp:51
-                    const uint32_t lim = ref_len - rpos;
-                    if (len > lim) cv.status[kStatMaybeOverflow] = 1u;   // would index past the matrix: exact check later
-                    rem = min(len, lim);
-                } else if (cls == 2u) {                              // insertion, count.cpp:74
-                    qb = (int)min((uint32_t)qb + len, 1u << 30);
-                } else if (cls == 3u) {                              // deletion / skip, count.cpp:80-87
-                    const uint32_t lim = ref_len - rpos, n = min(len, lim);
-                    if (len > lim) cv.status[kStatIndexError] = 1u;
-                    if (n <= kLaneSkipMax) {
-                        for (uint32_t t = 0; t < n; t++) atomicAdd(ds_plane + rpos + t, 1u);
-                    } else {
-                        ds_pos = rpos;
-                        ds_n = n;
-                    }
-                    rpos += n;
-                }                                                    // S, H, P, B: ignored, count.cpp:92-95
-            }
-            // ---- D: long D/N runs, all lanes help
-            uint32_t dsm = __ballot_sync(kFull, ds_n != 0u);
-            while (dsm) {
-                const int src = __ffs((int)dsm) - 1;
-                dsm &= dsm - 1u;
-                const uint32_t p = __shfl_sync(kFull, ds_pos, src), n = __shfl_sync(kFull, ds_n, src);
-                for (uint32_t t = lane; t < n; t += 32u) atomicAdd(ds_plane + p + t, 1u);
-            }
-            ds_n = 0u;
-            // ---- P: the part of the open run that fits the window becomes a piece
-            const uint32_t relp = rpos - win_lo;
-            uint32_t n1 = 0u;
-            if (rem != 0u && win_valid && relp < kWin && qb < qend)
-                n1 = min(min(rem, kWin - relp), (uint32_t)(qend - qb));
-            const uint32_t pm = __ballot_sync(kFull, n1 != 0u);
-            if (pm) {
-                __syncwarp();                                        // earlier ring reads are done
-                if (n1) {
-                    ring[(ring_tail + __popc(pm & lt_mask)) & (kRing - 1u)] =
-                        make_uint4(relp, relp + n1, (uint32_t)(qb - (int)relp), 0u);
-                    rpos += n1;
-                    qb += (int)n1;
-                    rem -= n1;
-                    moved = true;
-                }
-                ring_tail += __popc(pm);
-                __syncwarp();
-            }
-            }                                                        // !prewalked
-            // ---- what next?  0: keep walking, 1: everyone waits for a window move, 2: this pass is over
-            int action = 0;
+            int action = 2;                 // 0: keep walking, 1: everyone waits for a window move, 2: this pass is over
             uint32_t new_lo = 0u;
-            if (!__any_sync(kFull, cur < cend || rem != 0u)) {
-                action = 2;
-            } else if (!__any_sync(kFull, moved)) {
-                const bool wst = rem != 0u && qb < qend;             // waits for the window (not for data)
-                if (__any_sync(kFull, wst)) {
-                    action = 1;
-                    new_lo = __reduce_min_sync(kFull, wst ? rpos : 0xFFFFFFFFu) & ~31u;
-                } else {
-                    action = 2;
+            if (!prewalked) {
+                // ---- F: fetch CIGAR ops until an M/=/X run is open (count.cpp:40-96)
+                bool moved = false;
+                while (rem == 0u && ds_n == 0u && cur < cend) {
+                    const uint32_t cw = (cur - rg.z) < rg.w ? lds32(cg + cur * 4u) : __ldg(bv.cigar + cur);
+                    cur++;
+                    moved = true;
+                    const uint32_t len = cw >> 4;
+                    const uint32_t cls = (kOpClass >> ((cw << 1) & 30u)) & 3u;
+                    if (cls == 1u) {                                     // M / = / X, count.cpp:51
+                        const uint32_t lim = ref_len - rpos;
+                        if (len > lim) cv.status[kStatMaybeOverflow] = 1u;   // would index past the matrix: exact check later
+                        rem = min(len, lim);
+                    } else if (cls == 2u) {                              // insertion, count.cpp:74
+                        qb = (int)min((uint32_t)qb + len, 1u << 30);
+                    } else if (cls == 3u) {                              // deletion / skip, count.cpp:80-87
+                        const uint32_t lim = ref_len - rpos, n = min(len, lim);
+                        if (len > lim) cv.status[kStatIndexError] = 1u;
+                        if (n <= kLaneSkipMax) {
+                            for (uint32_t t = 0; t < n; t++) atomicAdd(ds_plane + rpos + t, 1u);
+                        } else {
+                            ds_pos = rpos;
+                            ds_n = n;
+                        }
+                        rpos += n;
+                    }                                                    // S, H, P, B: ignored, count.cpp:92-95
+                }
+                // ---- D: long D/N runs, all lanes help
+                uint32_t dsm = __ballot_sync(kFull, ds_n != 0u);
+                while (dsm) {
+                    const int src = __ffs((int)dsm) - 1;
+                    dsm &= dsm - 1u;
+                    const uint32_t p = __shfl_sync(kFull, ds_pos, src), n = __shfl_sync(kFull, ds_n, src);
+                    for (uint32_t t = lane; t < n; t += 32u) atomicAdd(ds_plane + p + t, 1u);
+                }
+                ds_n = 0u;
+                // ---- P: the part of the open run that fits the window becomes a piece
+                const uint32_t relp = rpos - win_lo;
+                uint32_t n1 = 0u;
+                if (rem != 0u && win_valid && relp < kWin && qb < qend)
+                    n1 = min(min(rem, kWin - relp), (uint32_t)(qend - qb));
+                const uint32_t pm = __ballot_sync(kFull, n1 != 0u);
+                if (pm) {
+                    __syncwarp();                                        // earlier ring reads are done
+                    if (n1) {
+                        sts128(ringb + 16u * ((ring_tail + __popc(pm & lt_mask)) & (kRing - 1u)), make_entry(relp, n1, qb));
+                        rpos += n1;
+                        qb += (int)n1;
+                        rem -= n1;
+                        moved = true;
+                    }
+                    ring_tail += __popc(pm);
+                    __syncwarp();
+                }
+                if (__any_sync(kFull, cur < cend || rem != 0u)) {
+                    action = 0;
+                    if (!__any_sync(kFull, moved)) {
+                        const bool wst = rem != 0u && qb < qend;         // waits for the window (not for data)
+                        if (__any_sync(kFull, wst)) {
+                            action = 1;
+                            new_lo = __reduce_min_sync(kFull, wst ? rpos : 0xFFFFFFFFu) & ~31u;
+                        } else {
+                            action = 2;
+                        }
+                    }
                 }
             }
             // ---- the one trip site and the one flush site
             for (;;) {
                 const uint32_t avail = ring_tail - ring_head;
-                bool want_flush;
-                if (avail >= (uint32_t)Q) {
-                    want_flush = (cnt == kCntMax);
-                } else {
-                    const bool drain = action == 1 || (action == 2 && (last || unst != 0u || slow_lane >= 0 ||
-                                                                       (issue_pending && (int)(ring_head - mark) < 0)));
-                    if (avail != 0u && drain) {                      // pad the ring with empty pieces to a full trip
-                        if ((uint32_t)lane < (uint32_t)Q - avail) ring[(ring_tail + lane) & (kRing - 1u)] = make_uint4(0u, 0u, 0u, 0u);
-                        ring_tail += (uint32_t)Q - avail;
-                        __syncwarp();
-                        continue;
+                if (avail < (uint32_t)Q || cnt == kCntMax) {         // rare: everything but a plain trip
+                    bool want_flush = true;                          // a full trip is waiting but the counters are full
+                    if (avail < (uint32_t)Q) {
+                        const bool drain = action == 1 || (action == 2 && (last || unst != 0u || slow_lane >= 0 ||
+                                                                           (issue_pending && (int)(ring_head - mark) < 0)));
+                        if (avail != 0u && drain) {                  // pad the ring with empty pieces to a full trip
+                            if ((uint32_t)lane < (uint32_t)Q - avail)
+                                sts128(ringb + 16u * ((ring_tail + lane) & (kRing - 1u)), make_uint4(0u, 0u, 0u, seqb));
+                            ring_tail += (uint32_t)Q - avail;
+                            __syncwarp();
+                            continue;
+                        }
+                        want_flush = cnt != 0u && (action == 1 || (action == 2 && last));
                     }
-                    want_flush = cnt != 0u && (action == 1 || (action == 2 && last));
                     if (!want_flush) break;
-                }
-                if (want_flush) {
                     flush_counters<G>(pl, pa, pb, cnt, frow, plane0 + win_lo, cv.stride, lane);
                     cnt = 0u;
                     continue;
                 }
-                // -- trip: four pieces per read slot, straight-line
+                // -- trip: four pieces per read slot, straight-line.  ring_head is a multiple of Q
+                //    and Q divides kRing, so the Q entries of a trip never wrap.
+                const uint32_t ea = trip_ringb + 16u * (ring_head & (kRing - 1u));
                 uint4 e[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) e[q] = ring[(ring_head + (uint32_t)(q * S + slot)) & (kRing - 1u)];
+                for (int q = 0; q < 4; q++) e[q] = lds128(ea + 16u * (uint32_t)(q * S));
                 ring_head += (uint32_t)Q;
                 uint32_t x[4][kW][kNC];
 #pragma unroll
@@ -678,21 +729,21 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
 #pragma unroll
                             for (int w = 0; w < kW; w++)
 #pragma unroll
-                                for (int k = 0; k < kNC; k++) sp[((w * kNC + k) * 4) * 32] = c4[w][k];
+                                for (int k = 0; k < kNC; k++) sts32(spb + 128u * (uint32_t)((w * kNC + k) * 4), c4[w][k]);
                         } else {                                      // every 8th trip: planes 5..7 in shared memory
                             const bool have = cnt >= 32u;             // (they were never written before trip 8)
 #pragma unroll
                             for (int w = 0; w < kW; w++) {
 #pragma unroll
                                 for (int k = 0; k < kNC; k++) {
-                                    uint32_t *q = sp + ((w * kNC + k) * 4) * 32;
-                                    const uint32_t pcv = q[0];
+                                    const uint32_t qa = spb + 128u * (uint32_t)((w * kNC + k) * 4);
+                                    const uint32_t pcv = lds32(qa);
                                     uint32_t c = maj3(pl[w][k][4], pcv, c4[w][k]);
                                     pl[w][k][4] ^= pcv ^ c4[w][k];
 #pragma unroll
                                     for (int p = 1; p < 4; p++) {     // ripple the weight-32 carry upwards
-                                        const uint32_t v = have ? q[p * 32] : 0u;
-                                        q[p * 32] = v ^ c;
+                                        const uint32_t v = have ? lds32(qa + 128u * p) : 0u;
+                                        sts32(qa + 128u * p, v ^ c);
                                         c &= v;
                                     }
                                 }
@@ -711,6 +762,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 win_valid = true;
             }
             if (action != 2) continue;
+            if (prewalked) break;
 
             // ---- pass over: reads that were not staged are copied into this stage segment by segment
             if (slow_lane >= 0) {
@@ -745,8 +797,8 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             {
                 const uint32_t nw = min(seg_end - seg_w, kSeqCap);
                 for (uint32_t i = lane; i < nw; i += 32u) {
-                    seq_buf[st * kSeqCap + i] = __ldg(bv.planes + seg_w + i);
-                    if (HAS_OK) ok_buf[st * kSeqCap + i] = __ldg(bv.okmask + seg_w + i);
+                    sts64(seqb + (st * kSeqCap + i) * 8u, __ldg(bv.planes + seg_w + i));
+                    if (HAS_OK) sts32(okb + (st * kSeqCap + i) * 4u, __ldg(bv.okmask + seg_w + i));
                 }
                 if (lane == slow_lane) qend = seg_bit0 + (int)(nw * 32u);
                 __syncwarp();
