@@ -71,6 +71,14 @@ struct bc_handle {
     DevBuf scratch_cov, scratch_pc, scratch_ent, scratch_sec, scratch_flags, scratch_i64, scratch_misc;
     SummaryPartial *d_partials = nullptr;
     size_t partials_cap = 0;
+    // asynchronous summaries: k2_summary_final writes into a pinned host block (zero-copy), the
+    // values are handed to the caller's arrays at the next synchronisation
+    struct PendingSummary { char *block; uint32_t n; int64_t *nonzero; int64_t *cov_sum; double *entropy_sum; };
+    std::vector<PendingSummary> pending;
+    std::vector<std::pair<char *, size_t>> free_blocks;      // pinned blocks to reuse (ptr, bytes)
+    uint32_t *d_part_off = nullptr;       // first partial of every slot (see summary_blocks)
+    uint32_t part_off_refs = 0;           // 0 = stale (slot lengths changed)
+    uint32_t summary_max_blocks = 1;
 
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     static constexpr int kHist = 256;           // ring of (start, stop) events around the counting kernel
@@ -108,6 +116,33 @@ static int ensure(bc_handle *h, DevBuf &b, size_t bytes)
     CU(h, cudaMalloc(&b.p, want));
     b.cap = want;
     return BC_OK;
+}
+
+static char *take_block(bc_handle *h, size_t bytes)
+{
+    for (size_t i = 0; i < h->free_blocks.size(); i++) {
+        if (h->free_blocks[i].second >= bytes) {
+            char *p = h->free_blocks[i].first;
+            h->free_blocks.erase(h->free_blocks.begin() + (long)i);
+            return p;
+        }
+    }
+    char *p = nullptr;
+    if (cudaHostAlloc((void **)&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+// Call after the compute stream has been synchronised: hands finished summaries to their callers.
+static void deliver_summaries(bc_handle *h)
+{
+    for (auto &p : h->pending) {
+        const size_t n = p.n;
+        std::memcpy(p.nonzero, p.block, n * 8);
+        std::memcpy(p.cov_sum, p.block + n * 8, n * 8);
+        std::memcpy(p.entropy_sum, p.block + n * 16, n * 8);
+        h->free_blocks.push_back({p.block, n * 24});
+    }
+    h->pending.clear();
 }
 
 static void release(DevBuf &b)
@@ -205,6 +240,9 @@ void bc_destroy(bc_handle *h)
                       &h->scratch_i64, &h->scratch_misc})
         release(*b);
     if (h->d_partials) cudaFree(h->d_partials);
+    if (h->d_part_off) cudaFree(h->d_part_off);
+    for (auto &p : h->pending) cudaFreeHost(p.block);
+    for (auto &p : h->free_blocks) cudaFreeHost(p.first);
     if (h->d_counts) cudaFree(h->d_counts);
     if (h->d_counts64) cudaFree(h->d_counts64);
     if (h->d_col_base) cudaFree(h->d_col_base);
@@ -253,7 +291,7 @@ int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens)
         cb[r] = (uint32_t)total;
         total += ((uint64_t)ref_lens[r] + kColAlign - 1) / kColAlign * kColAlign;
     }
-    total += 32u * 32u;      // slack so a window overhanging the last slot stays inside the allocation
+    total += 32u * kW * 32u + 64u;   // slack: a full window (64 * G columns, G <= 32) may overhang the last slot
     if (total > 0xFFFFFFFFull) return fail(h, BC_ERR_ARG, "bc_begin: more than 2^32 columns in one handle");
     if (total != h->stride || n_refs != h->n_refs) {
         if (h->d_counts) CU(h, cudaFree(h->d_counts));
@@ -272,6 +310,7 @@ int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens)
     }
     h->stride = total;
     h->n_refs = n_refs;
+    h->part_off_refs = 0;
     h->ref_len = rl;
     h->col_base = cb;
     h->reads_since_fold = 0;
@@ -556,6 +595,7 @@ int bc_sync(bc_handle *h)
     CU(h, cudaStreamSynchronize(h->copy));
     CU(h, cudaMemcpyAsync(h->h_status, h->d_status, kStatWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
+    deliver_summaries(h);
     if (h->h_status[kStatIndexError]) {
         CU(h, cudaMemsetAsync(h->d_status, 0, kStatWords * sizeof(uint32_t), h->compute));
         return fail(h, BC_ERR_INDEX, "alignment counted past the end of the reference (std::out_of_range in count.cpp)");
@@ -693,32 +733,46 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
     if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
     CU(h, cudaSetDevice(h->device));
     const uint32_t R = h->n_refs;
-    const size_t need = (size_t)R * kSummaryBlocks;
-    if (need > h->partials_cap) {
-        if (h->d_partials) {
-            CU(h, cudaDeviceSynchronize());
-            CU(h, cudaFree(h->d_partials));
-            h->d_partials = nullptr;
+    // partial offsets per slot (a fixed function of the slot lengths), uploaded once per bc_begin
+    if (h->part_off_refs != R || !h->d_part_off) {
+        std::vector<uint32_t> off(R);
+        size_t need = 0;
+        uint32_t maxb = 1;
+        for (uint32_t r = 0; r < R; r++) {
+            off[r] = (uint32_t)need;
+            const uint32_t nb = summary_blocks(h->ref_len[r]);
+            need += nb;
+            maxb = std::max(maxb, nb);
         }
+        CU(h, cudaDeviceSynchronize());
+        if (h->d_partials) CU(h, cudaFree(h->d_partials));
+        if (h->d_part_off) CU(h, cudaFree(h->d_part_off));
+        h->d_partials = nullptr;
+        h->d_part_off = nullptr;
         CU(h, cudaMalloc(&h->d_partials, need * sizeof(SummaryPartial)));
+        CU(h, cudaMalloc(&h->d_part_off, (size_t)R * sizeof(uint32_t)));
+        CU(h, cudaMemcpy(h->d_part_off, off.data(), (size_t)R * sizeof(uint32_t), cudaMemcpyHostToDevice));
         h->partials_cap = need;
+        h->part_off_refs = R;
+        h->summary_max_blocks = maxb;
     }
-    int rc = ensure(h, h->scratch_misc, (size_t)R * 24);
-    if (rc) return rc;
-    long long *d_nz = (long long *)h->scratch_misc.p;
+    char *block = take_block(h, (size_t)R * 24);
+    if (!block) return fail(h, BC_ERR_CUDA, "pinned allocation for the summary failed");
+    long long *d_nz = (long long *)block;                 // pinned host memory, written by the kernel over PCIe
     long long *d_cs = d_nz + R;
     double *d_es = (double *)(d_cs + R);
     const int K = show_n ? 6 : 5;
-    k2_summary_partials<<<dim3(kSummaryBlocks, R), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride,
-                                                                        h->d_col_base, h->d_ref_len, K, norm, norm2,
-                                                                        h->d_partials);
-    k2_summary_final<<<R, kSummaryBlocks, 0, h->compute>>>(h->d_partials, d_nz, d_cs, d_es);
+    k2_summary_partials<<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride,
+                                                                               h->d_col_base, h->d_ref_len, K, norm, norm2,
+                                                                               h->d_part_off, h->d_partials);
+    k2_summary_final<<<R, 256, 0, h->compute>>>(h->d_partials, h->d_part_off, h->d_ref_len, d_nz, d_cs, d_es);
     h->launches += 2;
+    h->pending.push_back({block, R, nonzero, cov_sum, entropy_sum});
     CU(h, cudaGetLastError());
-    CU(h, cudaMemcpyAsync(nonzero, d_nz, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
-    CU(h, cudaMemcpyAsync(cov_sum, d_cs, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
-    CU(h, cudaMemcpyAsync(entropy_sum, d_es, (size_t)R * 8, cudaMemcpyDeviceToHost, h->compute));
-    if (sync) CU(h, cudaStreamSynchronize(h->compute));
+    if (sync) {
+        CU(h, cudaStreamSynchronize(h->compute));
+        deliver_summaries(h);
+    }
     return BC_OK;
 }
 
@@ -805,6 +859,7 @@ int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len)
     if (ref >= h->n_refs || new_len > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "bc_truncate: out of range");
     CU(h, cudaSetDevice(h->device));
     h->ref_len[ref] = new_len;
+    h->part_off_refs = 0;
     CU(h, cudaMemcpyAsync(h->d_ref_len + ref, &h->ref_len[ref], sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
     return BC_OK;

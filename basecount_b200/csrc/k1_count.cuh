@@ -130,9 +130,11 @@ __host__ __device__ constexpr uint32_t k1_cta_smem_bytes()
     return K1Cfg<G, HAS_OK>::cta_bytes;
 }
 
-__device__ __forceinline__ void red_add_nz(uint32_t *p, uint32_t v)
+// Unconditional: a window that overhangs the reference end adds zeros to the slack columns behind
+// it (bc_begin pads every plane by a full window), which is cheaper than testing every value.
+__device__ __forceinline__ void red_add(uint32_t *p, uint32_t v)
 {
-    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %1, 0;\n@q red.global.add.u32 [%0], %1;\n}\n" ::"l"(p), "r"(v) : "memory");
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // Convert the warp's vertical counters to integers and add them to the HBM planes.
@@ -145,7 +147,7 @@ __device__ __forceinline__ void red_add_nz(uint32_t *p, uint32_t v)
 //   3. byte-packed extraction (the loop over the shift amount jj is deliberately NOT unrolled:
 //      registers stay statically indexed while the code stays small), staged as uint16 rows;
 //   4. letters from the four counted quantities, written with coalesced RED.ADD (128 B per
-//      warp instruction), zeros skipped.
+//      warp instruction).
 //   frow: kNC rows x (kW*G window words x kFlushStride) uint16, aliasing the spill words
 //   counts: plane A at window column 0
 template <int G>
@@ -252,10 +254,10 @@ __device__ __forceinline__ void flush_counters(uint32_t (&pl)[kW][kNC][kNR], uin
     for (int w = 0; w < kW * G; w++) {
         const int at = (int)kFlushStride * w + lane;
         const uint32_t nlo = frow[at], nhi = frow[kCols + at], nb = frow[2 * kCols + at], nv = frow[3 * kCols + at];
-        red_add_nz(pA + 32 * w, nv + nb - nlo - nhi);           // RED.ADD, 128 B per warp instruction
-        red_add_nz(pC + 32 * w, nlo - nb);
-        red_add_nz(pG + 32 * w, nhi - nb);
-        red_add_nz(pT + 32 * w, nb);
+        red_add(pA + 32 * w, nv + nb - nlo - nhi);           // RED.ADD, 128 B per warp instruction
+        red_add(pC + 32 * w, nlo - nb);
+        red_add(pG + 32 * w, nhi - nb);
+        red_add(pT + 32 * w, nb);
     }
     __syncwarp();
 #pragma unroll

@@ -30,6 +30,7 @@ __device__ __forceinline__ double neumaier_entropy(const long long *c, int n, lo
     const double tot = (double)total;
     for (int i = 0; i < n; i++) {
         if (i == skip || c[i] == 0) continue;            // p == 0 contributes int 0 (main.py:11)
+        if (c[i] == total) continue;                     // p == 1: -(1 * log2 1) = -0.0, and x + -0.0 == x exactly
         const double p = (double)c[i] / tot;
         const double x = -(p * log2(p));
         const double t = hi + x;
@@ -115,20 +116,31 @@ struct SummaryPartial {
     double ent_sum;
 };
 
-constexpr int kSummaryBlocks = 64;    // partials per slot (fixed -> deterministic reduction order)
+// Partials per slot: a fixed function of the slot length (-> deterministic reduction order), one
+// position per thread up to kSummaryMaxBlocks CTAs per slot.
+constexpr int kSummaryMaxBlocks = 2048;
+__host__ __device__ inline uint32_t summary_blocks(uint32_t ref_len)
+{
+    const uint32_t b = (ref_len + 255u) / 256u;
+    return b < 1u ? 1u : (b > (uint32_t)kSummaryMaxBlocks ? (uint32_t)kSummaryMaxBlocks : b);
+}
 
-// Fused stats + summarise partials for ALL slots: grid = (kSummaryBlocks, n_refs).
+// Fused stats + summarise partials for ALL slots: grid = (max blocks over slots, n_refs); partials of slot r
+// sit at part_off[r] .. part_off[r] + summary_blocks(ref_len[r]).
 __global__ void __launch_bounds__(256)
 k2_summary_partials(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64, uint64_t stride,
                     const uint32_t *__restrict__ col_base, const uint32_t *__restrict__ ref_len, int K,
-                    double norm, double norm2, SummaryPartial *__restrict__ partials)
+                    double norm, double norm2, const uint32_t *__restrict__ part_off,
+                    SummaryPartial *__restrict__ partials)
 {
     const uint32_t r = blockIdx.y;
     const uint32_t L = ref_len[r];
+    const uint32_t nb = summary_blocks(L);
+    if (blockIdx.x >= nb) return;
     const uint64_t base = col_base[r];
     long long nz = 0, cs = 0;
     double es = 0.0;
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < L; pos += gridDim.x * blockDim.x) {
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < L; pos += nb * blockDim.x) {
         long long c[6];
         load_counts(c32, c64, stride, base + pos, K, c);
         long long cov;
@@ -157,30 +169,44 @@ k2_summary_partials(const uint32_t *__restrict__ c32, const unsigned long long *
         p.nonzero = s_nz[0];
         p.cov_sum = s_cs[0];
         p.ent_sum = s_es[0];
-        partials[(uint64_t)r * gridDim.x + blockIdx.x] = p;
+        partials[(uint64_t)part_off[r] + blockIdx.x] = p;
     }
 }
 
-// grid = n_refs, block = kSummaryBlocks: fixed-order tree over the partials.
-__global__ void k2_summary_final(const SummaryPartial *__restrict__ partials, long long *__restrict__ nonzero,
-                                 long long *__restrict__ cov_sum, double *__restrict__ ent_sum)
+// grid = n_refs, block = 256: every thread sums its partials in index order, then a fixed-order tree.
+__global__ void __launch_bounds__(256)
+k2_summary_final(const SummaryPartial *__restrict__ partials, const uint32_t *__restrict__ part_off,
+                 const uint32_t *__restrict__ ref_len, long long *__restrict__ nonzero, long long *__restrict__ cov_sum,
+                 double *__restrict__ ent_sum)
 {
-    __shared__ SummaryPartial s[kSummaryBlocks];
+    __shared__ long long s_nz[256], s_cs[256];
+    __shared__ double s_es[256];
     const uint32_t r = blockIdx.x;
-    s[threadIdx.x] = partials[(uint64_t)r * kSummaryBlocks + threadIdx.x];
+    const uint32_t nb = summary_blocks(ref_len[r]);
+    const SummaryPartial *p = partials + part_off[r];
+    long long nz = 0, cs = 0;
+    double es = 0.0;
+    for (uint32_t i = threadIdx.x; i < nb; i += 256u) {
+        nz += p[i].nonzero;
+        cs += p[i].cov_sum;
+        es += p[i].ent_sum;
+    }
+    s_nz[threadIdx.x] = nz;
+    s_cs[threadIdx.x] = cs;
+    s_es[threadIdx.x] = es;
     __syncthreads();
-    for (int d = kSummaryBlocks / 2; d > 0; d >>= 1) {
+    for (int d = 128; d > 0; d >>= 1) {
         if ((int)threadIdx.x < d) {
-            s[threadIdx.x].nonzero += s[threadIdx.x + d].nonzero;
-            s[threadIdx.x].cov_sum += s[threadIdx.x + d].cov_sum;
-            s[threadIdx.x].ent_sum += s[threadIdx.x + d].ent_sum;
+            s_nz[threadIdx.x] += s_nz[threadIdx.x + d];
+            s_cs[threadIdx.x] += s_cs[threadIdx.x + d];
+            s_es[threadIdx.x] += s_es[threadIdx.x + d];
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        nonzero[r] = s[0].nonzero;
-        cov_sum[r] = s[0].cov_sum;
-        ent_sum[r] = s[0].ent_sum;
+        nonzero[r] = s_nz[0];
+        cov_sum[r] = s_cs[0];
+        ent_sum[r] = s_es[0];
     }
 }
 

@@ -135,8 +135,8 @@ int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
  * (entropy = 1 at zero coverage). */
 int bc_summary(bc_handle *h, int show_n, double norm, double norm2,
                int64_t *nonzero, int64_t *cov_sum, double *entropy_sum);
-/* Same, without waiting: the three outputs must be pinned host buffers (bc_host_alloc) and are
- * valid after the next bc_sync.  Lets a stream of batches pipeline without a host sync each. */
+/* Same, without waiting: the three outputs (any host memory) are filled in by the next bc_sync
+ * and must stay alive until then.  Lets a stream of batches pipeline without a host sync each. */
 int bc_summary_async(bc_handle *h, int show_n, double norm, double norm2,
                      int64_t *nonzero, int64_t *cov_sum, double *entropy_sum);
 
