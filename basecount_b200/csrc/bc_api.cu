@@ -337,14 +337,40 @@ int bc_reset(bc_handle *h)
 }  // extern "C"
 
 // ------------------------------------------------------------------ batches
-static int pick_group_width(const bc_batch *b, uint64_t total_words)
+// Lanes per read slot.  The window (64 * G columns) must hold a typical read at any 32-column
+// alignment; beyond that a wider window means fewer flushes (one per window of reads) but fewer
+// pieces per trip, so pick the G that minimises an instruction estimate per read:
+//     flush(G) / reads per flush  +  trip / pieces per trip
+// with reads per flush = what starts inside one window at the batch's mean depth, capped by the
+// 252-pieces-per-slot counter limit.  Deep amplicon piles end up at the narrowest G that fits the
+// reads; shallow whole-genome coverage (30x) at the next one up.
+static int pick_group_width(const bc_handle *h, const bc_batch *b, uint64_t total_words)
 {
-    // window = 32 * kW * G columns must hold a typical read at any 32-column alignment
     uint64_t mean = b->mean_read_len;
     if (mean == 0 && b->n_reads) mean = total_words * 32u / b->n_reads;
-    for (int G : {4, 8, 16})
-        if (mean + mean / 8 <= 32u * kW * G - 31u) return G;
-    return 32;
+    if (mean == 0) mean = 1;
+    uint64_t cols = 0;                                           // reference columns of the slots that got reads
+    for (uint32_t r = 0; r < b->n_refs; r++)
+        if (b->ref_read_off[r + 1] > b->ref_read_off[r]) cols += h->ref_len[r];
+    const double depth = cols ? (double)b->n_reads * (double)mean / (double)cols : 1e9;
+    static const double flush_cost[4] = {1000.0, 1500.0, 2300.0, 4000.0};      // G = 4, 8, 16, 32 (profiled / estimated)
+    int best = 32;
+    double best_cost = 1e300;
+    for (int i = 0; i < 4; i++) {
+        const int G = 4 << i;
+        const double win = 32.0 * kW * G;
+        if (G < 32 && (double)(mean + mean / 8) > win - 31.0) continue;          // reads would not fit
+        const int S = 32 / G;
+        const double fit = std::max(win - 31.0 - (double)mean, 32.0);           // start positions that fit one window
+        const double per_window = std::max(1.0, depth * fit / (double)mean);
+        const double per_flush = std::min(per_window, 252.0 * S / 1.1);
+        const double cost = flush_cost[i] / per_flush + 240.0 / (4.0 * S);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = G;
+        }
+    }
+    return best;
 }
 
 template <int G, bool OK>
@@ -511,7 +537,7 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
     const uint64_t n_words = b->seq_woff[n];
     if (n_cigar && !b->cigar) return fail(h, BC_ERR_ARG, "batch is missing cigar words");
     if (n_words && !b->planes) return fail(h, BC_ERR_ARG, "batch is missing sequence planes");
-    G = pick_group_width(b, n_words);
+    G = pick_group_width(h, b, n_words);
     mean_words = (uint32_t)((n_words + n - 1) / n);
 
     std::vector<Chunk> chunks;

@@ -133,3 +133,93 @@ def test_config1_full_size_vs_oracle(eng):
     # size-independent property: every aligned base lands in exactly one cell, unless it is an
     # uncounted letter (none here: only ACGTN are generated)
     assert int(got.sum()) == b.aligned_bases()
+
+
+def _reads_to_batch(reads):
+    """reads: list of (start, [(op, len), ...]); random ACGT bases, quality 30."""
+    rng = np.random.default_rng(len(reads))
+    seqs, quals, starts, cts = [], [], [], []
+    for start, ct in reads:
+        qn = sum(l for o, l in ct if o in (0, 1, 7, 8))
+        seqs.append("".join("ACGT"[i] for i in rng.integers(0, 4, size=qn)))
+        quals.append([30] * qn)
+        starts.append(start)
+        cts.append(ct)
+    return ReadBatch.from_lists(seqs, quals, starts, cts)
+
+
+def test_long_reads_inside_short_read_batches(eng):
+    """Reads far longer than the batch mean are not covered by the TMA stage of their block: they are
+    copied into a free stage segment by segment (20 kb = several segments), with indels inside."""
+    L = 60000
+    rng = np.random.default_rng(3)
+    reads = []
+    for i in range(3000):
+        s = int(rng.integers(0, L - 200))
+        reads.append((s, [(0, 150)]))
+        if i % 500 == 250:
+            s2 = int(rng.integers(0, L - 26000))
+            reads.append((s2, [(4, 10), (0, 9000), (1, 37), (0, 3000), (2, 5), (0, 8000), (3, 700), (8, 4000), (4, 3)]))
+        if i % 700 == 350:
+            reads.append((int(rng.integers(0, L - 3000)), [(0, 1400), (2, 1), (7, 1400)]))
+    reads.sort(key=lambda r: r[0])
+    b = _reads_to_batch(reads)
+    for mbq in (0, 31):
+        got = gpu_counts(eng, b, [L], mbq)[0]
+        assert np.array_equal(got, oracle_counts(b, L, mbq)), mbq
+
+
+def test_long_skips_many_ops_and_unsorted_windows(eng):
+    """N skips longer than a window (spliced reads), D runs beyond the single-lane limit, reads with more
+    than three ops next to plain ones, and a position order that forces windows to move backwards."""
+    L = 50000
+    rng = np.random.default_rng(11)
+    reads = []
+    for i in range(4000):
+        s = int(rng.integers(0, L - 12000))
+        kind = i % 8
+        if kind == 0:
+            reads.append((s, [(0, 60), (3, int(rng.integers(33, 9000))), (0, 90)]))
+        elif kind == 1:
+            reads.append((s, [(0, 40), (2, int(rng.integers(30, 200))), (0, 50), (1, 3), (0, 57)]))
+        elif kind == 2:
+            reads.append((s, [(4, 5), (7, 30), (8, 1), (7, 30), (1, 2), (0, 20), (2, 2), (0, 40), (5, 9)]))
+        elif kind == 3:
+            reads.append((s, [(3, 40), (0, 150)]))              # leading skip: run B only
+        else:
+            reads.append((s, [(0, 150)]))
+    for order in ("sorted", "reverse", "random"):
+        rs = sorted(reads, key=lambda r: r[0])
+        if order == "reverse":
+            rs = rs[::-1]
+        elif order == "random":
+            rs = [rs[i] for i in rng.permutation(len(rs))]
+        b = _reads_to_batch(rs)
+        got = gpu_counts(eng, b, [L])[0]
+        assert np.array_equal(got, oracle_counts(b, L)), order
+
+
+def test_fuzz_with_alignments_past_the_reference_end(eng):
+    """Batches where some alignments run past ref_len: the GPU path must raise IndexError exactly when
+    the reference does (count.cpp .at()), and agree on the counts otherwise."""
+    from basecount_b200.pack import pack_batches
+    raised = clean = 0
+    for seed in range(300, 360):
+        b = synth.fuzz_batch(seed, n_reads=5, ref_len=400, allow_overflow=True, sorted_by_pos=(seed % 2 == 0),
+                             long_op_frac=0.02)
+        for mbq in (0, 30):
+            try:
+                want = oracle_counts(b, 400, mbq)
+            except IndexError:
+                want = None
+            eng.begin([400])
+            eng.push(pack_batches(b, mbq))
+            if want is None:
+                with pytest.raises(IndexError):
+                    eng.sync()
+                raised += 1
+            else:
+                eng.sync()
+                assert np.array_equal(eng.counts(0), want), (seed, mbq)
+                clean += 1
+    assert raised > 5 and clean > 5
