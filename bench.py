@@ -98,6 +98,17 @@ def build_workload(args, rank):
         return sets, [synth.SARS2_LEN], "cfg3_2M_reads_150bp"
     n = args.cfg5_reads
     L = int(synth.CHR20_LEN * (n / 12_888_833))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # region sharding: ONE reference, rank r owns [bounds[r], bounds[r+1]) and generates
+        # only the reads that start there (they may run past the right edge -> halo columns)
+        from basecount_b200 import dist as bdist
+        bounds = bdist.region_bounds(L, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        rec = synth.uniform_short_read_sample(seed=5 + rank, ref_len=L, n_reads=n // world, start_lo=lo,
+                                              start_hi=min(hi, L - 150))
+        local = bdist.select_region(select_reads(rec, 0, 0), lo, hi)
+        return [[local]], [L], f"cfg5_uniform_150bp_L{L}_region_sharded"
     sets = [[select_reads(synth.uniform_short_read_sample(seed=5 + rank, ref_len=L, n_reads=n), 0, 0)]]
     return sets, [L], f"cfg5_uniform_150bp_L{L}"
 
@@ -250,6 +261,107 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- config 5 over N GPUs
+def run_region_sharded(args, local_reads, ref_len, label, rank, world, local, barrier, max_over_ranks, sum_over_ranks):
+    """One reference cut into `world` regions (strong scaling).  A step = zero the accumulators, count
+    the rank's reads (resident in HBM), send the halo columns to the ranks that own them (NCCL
+    send/recv on device buffers), add the received ones, cut the slot back to the owned columns,
+    the --summarise reductions and the all-reduce of the three scalars."""
+    import torch
+    import torch.distributed as dist
+    from basecount_b200 import dist as bdist
+    from basecount_b200.engine import Engine
+    from basecount_b200.pack import pack_batches
+    bounds = bdist.region_bounds(ref_len, world)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    h = bdist.halo_columns(local_reads, hi - lo, ref_len - hi)
+    mine = torch.tensor([h], dtype=torch.int64, device="cuda")
+    gathered = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    halos = [int(t.item()) for t in gathered]                 # known once the reads are packed
+    eng = Engine(local)
+    be = bdist.GpuBackend(eng, torch.device("cuda", local))
+    eng.begin([hi - lo + h])
+    packed = pack_batches([local_reads], 0, pinned=True)
+    resident = eng.upload(packed)
+    bases = packed.aligned_bases
+
+    def step():
+        eng.begin([hi - lo + h])
+        eng.push(resident)
+        eng.sync()
+        bdist.exchange_halos(be, dist, rank, world, bounds, halos)
+        eng.truncate(0, hi - lo)
+        return bdist.summary_region_sharded(be, dist, world, ref_len)
+
+    res = step()
+    # size-independent checks: every aligned base of every rank is in exactly one cell of the merged
+    # matrix (sum of coverage + N column), and all ranks hold the same all-reduced summary
+    total_bases = sum_over_ranks(float(bases))
+    cells = sum_over_ranks(float(eng.counts(0).sum()))
+    assert cells == total_bases, (cells, total_bases)
+    chk = torch.tensor([res[0], float(res[1]), float(res[2])], dtype=torch.float64, device="cuda")
+    ref = chk.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(chk, ref)
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.kernel_launches()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.kernel_launches() - launches0
+    clk = clocks.stop()
+    hist = eng.count_kernel_ms_history(min(args.steps, 256))
+    k1_ms = max_over_ranks(float(np.mean(hist)))
+    # e2e: the same step from pinned host buffers (H2D inside), result read back every step
+    def step_e2e():
+        eng.begin([hi - lo + h])
+        eng.push(packed)
+        eng.sync()
+        bdist.exchange_halos(be, dist, rank, world, bounds, halos)
+        eng.truncate(0, hi - lo)
+        return bdist.summary_region_sharded(be, dist, world, ref_len)
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+    alg = packed.algorithmic_bytes([hi - lo + h])
+    achieved = alg / (k1_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": total_bases * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": label, "ref_len": ref_len, "reads_total": int(sum_over_ranks(float(packed.n_reads))),
+                       "aligned_bases_total": total_bases, "halo_columns": halos,
+                       "collective": "NCCL send/recv of the halo columns + all-reduce of 3 scalars",
+                       "l2": f"inputs {packed.h2d_bytes() / 1e6:.0f} MB per rank per step; count planes "
+                             f"{(hi - lo) * 24 / 1e6:.0f} MB per rank",
+                       "timing": "CUDA events around the K steps (each step host-synchronised for the exchange); max over ranks"},
+            "e2e": {"value": total_bases * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": packed.h2d_bytes(),
+                    "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "timing": "host wall clock, device-synchronised both sides"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k1_count_tiled", "kernel_ms": k1_ms,
+                         "algorithmic_bytes_per_launch": alg, "note": "per rank (max over ranks of the mean K1 time)"},
+            "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": None}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    resident.free()
+    eng.close()
+
+
 # ----------------------------------------------------------------------------- our arm
 def main():
     args = parse()
@@ -293,6 +405,10 @@ def main():
     from basecount_b200.pack import pack_batches
 
     sets, ref_lens, label = build_workload(args, rank)
+    if args.workload == "cfg5" and world > 1:
+        run_region_sharded(args, sets[0][0], ref_lens[0], label, rank, world, local, barrier, max_over_ranks, sum_over_ranks)
+        dist.destroy_process_group()
+        return
     eng = Engine(local)
     eng.set_count_variant(args.variant)
     eng.begin(ref_lens)
