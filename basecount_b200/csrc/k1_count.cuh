@@ -514,22 +514,23 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         int slow_lane = -1;                                          // lane whose read is staged by hand right now
         uint32_t seg_w = 0u, seg_end = 0u;                           // its current segment / end (plane word indices)
 
-        // ---- fast path: reads with at most three CIGAR ops (which is nearly all short reads: M, M-I-M,
+        // ---- fast mode: reads with at most three CIGAR ops (which is nearly all short reads: M, M-I-M,
         //      M-D-M, clipped or =/X spellings) are decoded in straight-line code, no loop and no
         //      votes: a missing op reads as a zero-length M, which changes nothing.  Ops of one match
         //      run (nothing but zero-length or S/H/P ops between them) merge into one piece; a run
         //      starts at the read start (run A) or right after the first non-empty I/D/N (run B).
-        //      If every read of the block qualifies and every piece fits the current window, the
-        //      pieces are committed in one go.  Anything else (more ops, window moves, clipping at
-        //      the reference end, long D/N runs, hand-staged reads) takes the lock-step walker
-        //      below, which starts the block from scratch: nothing here has side effects before
-        //      the commit.
-        bool prewalked = false;
+        //      If every read of the block qualifies, the block runs in fast mode: pieces that fit the
+        //      window are pushed with two votes, the rest after a window move.  Anything else (more
+        //      ops, clipping at the reference end, long D/N runs, runs longer than a window,
+        //      hand-staged reads) takes the lock-step walker, which starts the block from scratch:
+        //      the decode has no side effects.
+        uint32_t nA = 0u, nB = 0u, ppB = 0u;                          // pending pieces of this lane (length 0 = none)
+        int pqB = 0;
+        bool fast = false;
         if (!last) {
             const uint32_t ncig = cend_all - cbase;
-            bool bad = unst != 0u || !win_valid || (valid && (!cig_staged || ncig > 3u));
-            uint32_t nA = 0u, nB = 0u, ppB = 0u, sk_pos = 0u, sk_n = 0u;
-            int pqB = 0;
+            bool bad = unst != 0u || (valid && (!cig_staged || ncig > 3u));
+            uint32_t sk_pos = 0u, sk_n = 0u;
             if (staged) {
                 const uint32_t ca = cg + cbase * 4u;
                 uint32_t cw[3];
@@ -558,34 +559,59 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 sk_n = dlen[0] + dlen[1] + dlen[2];
                 sk_pos = dlen[0] ? r[0] : (dlen[1] ? r[1] : r[2]);
                 const uint32_t nsk = (dlen[0] ? 1u : 0u) + (dlen[1] ? 1u : 0u) + (dlen[2] ? 1u : 0u);
-                // reference end, data bounds, piece lengths, window fit: rel + n <= kWin with
-                // rel = pp - win_lo as unsigned (pp below the window wraps)
+                // reference end, data bounds, piece lengths
                 bad = bad || r[3] > ref_len || q[3] > (uint32_t)qend || (brk[0] && brk[1] && mlen[2] != 0u) || nsk > 1u ||
-                      sk_n > kLaneSkipMax || nA > C::kMaxFit || nB > C::kMaxFit ||
-                      (nA != 0u && rpos - win_lo > kWin - nA) || (nB != 0u && ppB - win_lo > kWin - nB);
+                      sk_n > kLaneSkipMax || nA > C::kMaxFit || nB > C::kMaxFit;
             }
-            const uint32_t has0 = __ballot_sync(kFull, nA != 0u), has1 = __ballot_sync(kFull, nB != 0u);
-            const uint32_t np = __popc(has0) + __popc(has1);
-            if (!__any_sync(kFull, bad) && (ring_tail - ring_head) + np <= kRing) {
-                __syncwarp();                                        // earlier ring reads are done
-                uint32_t at = ring_tail + __popc(has0 & lt_mask) + __popc(has1 & lt_mask);
-                if (nA != 0u) {
-                    sts128(ringb + 16u * (at & (kRing - 1u)), make_entry(rpos - win_lo, nA, qb));
-                    at++;
-                }
-                if (nB != 0u) sts128(ringb + 16u * (at & (kRing - 1u)), make_entry(ppB - win_lo, nB, pqB));
-                ring_tail += np;
+            fast = !__any_sync(kFull, bad);
+            if (fast) {
                 for (uint32_t t = 0; t < sk_n; t++) atomicAdd(ds_plane + sk_pos + t, 1u);     // count.cpp:80-87
-                __syncwarp();
-                cur = cend;                                          // every read of the block is done
-                prewalked = true;
+                cur = cend;                                          // the walker has nothing to do
+            } else {
+                nA = 0u;
+                nB = 0u;
             }
         }
 
         for (;;) {
-            int action = 2;                 // 0: keep walking, 1: everyone waits for a window move, 2: this pass is over
+            int action = 2;                 // 0: keep going, 1: everyone waits for a window move, 2: this pass is over
             uint32_t new_lo = 0u;
-            if (!prewalked) {
+            if (fast) {
+                // ---- push the pending pieces that fit the window: rel + n <= kWin with rel = pp - win_lo
+                //      as unsigned (pp below the window wraps)
+                const uint32_t relA = rpos - win_lo, relB = ppB - win_lo;
+                const bool fitA = nA != 0u && win_valid && relA <= kWin - nA;
+                const bool fitB = nB != 0u && win_valid && relB <= kWin - nB;
+                const uint32_t mA = __ballot_sync(kFull, fitA), mB = __ballot_sync(kFull, fitB);
+                const uint32_t npA = __popc(mA), npB = __popc(mB);
+                // the ring always has room for one piece per lane; run B waits a round if both do not fit
+                const bool allB = npA + npB <= kRing - (ring_tail - ring_head);
+                const uint32_t mBp = allB ? mB : 0u;
+                if (mA | mBp) {
+                    __syncwarp();                                    // earlier ring reads are done
+                    uint32_t at = ring_tail + __popc(mA & lt_mask) + __popc(mBp & lt_mask);
+                    if (fitA) {
+                        sts128(ringb + 16u * (at & (kRing - 1u)), make_entry(relA, nA, qb));
+                        at++;
+                        nA = 0u;
+                    }
+                    if (fitB && allB) {
+                        sts128(ringb + 16u * (at & (kRing - 1u)), make_entry(relB, nB, pqB));
+                        nB = 0u;
+                    }
+                    ring_tail += npA + (allB ? npB : 0u);
+                    __syncwarp();
+                }
+                const bool left = (nA | nB) != 0u;
+                if (__any_sync(kFull, left)) {
+                    if (mB != 0u && !allB) {
+                        action = 0;                                  // run B pieces fit, they only waited for ring room
+                    } else {                                         // move the window to the lowest pending piece
+                        action = 1;
+                        new_lo = __reduce_min_sync(kFull, min(nA ? rpos : 0xFFFFFFFFu, nB ? ppB : 0xFFFFFFFFu)) & ~31u;
+                    }
+                }
+            } else {
                 // ---- F: fetch CIGAR ops until an M/=/X run is open (count.cpp:40-96)
                 bool moved = false;
                 while (rem == 0u && ds_n == 0u && cur < cend) {
@@ -764,7 +790,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 win_valid = true;
             }
             if (action != 2) continue;
-            if (prewalked) break;
+            if (fast) break;
 
             // ---- pass over: reads that were not staged are copied into this stage segment by segment
             if (slow_lane >= 0) {
