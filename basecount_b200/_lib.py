@@ -72,6 +72,21 @@ _SIGNATURES = {
     "bc_count_kernel_ms_history": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
     "bc_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
     "bc_set_count_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    # native BAM decode (host code in the same library)
+    "bc_bam_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "bc_bam_last_error": (ctypes.c_char_p, []),
+    "bc_bam_close": (None, [ctypes.c_void_p]),
+    "bc_bam_num_records": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "bc_bam_num_refs": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "bc_bam_ref_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_uint32]),
+    "bc_bam_ref_len": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_uint32]),
+    "bc_bam_core": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bc_bam_select_sizes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint32,
+                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                                           ctypes.POINTER(ctypes.c_uint64)]),
+    "bc_bam_select_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint32,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -172,6 +172,69 @@ def read_bam(path: str, threads: int = 8) -> Records:
     return decode_bam_bytes(bgzf_decompress(data, threads))
 
 
+# ----------------------------------------------------------------------------- native decoder
+class NativeBam:
+    """BAM file decoded by the C-ABI library (csrc/bam_decode.h): block-parallel inflate, one record
+    index, and thread-parallel selections straight into ReadBatch arrays -- no per-read objects.
+    Same results as `select_reads(read_bam(path), ...)` (tests/test_bamio.py)."""
+
+    def __init__(self, path: str, threads: int = 0):
+        import ctypes
+        from . import _lib
+        self._h = None
+        self._L = _lib.lib()
+        h = ctypes.c_void_p()
+        if self._L.bc_bam_open(str(path).encode(), int(threads), ctypes.byref(h)) != 0 or not h.value:
+            msg = self._L.bc_bam_last_error()
+            raise ValueError(msg.decode() if msg else "cannot read BAM file")
+        self._h = h
+        self.n = int(self._L.bc_bam_num_records(h))
+        nref = int(self._L.bc_bam_num_refs(h))
+        self.ref_names = [self._L.bc_bam_ref_name(h, i).decode("ascii") for i in range(nref)]
+        self.ref_lengths = [int(self._L.bc_bam_ref_len(h, i)) for i in range(nref)]
+        self._core = None
+
+    def close(self):
+        if self._h is not None:
+            self._L.bc_bam_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def core(self):
+        """(ref_id int32[n], pos int32[n], mapq uint8[n], flag uint16[n]) of every record."""
+        if self._core is None:
+            from . import _lib
+            ref_id = np.empty(self.n, np.int32)
+            pos = np.empty(self.n, np.int32)
+            mapq = np.empty(self.n, np.uint8)
+            flag = np.empty(self.n, np.uint16)
+            self._L.bc_bam_core(self._h, _lib.ptr(ref_id), _lib.ptr(pos), _lib.ptr(mapq), _lib.ptr(flag))
+            self._core = (ref_id, pos, mapq, flag)
+        return self._core
+
+    def select(self, ref_id: int, min_mapping_quality: int = 0, rec_a: int = 0, rec_b: int | None = None):
+        """ReadBatch of the kept reads of one reference among records [rec_a, rec_b)."""
+        import ctypes
+        from . import _lib
+        from .records import ReadBatch
+        rec_b = self.n if rec_b is None else rec_b
+        nr, nc, nb = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        self._L.bc_bam_select_sizes(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), ctypes.byref(nr),
+                                    ctypes.byref(nc), ctypes.byref(nb))
+        n = nr.value
+        starts = np.empty(n, np.uint32)
+        cigar = np.empty(nc.value, np.uint32)
+        cigar_off = np.empty(n + 1, np.uint64)
+        seq = np.empty(nb.value, np.uint8)
+        qual = np.empty(nb.value, np.uint8)
+        seq_off = np.empty(n + 1, np.uint64)
+        self._L.bc_bam_select_fill(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), _lib.ptr(starts),
+                                   _lib.ptr(cigar), _lib.ptr(cigar_off), _lib.ptr(seq), _lib.ptr(qual), _lib.ptr(seq_off))
+        return ReadBatch(starts, cigar, cigar_off, seq, qual, seq_off)
+
+
 # ----------------------------------------------------------------------------- Records -> BAM
 def _reg2bin(beg: np.ndarray, end: np.ndarray) -> np.ndarray:
     end = end - 1

@@ -1,0 +1,380 @@
+// bam_decode.h -- native BGZF / BAM decode straight into the flat arrays the packer consumes.
+//
+// Replaces, on the host side of the path, what the reference does per read through pysam
+// (basecount/main.py:97-99 open, :127 fetch(until_eof=True), :165 the read filter, :166-173 the
+// four per-read attributes query_alignment_sequence / query_alignment_qualities /
+// reference_start / cigartuples) -- SURVEY.md section 8(f) rank 1.  No per-read objects: the file
+// is inflated block-parallel (BGZF blocks are independent deflate streams, SAM spec 4.1), the
+// records are indexed once, and a selection (record range, reference id, minimum MAPQ) is copied
+// into caller-owned arrays by a pool of threads: start, BAM-native CIGAR words, soft-clip-trimmed
+// ASCII bases and phred bytes -- exactly a ReadBatch (basecount_b200/records.py).
+//
+// Host-only code (zlib + std::thread); compiled into the same C-ABI library as the kernels.
+#pragma once
+#include <stdint.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+struct bc_bam {
+    std::vector<uint8_t> raw;               // the inflated BAM stream
+    std::vector<std::string> ref_names;
+    std::vector<uint32_t> ref_lens;
+    std::vector<uint64_t> rec_off;          // offset of every record's block_size field, plus the end
+    int threads = 1;
+    std::string err;
+};
+
+namespace bcbam {
+
+inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+struct Block { uint64_t c0, c1, u0; uint32_t isize, crc; };
+
+template <class F>
+inline void parallel_for(int threads, uint64_t n, uint64_t grain, F f)
+{
+    if (n == 0) return;
+    const uint64_t chunks = (n + grain - 1) / grain;
+    const int t = (int)std::min<uint64_t>((uint64_t)std::max(threads, 1), chunks);
+    if (t <= 1) {
+        f(0, n);
+        return;
+    }
+    std::atomic<uint64_t> next(0);
+    std::vector<std::thread> pool;
+    for (int i = 0; i < t; i++)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const uint64_t c = next.fetch_add(1);
+                if (c >= chunks) break;
+                f(c * grain, std::min(n, (c + 1) * grain));
+            }
+        });
+    for (auto &th : pool) th.join();
+}
+
+// Every BGZF block of the file (SAM spec 4.1: gzip member with a 'BC' extra subfield holding BSIZE-1).
+inline bool scan_blocks(const std::vector<uint8_t> &d, std::vector<Block> &out, uint64_t &total, std::string &err)
+{
+    uint64_t off = 0;
+    const uint64_t n = d.size();
+    total = 0;
+    while (off < n) {
+        if (n - off < 18 || d[off] != 31 || d[off + 1] != 139 || d[off + 2] != 8 || !(d[off + 3] & 4)) {
+            err = "not a BGZF file (bad gzip member header)";
+            return false;
+        }
+        const uint32_t xlen = rd16(&d[off + 10]);
+        uint64_t p = off + 12;
+        const uint64_t end = off + 12 + xlen;
+        uint32_t bsize = 0;
+        if (end > n) {
+            err = "truncated BGZF block";
+            return false;
+        }
+        while (p + 4 <= end) {
+            const uint32_t slen = rd16(&d[p + 2]);
+            if (d[p] == 66 && d[p + 1] == 67 && slen == 2 && p + 6 <= end) bsize = (uint32_t)rd16(&d[p + 4]) + 1u;
+            p += 4 + slen;
+        }
+        if (bsize == 0 || off + bsize > n || bsize < 12 + xlen + 8) {
+            err = "BGZF block without BC subfield or truncated";
+            return false;
+        }
+        Block b;
+        b.c0 = off + 12 + xlen;
+        b.c1 = off + bsize - 8;
+        b.crc = rd32(&d[off + bsize - 8]);
+        b.isize = rd32(&d[off + bsize - 4]);
+        b.u0 = total;
+        total += b.isize;
+        out.push_back(b);
+        off += bsize;
+    }
+    return true;
+}
+
+// Soft-clipped bases at the left / right end of a record's CIGAR: what pysam's
+// query_alignment_start / query_alignment_end trim (hard clips hold no bases; an optional H may sit
+// outside the S).  Same rule as records._leading_trailing_clips.
+inline void clips(const uint8_t *cig, uint32_t n_cigar, uint32_t &lead, uint32_t &trail)
+{
+    lead = trail = 0;
+    if (n_cigar == 0) return;
+    const uint32_t l = n_cigar - 1;
+    uint32_t f2 = 0, l2 = l;
+    if ((rd32(cig) & 15u) == 5u && 1u <= l) f2 = 1;                        // optional hard clip outside the soft clip
+    const uint32_t wf = rd32(cig + 4 * f2);
+    if ((wf & 15u) == 4u) lead = wf >> 4;
+    if ((rd32(cig + 4 * l) & 15u) == 5u && l >= 1u) l2 = l - 1;
+    const uint32_t wl = rd32(cig + 4 * l2);
+    if ((wl & 15u) == 4u && !(l2 == f2 && (wf & 15u) == 4u)) trail = wl >> 4;   // a single S op is not counted twice
+}
+
+struct RecView {
+    int32_t ref_id, pos;
+    uint32_t l_read_name, mapq, n_cigar, flag, l_seq;
+    const uint8_t *cig, *seq, *qual;
+};
+
+inline bool view(const bc_bam *b, uint64_t i, RecView &v)
+{
+    const uint64_t o = b->rec_off[i], e = b->rec_off[i + 1];
+    if (e - o < 36) return false;
+    const uint8_t *p = b->raw.data() + o;
+    v.ref_id = (int32_t)rd32(p + 4);
+    v.pos = (int32_t)rd32(p + 8);
+    v.l_read_name = p[12];
+    v.mapq = p[13];
+    v.n_cigar = rd16(p + 16);
+    v.flag = rd16(p + 18);
+    v.l_seq = rd32(p + 20);
+    const uint64_t need = 36ull + v.l_read_name + 4ull * v.n_cigar + (v.l_seq + 1ull) / 2 + v.l_seq;
+    if (need > e - o) return false;
+    v.cig = p + 36 + v.l_read_name;
+    v.seq = v.cig + 4ull * v.n_cigar;
+    v.qual = v.seq + (v.l_seq + 1ull) / 2;
+    return true;
+}
+
+inline bool keep(const RecView &v, int32_t ref_id, uint32_t min_mapq)
+{
+    return !(v.flag & 4u) && v.mapq >= min_mapq && v.ref_id == ref_id;      // basecount/main.py:165-166
+}
+
+}  // namespace bcbam
+
+// ---- API (exported with C linkage from bc_api.cu) ---------------------------------------------
+inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::string &err)
+{
+    using namespace bcbam;
+    FILE *fh = std::fopen(path, "rb");
+    if (!fh) {
+        err = std::string("cannot open ") + path;
+        return 1;
+    }
+    std::vector<uint8_t> file;
+    std::fseek(fh, 0, SEEK_END);
+    const long sz = std::ftell(fh);
+    std::fseek(fh, 0, SEEK_SET);
+    if (sz < 0) {
+        std::fclose(fh);
+        err = "cannot size the file";
+        return 1;
+    }
+    file.resize((size_t)sz);
+    if (sz && std::fread(file.data(), 1, (size_t)sz, fh) != (size_t)sz) {
+        std::fclose(fh);
+        err = "short read";
+        return 1;
+    }
+    std::fclose(fh);
+
+    bc_bam *b = new bc_bam();
+    b->threads = threads > 0 ? threads : (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    std::vector<Block> blocks;
+    uint64_t total = 0;
+    if (!scan_blocks(file, blocks, total, err)) {
+        delete b;
+        return 2;
+    }
+    b->raw.resize(total);
+    std::atomic<int> bad(0);
+    parallel_for(b->threads, blocks.size(), 16, [&](uint64_t a, uint64_t e) {
+        z_stream zs;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            bad = 1;
+            return;
+        }
+        for (uint64_t i = a; i < e; i++) {
+            const Block &k = blocks[i];
+            if (k.isize == 0) continue;
+            inflateReset(&zs);
+            zs.next_in = const_cast<Bytef *>(file.data() + k.c0);
+            zs.avail_in = (uInt)(k.c1 - k.c0);
+            zs.next_out = b->raw.data() + k.u0;
+            zs.avail_out = k.isize;
+            const int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), b->raw.data() + k.u0, k.isize) != k.crc)
+                bad = 1;
+        }
+        inflateEnd(&zs);
+    });
+    if (bad) {
+        err = "corrupt BGZF block (inflate or CRC failed)";
+        delete b;
+        return 2;
+    }
+    // header (SAM spec 4.2)
+    const std::vector<uint8_t> &r = b->raw;
+    if (r.size() < 12 || std::memcmp(r.data(), "BAM\1", 4) != 0) {
+        err = "not a BAM file (bad magic)";
+        delete b;
+        return 2;
+    }
+    uint64_t p = 8ull + rd32(&r[4]);
+    if (p + 4 > r.size()) {
+        err = "truncated BAM header";
+        delete b;
+        return 2;
+    }
+    const uint32_t n_ref = rd32(&r[p]);
+    p += 4;
+    for (uint32_t i = 0; i < n_ref; i++) {
+        if (p + 4 > r.size()) {
+            err = "truncated BAM header";
+            delete b;
+            return 2;
+        }
+        const uint32_t l_name = rd32(&r[p]);
+        if (p + 8ull + l_name > r.size() || l_name == 0) {
+            err = "truncated BAM header";
+            delete b;
+            return 2;
+        }
+        b->ref_names.emplace_back((const char *)&r[p + 4], l_name - 1);
+        b->ref_lens.push_back(rd32(&r[p + 4 + l_name]));
+        p += 8ull + l_name;
+    }
+    // record index
+    while (p + 4 <= r.size()) {
+        b->rec_off.push_back(p);
+        p += 4ull + rd32(&r[p]);
+    }
+    if (p != r.size()) {
+        err = "truncated BAM record";
+        delete b;
+        return 2;
+    }
+    b->rec_off.push_back(p);
+    RecView v;
+    for (uint64_t i = 0; i + 1 < b->rec_off.size(); i++)
+        if (!view(b, i, v)) {
+            err = "malformed BAM record";
+            delete b;
+            return 2;
+        }
+    *out = b;
+    return 0;
+}
+
+// ref_id / pos / mapq / flag of every record (what count_alignments needs to place its chunk cuts).
+inline void bc_bam_core_impl(const bc_bam *b, int32_t *ref_id, int32_t *pos, uint8_t *mapq, uint16_t *flag)
+{
+    using namespace bcbam;
+    const uint64_t n = b->rec_off.size() - 1;
+    parallel_for(b->threads, n, 1 << 14, [&](uint64_t a, uint64_t e) {
+        RecView v;
+        for (uint64_t i = a; i < e; i++) {
+            view(b, i, v);
+            if (ref_id) ref_id[i] = v.ref_id;
+            if (pos) pos[i] = v.pos;
+            if (mapq) mapq[i] = (uint8_t)v.mapq;
+            if (flag) flag[i] = (uint16_t)v.flag;
+        }
+    });
+}
+
+// Sizes of the selection: kept reads, their CIGAR ops and their soft-clip-trimmed bases.
+inline void bc_bam_select_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                                     uint64_t *n_reads, uint64_t *n_cigar, uint64_t *n_bases)
+{
+    using namespace bcbam;
+    std::atomic<uint64_t> nr(0), nc(0), nb(0);
+    parallel_for(b->threads, rec_b - rec_a, 1 << 13, [&](uint64_t a, uint64_t e) {
+        uint64_t r = 0, c = 0, s = 0;
+        RecView v;
+        for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
+            view(b, i, v);
+            if (!keep(v, ref_id, min_mapq)) continue;
+            uint32_t lead, trail;
+            clips(v.cig, v.n_cigar, lead, trail);
+            const uint64_t s0 = std::min<uint64_t>(lead, v.l_seq);
+            const uint64_t s1 = std::max<uint64_t>(s0, (uint64_t)v.l_seq > trail ? v.l_seq - trail : 0);
+            r++;
+            c += v.n_cigar;
+            s += s1 - s0;
+        }
+        nr += r;
+        nc += c;
+        nb += s;
+    });
+    *n_reads = nr;
+    *n_cigar = nc;
+    *n_bases = nb;
+}
+
+// Fill a ReadBatch for the selection.  Arrays sized by bc_bam_select_sizes (offset arrays n+1).
+inline void bc_bam_select_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                                    uint32_t *starts, uint32_t *cigar, uint64_t *cigar_off, uint8_t *seq, uint8_t *qual,
+                                    uint64_t *seq_off)
+{
+    using namespace bcbam;
+    static const char kNib[] = "=ACMGRSVTWYHKDBN";
+    const uint64_t n = rec_b - rec_a;
+    const uint64_t grain = 1 << 13;
+    const uint64_t chunks = (n + grain - 1) / grain;
+    // pass 1: per-chunk totals -> exclusive offsets, so every chunk writes its own disjoint range
+    std::vector<uint64_t> cr(chunks + 1, 0), cc(chunks + 1, 0), cs(chunks + 1, 0);
+    parallel_for(b->threads, n, grain, [&](uint64_t a, uint64_t e) {
+        uint64_t r = 0, c = 0, s = 0;
+        RecView v;
+        for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
+            view(b, i, v);
+            if (!keep(v, ref_id, min_mapq)) continue;
+            uint32_t lead, trail;
+            clips(v.cig, v.n_cigar, lead, trail);
+            const uint64_t s0 = std::min<uint64_t>(lead, v.l_seq);
+            const uint64_t s1 = std::max<uint64_t>(s0, (uint64_t)v.l_seq > trail ? v.l_seq - trail : 0);
+            r++;
+            c += v.n_cigar;
+            s += s1 - s0;
+        }
+        const uint64_t k = a / grain;
+        cr[k + 1] = r;
+        cc[k + 1] = c;
+        cs[k + 1] = s;
+    });
+    for (uint64_t k = 0; k < chunks; k++) {
+        cr[k + 1] += cr[k];
+        cc[k + 1] += cc[k];
+        cs[k + 1] += cs[k];
+    }
+    cigar_off[0] = 0;
+    seq_off[0] = 0;
+    parallel_for(b->threads, n, grain, [&](uint64_t a, uint64_t e) {
+        const uint64_t k = a / grain;
+        uint64_t r = cr[k], c = cc[k], s = cs[k];
+        RecView v;
+        for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
+            view(b, i, v);
+            if (!keep(v, ref_id, min_mapq)) continue;
+            uint32_t lead, trail;
+            clips(v.cig, v.n_cigar, lead, trail);
+            const uint64_t s0 = std::min<uint64_t>(lead, v.l_seq);
+            const uint64_t s1 = std::max<uint64_t>(s0, (uint64_t)v.l_seq > trail ? v.l_seq - trail : 0);
+            starts[r] = (uint32_t)v.pos;
+            for (uint32_t t = 0; t < v.n_cigar; t++) cigar[c + t] = rd32(v.cig + 4 * t);
+            for (uint64_t q = s0; q < s1; q++) {
+                const uint8_t byte = v.seq[q >> 1];
+                seq[s + (q - s0)] = (uint8_t)kNib[(q & 1) ? (byte & 15) : (byte >> 4)];
+            }
+            std::memcpy(qual + s, v.qual + s0, s1 - s0);
+            r++;
+            c += v.n_cigar;
+            s += s1 - s0;
+            cigar_off[r] = c;
+            seq_off[r] = s;
+        }
+    });
+}

@@ -10,8 +10,11 @@
 #include "k1_count.cuh"
 #include "k2_stats.cuh"
 #include "k3_reduce.cuh"
+#include "bam_decode.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -954,59 +957,130 @@ int bc_pack_reads(uint32_t n_reads, const uint8_t *seq, const uint8_t *qual, con
     uint8_t cls[256];
     std::memset(cls, 5, sizeof(cls));
     cls['A'] = 0; cls['C'] = 1; cls['G'] = 2; cls['T'] = 3; cls['N'] = 4;
+    // word offsets first (every read starts on a fresh 32-base word), then the reads in parallel
     uint64_t w = 0;
-    uint64_t ne = 0;
-    int status = BC_OK;
     for (uint32_t i = 0; i < n_reads; i++) {
-        const uint64_t s0 = seq_off[i], len = seq_off[i + 1] - s0;
-        if (w > 0xFFFFFFFFull) return BC_ERR_ARG;
+        const uint64_t len = seq_off[i + 1] - seq_off[i];
+        if (w > 0xFFFFFFFFull || len >= (1ull << 30)) return BC_ERR_ARG;
         seq_woff_out[i] = (uint32_t)w;
-        if (cigar && cigar_off) {          // count.cpp:56,58 index quals/read unchecked: reject what would be UB there
-            uint64_t rp = 0;
-            for (uint32_t c = cigar_off[i]; c < cigar_off[i + 1]; c++) {
-                const uint32_t op = cigar[c] & 0xFu, l = cigar[c] >> 4;
-                if (op == 0 || op == 7 || op == 8) {
-                    if (l && rp + l > len) status = BC_ERR_READ_OVERRUN;
-                    rp += l;
-                } else if (op == 1) {
-                    rp += l;
-                }
-            }
-        }
-        for (uint64_t j0 = 0; j0 < len; j0 += 32, w++) {
-            const uint32_t m = (uint32_t)std::min<uint64_t>(32, len - j0);
-            uint32_t lo = 0, hi = 0, ok = 0;
-            const uint8_t *sp = seq + s0 + j0;
-            const uint8_t *qp = qual ? qual + s0 + j0 : nullptr;
-            for (uint32_t j = 0; j < m; j++) {
-                const uint8_t c = cls[sp[j]];
-                const bool pass = !qp || qp[j] >= min_base_quality;
-                if (c < 4) {
-                    lo |= (uint32_t)(c & 1u) << j;
-                    hi |= (uint32_t)(c >> 1) << j;
-                    ok |= (uint32_t)pass << j;
-                } else {
-                    uint32_t flags = 0;
-                    if (min_base_quality == 0) flags = (c == 4) ? 3u : 2u;     // undo the 'A', maybe count N
-                    else if (c == 4 && pass) flags = 1u;                       // masked out already; count N
-                    if (flags) {
-                        if (ne < exc_cap && exc_read_out && exc_pos_out) {
-                            exc_read_out[ne] = i;
-                            exc_pos_out[ne] = (uint32_t)((j0 + j) << 2) | flags;
-                        }
-                        ne++;
+        w += (len + 31) / 32;
+    }
+    if (w > 0xFFFFFFFFull) return BC_ERR_ARG;
+    seq_woff_out[n_reads] = (uint32_t)w;
+
+    const uint64_t grain = 2048;
+    const uint64_t chunks = ((uint64_t)n_reads + grain - 1) / grain;
+    std::vector<std::vector<uint32_t>> exc(chunks);              // per chunk: (read, pos << 2 | flags) pairs, in order
+    std::atomic<int> overrun(0);
+    const int threads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    bcbam::parallel_for(threads, n_reads, grain, [&](uint64_t a, uint64_t e) {
+        std::vector<uint32_t> &ex = exc[a / grain];
+        for (uint64_t i = a; i < e; i++) {
+            const uint64_t s0 = seq_off[i], len = seq_off[i + 1] - s0;
+            if (cigar && cigar_off) {      // count.cpp:56,58 index quals/read unchecked: reject what would be UB there
+                uint64_t rp = 0;
+                for (uint32_t c = cigar_off[i]; c < cigar_off[i + 1]; c++) {
+                    const uint32_t op = cigar[c] & 0xFu, l = cigar[c] >> 4;
+                    if (op == 0 || op == 7 || op == 8) {
+                        if (l && rp + l > len) overrun = 1;
+                        rp += l;
+                    } else if (op == 1) {
+                        rp += l;
                     }
                 }
             }
-            if (planes_out) planes_out[w] = (uint64_t)lo | ((uint64_t)hi << 32);
-            if (okmask_out) okmask_out[w] = ok;
+            uint64_t wi = seq_woff_out[i];
+            for (uint64_t j0 = 0; j0 < len; j0 += 32, wi++) {
+                const uint32_t m = (uint32_t)std::min<uint64_t>(32, len - j0);
+                uint32_t lo = 0, hi = 0, ok = 0;
+                const uint8_t *sp = seq + s0 + j0;
+                const uint8_t *qp = qual ? qual + s0 + j0 : nullptr;
+                for (uint32_t j = 0; j < m; j++) {
+                    const uint8_t c = cls[sp[j]];
+                    const bool pass = !qp || qp[j] >= min_base_quality;
+                    if (c < 4) {
+                        lo |= (uint32_t)(c & 1u) << j;
+                        hi |= (uint32_t)(c >> 1) << j;
+                        ok |= (uint32_t)pass << j;
+                    } else {
+                        uint32_t flags = 0;
+                        if (min_base_quality == 0) flags = (c == 4) ? 3u : 2u;     // undo the 'A', maybe count N
+                        else if (c == 4 && pass) flags = 1u;                       // masked out already; count N
+                        if (flags) {
+                            ex.push_back((uint32_t)i);
+                            ex.push_back((uint32_t)((j0 + j) << 2) | flags);
+                        }
+                    }
+                }
+                if (planes_out) planes_out[wi] = (uint64_t)lo | ((uint64_t)hi << 32);
+                if (okmask_out) okmask_out[wi] = ok;
+            }
         }
-        if (len >= (1ull << 30)) return BC_ERR_ARG;
+    });
+    uint64_t ne = 0;
+    for (const auto &ex : exc) {
+        for (size_t k = 0; k + 1 < ex.size(); k += 2, ne++) {
+            if (ne < exc_cap && exc_read_out && exc_pos_out) {
+                exc_read_out[ne] = ex[k];
+                exc_pos_out[ne] = ex[k + 1];
+            }
+        }
     }
-    if (w > 0xFFFFFFFFull || ne > 0xFFFFFFFFull) return BC_ERR_ARG;
-    seq_woff_out[n_reads] = (uint32_t)w;
+    if (ne > 0xFFFFFFFFull) return BC_ERR_ARG;
     *n_exc = (uint32_t)ne;
-    return status;
+    return overrun ? BC_ERR_READ_OVERRUN : BC_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ native BAM decode (bam_decode.h)
+static thread_local std::string g_bam_err;
+
+extern "C" {
+
+int bc_bam_open(const char *path, int threads, bc_bam **out)
+{
+    if (!path || !out) return BC_ERR_ARG;
+    *out = nullptr;
+    g_bam_err.clear();
+    const int rc = bc_bam_open_impl(path, threads, out, g_bam_err);
+    return rc == 0 ? BC_OK : BC_ERR_ARG;
+}
+
+const char *bc_bam_last_error(void) { return g_bam_err.c_str(); }
+
+void bc_bam_close(bc_bam *b) { delete b; }
+
+uint64_t bc_bam_num_records(const bc_bam *b) { return b ? b->rec_off.size() - 1 : 0; }
+
+uint32_t bc_bam_num_refs(const bc_bam *b) { return b ? (uint32_t)b->ref_names.size() : 0; }
+
+const char *bc_bam_ref_name(const bc_bam *b, uint32_t i) { return (b && i < b->ref_names.size()) ? b->ref_names[i].c_str() : nullptr; }
+
+uint32_t bc_bam_ref_len(const bc_bam *b, uint32_t i) { return (b && i < b->ref_lens.size()) ? b->ref_lens[i] : 0; }
+
+int bc_bam_core(const bc_bam *b, int32_t *ref_id, int32_t *pos, uint8_t *mapq, uint16_t *flag)
+{
+    if (!b) return BC_ERR_ARG;
+    bc_bam_core_impl(b, ref_id, pos, mapq, flag);
+    return BC_OK;
+}
+
+int bc_bam_select_sizes(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                        uint64_t *n_reads, uint64_t *n_cigar, uint64_t *n_bases)
+{
+    if (!b || !n_reads || !n_cigar || !n_bases || rec_a > rec_b || rec_b > b->rec_off.size() - 1) return BC_ERR_ARG;
+    bc_bam_select_sizes_impl(b, rec_a, rec_b, ref_id, min_mapq, n_reads, n_cigar, n_bases);
+    return BC_OK;
+}
+
+int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                       uint32_t *starts, uint32_t *cigar, uint64_t *cigar_off, uint8_t *seq, uint8_t *qual,
+                       uint64_t *seq_off)
+{
+    if (!b || !cigar_off || !seq_off || rec_a > rec_b || rec_b > b->rec_off.size() - 1) return BC_ERR_ARG;
+    bc_bam_select_fill_impl(b, rec_a, rec_b, ref_id, min_mapq, starts, cigar, cigar_off, seq, qual, seq_off);
+    return BC_OK;
 }
 
 }  // extern "C"

@@ -83,6 +83,46 @@ def load_records(bam) -> Records:
     return rec
 
 
+def _decoder_choice() -> str:
+    """BASECOUNT_B200_DECODER = native (default) | pysam | python.  `native` is the C-ABI library's
+    block-parallel decoder (csrc/bam_decode.h); `pysam` reads through a real pysam exactly as the
+    reference does (main.py:95-100,127) when one is installed; `python` is the numpy decoder."""
+    import os
+    return os.environ.get("BASECOUNT_B200_DECODER", "native").lower()
+
+
+class _RecordSource:
+    """What count_alignments needs from an alignment file, over Records or the native decoder."""
+
+    def __init__(self, bam):
+        self.native = None
+        self.rec = None
+        if not isinstance(bam, Records) and _decoder_choice() == "native":
+            from . import bamio
+            self.native = bamio.NativeBam(bam)
+            self.ref_names, self.ref_lengths, self.n = self.native.ref_names, self.native.ref_lengths, self.native.n
+            self.ref_id, _, self.mapq, self.flag = self.native.core()
+        else:
+            if isinstance(bam, Records) or _decoder_choice() == "pysam":
+                self.rec = load_records(bam)
+            else:
+                from . import bamio
+                self.rec = bamio.read_bam(bam)
+            r = self.rec
+            self.ref_names, self.ref_lengths, self.n = r.ref_names, r.ref_lengths, r.n
+            self.ref_id, self.mapq, self.flag = r.ref_id, r.mapq, r.flag
+
+    def select(self, a, b, rid, min_mapping_quality):
+        if self.native is not None:
+            return self.native.select(rid, min_mapping_quality, a, b)
+        part = _slice_records(self.rec, a, b) if (a, b) != (0, self.rec.n) else self.rec
+        return select_reads(part, rid, min_mapping_quality)
+
+    def close(self):
+        if self.native is not None:
+            self.native.close()
+
+
 def _slice_records(rec: Records, a: int, b: int) -> Records:
     c0, c1 = int(rec.cigar_off[a]), int(rec.cigar_off[b])
     s0, s1 = int(rec.seq_off[a]), int(rec.seq_off[b])
@@ -129,7 +169,7 @@ class Pileup:
 def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quality=0, chunk_size=1000000,
                      show_n_bases=False, engine=None) -> Pileup:
     """BAM -> device count matrices (the numeric part of get_basecounts, main.py:119-189)."""
-    rec = load_records(bam)
+    rec = _RecordSource(bam)
     refs = get_references(rec.ref_names, references)
     ids = [rec.ref_names.index(r) for r in refs]
     lengths = [int(rec.ref_lengths[i]) for i in ids]
@@ -150,12 +190,12 @@ def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quali
         for a, b in zip(cuts[:-1], cuts[1:]):
             if b <= a:
                 continue
-            part = _slice_records(rec, a, b) if (a, b) != (0, rec.n) else rec
-            batches = [select_reads(part, rid, min_mapping_quality) for rid in ids]
+            batches = [rec.select(a, b, rid, min_mapping_quality) for rid in ids]
             for j, bt in enumerate(batches):
                 num_reads[j] += bt.n
             eng.push(pack_batches(batches, min_base_quality))
             eng.sync()
+    rec.close()
     return Pileup(eng, refs, lengths, num_reads, show_n_bases)
 
 

@@ -261,6 +261,53 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- BAM file -> summary
+def bam_end_to_end(eng, with_reference):
+    """wall clock from a BAM path to the --summarise numbers of one config-1 sample (124,000
+    reads x 400 bp) through the product's own API: native block-parallel BGZF/BAM decode, filter + soft-clip
+    trimming, 2-bit packing, H2D, K1, K2/K3, D2H.  Beside it (optional) the reference's path on one host
+    core: alignment decode by the in-repo numpy reader (pysam is not installable in this image), Python
+    lists as pysam would hand them over, the compiled count.cpp bcount and the get_stats/summarise port."""
+    from basecount_b200 import bamio, synth
+    from basecount_b200.main import count_alignments
+    from basecount_b200.records import select_reads
+    path = "/tmp/bc_bench_cfg1_seed100.bam"
+    if not os.path.exists(path):
+        bamio.write_bam(path + ".tmp", synth.amplicon_sample(seed=100))
+        os.replace(path + ".tmp", path)
+    count_alignments(path, engine=eng)                     # warm-up: page cache, allocations
+    eng.summary(False)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        pile = count_alignments(path, engine=eng)
+        nz, cs, es = eng.summary(False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    b = select_reads(bamio.read_bam(path), 0, 0)
+    bases = b.aligned_bases()
+    out = {"seconds": best, "aligned_bases": bases, "reads": int(pile.num_reads[0]), "value": bases / best, "unit": UNIT,
+           "decoder": "native (csrc/bam_decode.h: block-parallel inflate + thread-parallel select), best of 3",
+           "bam_mb": os.path.getsize(path) / 1e6}
+    if with_reference:
+        from oracle import bcount as obc
+        from oracle import stats as ost
+        use_ref = obc.load_ref_bcount() is not None
+        t0 = time.perf_counter()
+        rb = select_reads(bamio.read_bam(path), 0, 0)
+        lists = rb.to_lists()
+        t1 = time.perf_counter()
+        counts = obc.load_ref_bcount()(synth.SARS2_LEN, 0, *lists) if use_ref else obc.bcount_flat(synth.SARS2_LEN, 0, rb).tolist()
+        cov, ent, _ = ost.per_position_vectors(counts)
+        ost.summary(cov, ent, synth.SARS2_LEN)
+        t2 = time.perf_counter()
+        out["reference"] = {"seconds": t2 - t0, "decode_seconds": t1 - t0, "count_and_stats_seconds": t2 - t1, "cores": 1,
+                            "value": bases / (t2 - t0), "unit": UNIT,
+                            "decoder": "in-repo numpy BAM reader standing in for pysam (absent in this image)",
+                            "kind": "reference" if use_ref else "port"}
+    return out
+
+
 # ----------------------------------------------------------------------------- config 5 over N GPUs
 def run_region_sharded(args, local_reads, ref_len, label, rank, world, local, barrier, max_over_ranks, sum_over_ranks):
     """One reference cut into `world` regions (strong scaling).  A step = zero the accumulators, count
@@ -537,6 +584,11 @@ def main():
         line["cpu_baseline"] = cpu_baseline(sets[0], ref_lens[0])
     elif rank == 0:
         line["cpu_baseline"] = None
+    if rank == 0 and world == 1 and args.workload == "cfg2x12":
+        for r in resident:
+            r.free()
+        resident = []
+        line["bam_e2e"] = bam_end_to_end(eng, not args.no_cpu_baseline)
     if rank == 0:
         print(json.dumps(line), flush=True)
     for r in resident:

@@ -183,6 +183,33 @@ uint64_t bc_kernel_launches(bc_handle *h);
  * per-base atomics.  Both are CUDA; there is no host path. */
 int bc_set_count_variant(bc_handle *h, int variant);
 
+/* ---- native BAM decode (host code) -------------------------------------------
+ * Replaces what the reference does per read through pysam: open (basecount/main.py:97-99),
+ * fetch(until_eof=True) (main.py:127), the read filter `not is_unmapped and mapping_quality >=
+ * min_mapping_quality` (main.py:165) and the four per-read attributes (main.py:166-173:
+ * reference_start, cigartuples, query_alignment_sequence, query_alignment_qualities -- soft clips
+ * trimmed).  The file is inflated block-parallel and indexed once; a selection is copied into
+ * caller-owned flat arrays (the inputs of bc_pack_reads) by a pool of threads. */
+typedef struct bc_bam bc_bam;
+/* threads <= 0: one per host core (at most 32).  Errors: bc_bam_last_error() (thread-local text). */
+int bc_bam_open(const char *path, int threads, bc_bam **out);
+const char *bc_bam_last_error(void);
+void bc_bam_close(bc_bam *b);
+uint64_t bc_bam_num_records(const bc_bam *b);
+uint32_t bc_bam_num_refs(const bc_bam *b);
+const char *bc_bam_ref_name(const bc_bam *b, uint32_t i);
+uint32_t bc_bam_ref_len(const bc_bam *b, uint32_t i);
+/* refID, pos, MAPQ and FLAG of every record in file order (any pointer may be NULL). */
+int bc_bam_core(const bc_bam *b, int32_t *ref_id, int32_t *pos, uint8_t *mapq, uint16_t *flag);
+/* Selection = records [rec_a, rec_b) with refID == ref_id, FLAG & 4 == 0 and MAPQ >= min_mapq.
+ * Sizes first, then fill: starts[n], cigar[n_cigar] (BAM-native len << 4 | op), cigar_off[n + 1],
+ * seq[n_bases] (ASCII, soft clips trimmed), qual[n_bases] (phred bytes), seq_off[n + 1]. */
+int bc_bam_select_sizes(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                        uint64_t *n_reads, uint64_t *n_cigar, uint64_t *n_bases);
+int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                       uint32_t *starts, uint32_t *cigar, uint64_t *cigar_off, uint8_t *seq, uint8_t *qual,
+                       uint64_t *seq_off);
+
 #ifdef __cplusplus
 }
 #endif
