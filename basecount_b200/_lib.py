@@ -72,6 +72,12 @@ _SIGNATURES = {
     "bc_count_kernel_ms_history": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
     "bc_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
     "bc_set_count_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    # exact native TSV rows (host code)
+    "bc_format_tsv": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]),
+    "bc_free_text": (None, [ctypes.c_void_p]),
     # native BAM decode (host code in the same library)
     "bc_bam_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "bc_bam_last_error": (ctypes.c_char_p, []),

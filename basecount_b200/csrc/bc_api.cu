@@ -11,6 +11,7 @@
 #include "k2_stats.cuh"
 #include "k3_reduce.cuh"
 #include "bam_decode.h"
+#include "tsv_format.h"
 
 #include <algorithm>
 #include <atomic>
@@ -1082,5 +1083,27 @@ int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t 
     bc_bam_select_fill_impl(b, rec_a, rec_b, ref_id, min_mapq, starts, cigar, cigar_off, seq, qual, seq_off);
     return BC_OK;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ exact TSV rows (tsv_format.h)
+extern "C" {
+
+int bc_format_tsv(const char *ref_name, uint64_t n_pos, uint64_t first_pos, int k, int long_format, int decimal_places,
+                  const int64_t *counts, const int64_t *coverage, const double *pc, uint64_t pc_stride,
+                  const double *entropy, const double *secondary, const uint8_t *flags, int threads, char **text,
+                  uint64_t *len)
+{
+    if (!ref_name || !text || !len || (n_pos && (!counts || !coverage || !pc || !entropy || !secondary || !flags)))
+        return BC_ERR_ARG;
+    *text = nullptr;
+    *len = 0;
+    return bc_format_tsv_impl(ref_name, n_pos, first_pos, k, long_format, decimal_places, counts, coverage, pc, pc_stride,
+                              entropy, secondary, flags, threads, text, len) == 0
+               ? BC_OK
+               : BC_ERR_ARG;
+}
+
+void bc_free_text(char *text) { std::free(text); }
 
 }  // extern "C"

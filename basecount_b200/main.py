@@ -227,6 +227,34 @@ def build_rows(ref, counts, st, show_n_bases=False, long_format=False):
     return rows
 
 
+def format_rows_text(ref, counts, st, show_n_bases=False, long_format=False, decimal_places=3, first_pos=1,
+                     threads=0):
+    """The TSV lines of build_rows(...) as the reference prints them (main.py:456-466), produced by the
+    native emitter (csrc/tsv_format.h).  Returns None when the request is outside its exactness
+    envelope (decimal_places not in 0..4, non-finite or huge values): callers then format in Python."""
+    import ctypes
+    from . import _lib
+    k = 6 if show_n_bases else 5
+    L = int(counts.shape[0])
+    cnt = np.ascontiguousarray(counts, dtype=np.int64)
+    cov = np.ascontiguousarray(st["coverage"], dtype=np.int64)
+    pc = np.ascontiguousarray(st["pc"], dtype=np.float64)
+    ent = np.ascontiguousarray(st["entropy"], dtype=np.float64)
+    sec = np.ascontiguousarray(st["secondary"], dtype=np.float64)
+    flg = np.ascontiguousarray(st["flags"], dtype=np.uint8)
+    text, n = ctypes.c_void_p(), ctypes.c_uint64()
+    rc = _lib.lib().bc_format_tsv(str(ref).encode(), L, int(first_pos), k, int(bool(long_format)), int(decimal_places),
+                                  _lib.ptr(cnt), _lib.ptr(cov), _lib.ptr(pc), int(pc.shape[1]) if pc.ndim == 2 else L,
+                                  _lib.ptr(ent), _lib.ptr(sec), _lib.ptr(flg), int(threads), ctypes.byref(text),
+                                  ctypes.byref(n))
+    if rc != 0 or not text.value:
+        return None
+    try:
+        return ctypes.string_at(text.value, n.value).decode("ascii")
+    finally:
+        _lib.lib().bc_free_text(text)
+
+
 def get_basecounts(bam, references=None, min_base_quality=0, min_mapping_quality=0, chunk_size=1000000,
                    show_n_bases=False, long_format=False):
     """Same contract as the reference: {ref: {"rows": [...], "num_reads": int}} (main.py:192-205)."""
@@ -274,6 +302,18 @@ class BaseCount:
             self._data = {ref: {"rows": build_rows(ref, p.counts(i), p.stats(i), self._show_n, self._long),
                                 "num_reads": p.num_reads[i]} for i, ref in enumerate(self.references)}
         return self._data
+
+    def rows_text(self, decimal_places=3):
+        """Per reference, the TSV lines of rows() as `run` prints them, from the native emitter; None if
+        the request is outside its exactness envelope (then format rows() in Python)."""
+        p = self._pile
+        out = []
+        for i, ref in enumerate(self.references):
+            t = format_rows_text(ref, p.counts(i), p.stats(i), self._show_n, self._long, decimal_places)
+            if t is None:
+                return None
+            out.append(t)
+        return out
 
     def _index(self, reference):
         if reference not in self.reference_lengths:
@@ -387,8 +427,12 @@ def run(argv=None):
 
     if (not args.summarise) and (bed is None):
         out = ["\t".join(bc.columns)]
-        for row in bc.rows():
-            out.append("\t".join([x if isinstance(x, str) else str(round(x, decimal_places)) for x in row]))
+        texts = bc.rows_text(decimal_places)            # native emitter, byte-identical to the loop below
+        if texts is not None:
+            out += [t for t in texts if t]
+        else:
+            for row in bc.rows():
+                out.append("\t".join([x if isinstance(x, str) else str(round(x, decimal_places)) for x in row]))
         print("\n".join(out))
         return
 

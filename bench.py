@@ -474,16 +474,30 @@ def main():
 
     outs = [pinned_out() for _ in range(max(args.steps, args.warmup, 1))]
 
+    tiles = None
+    if args.workload == "cfg3":
+        # BASELINE configs[2] is --summarise-with-bed: the 98-amplicon scheme's windows go through K3 every step
+        from basecount_b200 import synth as _synth
+        from basecount_b200.scheme import load_scheme
+        bed = f"/tmp/bc_bench_artic_like_{rank}.bed"
+        _synth.artic_like_bed(bed)
+        sch = load_scheme(bed)
+        tiles = ([t[2]["inside_start"] for t in sch], [t[2]["inside_end"] for t in sch])
+
     def step_resident(i, out):
         """Queue one step; results land in the pinned `out` arrays (valid after eng.sync())."""
         eng.reset()
         eng.push(resident[i % len(resident)])
         eng.summary_async(out, False)             # K2 + K3, D2H of the per-sample scalars
+        if tiles is not None:
+            eng.amplicons(0, tiles[0], tiles[1])  # K2 rows + K3 segmented mean / median (synchronous)
 
     def step_e2e(i, out):
         eng.reset()
         eng.push(packed[i % len(packed)])         # pinned host SoA -> H2D -> K1
         eng.summary_async(out, False)
+        if tiles is not None:
+            eng.amplicons(0, tiles[0], tiles[1])
 
     # ---- correctness guard: the timed configuration must produce the oracle's summary
     # (size-independent property: the synthetic reads hold only A,C,G,T,N, so every aligned base

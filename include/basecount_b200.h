@@ -210,6 +210,21 @@ int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t 
                        uint32_t *starts, uint32_t *cigar, uint64_t *cigar_off, uint8_t *seq, uint8_t *qual,
                        uint64_t *seq_off);
 
+/* ---- exact native TSV rows (host code) --------------------------------------
+ * Replaces the row loop of basecount/main.py:456-466: one line per position (wide) or per
+ * position and base (long), cells joined by tabs, each cell `str(round(x, decimal_places))` --
+ * ints stay ints (incl. the zero-coverage sentinels -1 / 1 / 1, from `flags` as in bc_stats),
+ * floats are rounded on their exact binary value, ties to even, and printed as their shortest
+ * repr.  Exact for 0 <= decimal_places <= 4 and |x| < 1e11; returns BC_ERR_ARG otherwise (callers
+ * fall back to Python's own formatting).  counts: n_pos x 6 int64 row-major; pc: k planes of
+ * pc_stride doubles; first_pos: 1-based position of row 0.  *text is malloc'ed (rows joined by
+ * '\n', no trailing newline, NUL-terminated); release it with bc_free_text. */
+int bc_format_tsv(const char *ref_name, uint64_t n_pos, uint64_t first_pos, int k, int long_format, int decimal_places,
+                  const int64_t *counts, const int64_t *coverage, const double *pc, uint64_t pc_stride,
+                  const double *entropy, const double *secondary, const uint8_t *flags, int threads, char **text,
+                  uint64_t *len);
+void bc_free_text(char *text);
+
 #ifdef __cplusplus
 }
 #endif
