@@ -42,17 +42,54 @@ inline char *put_int(char *p, long long v)
 }
 
 // str(round(x, dp)) for a Python float, 0 <= dp <= 4, |x| < 1e11, finite.
+// A double is m * 2^e exactly, so x * 10^dp = m * 10^dp / 2^-e is an exact 128-bit integer division
+// by a power of two: quotient and remainder give the correctly rounded (ties-to-even) integer
+// q = round(x * 10^dp) with no floating-point step at all.
 inline char *put_float(char *p, double x, int dp)
 {
-    const int n = std::snprintf(p, 40, "%.*f", dp, x);
-    char *e = p + n;
-    if (dp == 0) {
-        *e++ = '.';
-        *e++ = '0';
-        return e;
+    static const uint64_t kPow10[5] = {1ull, 10ull, 100ull, 1000ull, 10000ull};
+    uint64_t bits;
+    std::memcpy(&bits, &x, 8);
+    if (bits >> 63) *p++ = '-';
+    const int be = (int)((bits >> 52) & 0x7FF);
+    uint64_t m = bits & ((1ull << 52) - 1);
+    int e;                                                    // x = m * 2^e
+    if (be == 0) {
+        e = -1074;
+    } else {
+        m |= 1ull << 52;
+        e = be - 1075;
     }
-    while (e[-1] == '0' && e[-2] != '.') e--;
-    return e;
+    unsigned __int128 q;
+    if (e >= 0) {
+        q = ((unsigned __int128)m << e) * kPow10[dp];         // |x| < 1e11 < 2^37: fits easily
+    } else {
+        const unsigned __int128 num = (unsigned __int128)m * kPow10[dp];     // < 2^67
+        const int s = -e;
+        if (s >= 100) {
+            q = 0;                                            // |x| < 2^-46 * ... far below half a unit
+        } else {
+            q = num >> s;
+            const unsigned __int128 rem = num - (q << s), half = (unsigned __int128)1 << (s - 1);
+            if (rem > half || (rem == half && (q & 1))) q++;
+        }
+    }
+    uint64_t ip = (uint64_t)(q / kPow10[dp]), fp = (uint64_t)(q % kPow10[dp]);
+    p = put_int(p, (long long)ip);
+    *p++ = '.';
+    if (dp == 0 || fp == 0) {
+        *p++ = '0';
+        return p;
+    }
+    char d[4];
+    for (int i = dp - 1; i >= 0; i--) {
+        d[i] = (char)('0' + fp % 10);
+        fp /= 10;
+    }
+    int n = dp;
+    while (n > 1 && d[n - 1] == '0') n--;
+    for (int i = 0; i < n; i++) *p++ = d[i];
+    return p;
 }
 
 }  // namespace bctsv
