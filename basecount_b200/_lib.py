@@ -13,7 +13,8 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbasecount_b200.so")
+# BASECOUNT_B200_LIB: another build of the same library (kernel A/B experiments); still no fallback
+LIB_PATH = os.environ.get("BASECOUNT_B200_LIB") or os.path.join(_HERE, "csrc", "libbasecount_b200.so")
 
 BC_OK, BC_ERR_ARG, BC_ERR_INDEX, BC_ERR_CUDA, BC_ERR_STATE, BC_ERR_READ_OVERRUN = range(6)
 
@@ -54,6 +55,8 @@ _SIGNATURES = {
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bc_summary": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bc_summary_min_coverage": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int64,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bc_summary_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bc_amplicons": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_double, ctypes.c_double,

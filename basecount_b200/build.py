@@ -37,19 +37,22 @@ def needs_build() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """`out` / `defines` build an experimental variant next to the product library (see BASECOUNT_B200_LIB)."""
+    if out == OUT and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES + ["-lz"]
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES + ["-lz"]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if verbose:
         sys.stderr.write(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    _out = next((a[6:] for a in sys.argv[1:] if a.startswith("--out=")), OUT)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out, defines=_defs))

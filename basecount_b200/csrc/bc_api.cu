@@ -36,7 +36,7 @@ struct Staging {                 // device copies of one host batch
     DevBuf ref_read_off, starts, cigar_off, cigar, seq_woff, planes, okmask, exc_read, exc_pos, chunks;
     Chunk *h_chunks = nullptr;   // pinned
     size_t h_chunks_cap = 0;
-    cudaEvent_t copied = nullptr, done = nullptr;
+    cudaEvent_t copied = nullptr, done = nullptr, checked = nullptr;   // checked: the overflow check (side stream) is over
     bool used = false;
 };
 
@@ -55,7 +55,7 @@ struct bc_handle {
     int device = 0;
     int sm_count = 148;
     cudaStream_t copy = nullptr, compute = nullptr, side = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, counted = nullptr, checked = nullptr;
     std::string err;
 
     uint32_t n_refs = 0;
@@ -75,11 +75,12 @@ struct bc_handle {
     DevBuf scratch_cov, scratch_pc, scratch_ent, scratch_sec, scratch_flags, scratch_i64, scratch_misc;
     SummaryPartial *d_partials = nullptr;
     size_t partials_cap = 0;
-    // asynchronous summaries: k2_summary_final writes into a pinned host block (zero-copy), the
+    // asynchronous summaries: k2_summary writes into a pinned host block (zero-copy), the
     // values are handed to the caller's arrays at the next synchronisation
     struct PendingSummary { char *block; uint32_t n; int64_t *nonzero; int64_t *cov_sum; double *entropy_sum; };
     std::vector<PendingSummary> pending;
     std::vector<std::pair<char *, size_t>> free_blocks;      // pinned blocks to reuse (ptr, bytes)
+    double *d_log2_tab = nullptr;         // log2 of small integers for the summarise reductions (k2_stats.cuh)
     uint32_t *d_part_off = nullptr;       // first partial of every slot (see summary_blocks)
     uint32_t part_off_refs = 0;           // 0 = stale (slot lengths changed)
     uint32_t summary_max_blocks = 1;
@@ -165,7 +166,8 @@ static void release_staging(Staging &s)
     s.h_chunks_cap = 0;
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.done) cudaEventDestroy(s.done);
-    s.copied = s.done = nullptr;
+    if (s.checked) cudaEventDestroy(s.checked);
+    s.copied = s.done = s.checked = nullptr;
 }
 
 extern "C" {
@@ -210,6 +212,8 @@ int bc_create(int device, bc_handle **out)
     if ((e = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
     if ((e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&h->counted, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&h->checked, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     for (cudaEvent_t *ev : {&h->t0, &h->t1})
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail(e, "event");
     for (int i = 0; i < bc_handle::kHist; i++) {
@@ -219,9 +223,13 @@ int bc_create(int device, bc_handle **out)
     for (Staging &s : h->stage) {
         if ((e = cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
         if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+        if ((e = cudaEventCreateWithFlags(&s.checked, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     }
     if ((e = cudaMalloc(&h->d_status, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(h->d_status, 0, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMalloc(&h->d_log2_tab, kLog2Tab * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc");
+    k_fill_log2<<<(kLog2Tab + 255) / 256, 256, 0, h->compute>>>(h->d_log2_tab);
+    if ((e = cudaStreamSynchronize(h->compute)) != cudaSuccess) return bail(e, "k_fill_log2");
     if ((e = cudaHostAlloc((void **)&h->h_status, kStatWords * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail(e, "cudaHostAlloc");
     *out = h;
@@ -252,6 +260,7 @@ void bc_destroy(bc_handle *h)
     if (h->d_col_base) cudaFree(h->d_col_base);
     if (h->d_ref_len) cudaFree(h->d_ref_len);
     if (h->d_status) cudaFree(h->d_status);
+    if (h->d_log2_tab) cudaFree(h->d_log2_tab);
     if (h->h_status) cudaFreeHost(h->h_status);
     for (cudaEvent_t ev : {h->t0, h->t1})
         if (ev) cudaEventDestroy(ev);
@@ -261,6 +270,8 @@ void bc_destroy(bc_handle *h)
     }
     if (h->fork) cudaEventDestroy(h->fork);
     if (h->join) cudaEventDestroy(h->join);
+    if (h->counted) cudaEventDestroy(h->counted);
+    if (h->checked) cudaEventDestroy(h->checked);
     if (h->copy) cudaStreamDestroy(h->copy);
     if (h->compute) cudaStreamDestroy(h->compute);
     if (h->side) cudaStreamDestroy(h->side);
@@ -466,7 +477,9 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     cv.status = h->d_status;
 
     // The sparse corrections only add to planes A and N with atomics, so they commute with K1:
-    // run them on a forked stream, concurrently with the counting kernel.
+    // run them on a forked stream, concurrently with the counting kernel.  The exact overflow
+    // check follows them there once K1 is done: it only writes status words (read in bc_sync),
+    // so the statistics kernels on the compute stream need not wait for it.
     if (v.n_exc) {
         CU(h, cudaEventRecord(h->fork, h->compute));
         CU(h, cudaStreamWaitEvent(h->side, h->fork, 0));
@@ -503,9 +516,12 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     CU(h, cudaEventRecord(h->k1[ki], h->compute));
     h->k_count++;
     h->launches++;
-    if (v.n_exc) CU(h, cudaStreamWaitEvent(h->compute, h->join, 0));
-    k1_check_overflow<<<std::min<unsigned>((v.n_reads + 255) / 256, (unsigned)h->sm_count * 2), 256, 0, h->compute>>>(v, cv);
+    CU(h, cudaEventRecord(h->counted, h->compute));
+    CU(h, cudaStreamWaitEvent(h->side, h->counted, 0));
+    k1_check_overflow<<<std::min<unsigned>((v.n_reads + 255) / 256, (unsigned)h->sm_count * 2), 256, 0, h->side>>>(v, cv);
+    CU(h, cudaEventRecord(h->checked, h->side));
     h->launches++;
+    if (v.n_exc) CU(h, cudaStreamWaitEvent(h->compute, h->join, 0));
     CU(h, cudaGetLastError());
     return BC_OK;
 }
@@ -605,6 +621,7 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
     if (st.used) {
         // the kernels that last read this staging set must be done before it is overwritten
         CU(h, cudaEventSynchronize(st.done));
+        CU(h, cudaEventSynchronize(st.checked));
     }
     BatchView view;
     uint32_t n_chunks, mean_words;
@@ -614,6 +631,7 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
     CU(h, cudaStreamWaitEvent(h->compute, st.copied, 0));
     rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G, mean_words);
     CU(h, cudaEventRecord(st.done, h->compute));
+    CU(h, cudaEventRecord(st.checked, h->side));
     st.used = true;
     return rc;
 }
@@ -623,6 +641,7 @@ int bc_sync(bc_handle *h)
     if (!h) return BC_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->copy));
+    CU(h, cudaStreamSynchronize(h->side));               // the overflow checks have written their status words
     CU(h, cudaMemcpyAsync(h->h_status, h->d_status, kStatWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
     deliver_summaries(h);
@@ -742,7 +761,7 @@ int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, 
 }
 
 static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
-                        double *entropy_sum, bool sync);
+                        double *entropy_sum, bool sync, long long min_cov = -1);
 
 int bc_summary(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
                double *entropy_sum)
@@ -756,8 +775,15 @@ int bc_summary_async(bc_handle *h, int show_n, double norm, double norm2, int64_
     return summary_impl(h, show_n, norm, norm2, nonzero, cov_sum, entropy_sum, false);
 }
 
+int bc_summary_min_coverage(bc_handle *h, int show_n, double norm, int64_t min_coverage, int64_t *selected,
+                            int64_t *cov_sum, double *entropy_sum_selected)
+{
+    return summary_impl(h, show_n, norm, 0.0, selected, cov_sum, entropy_sum_selected, true,
+                        min_coverage < 0 ? 0 : (long long)min_coverage);
+}
+
 static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
-                        double *entropy_sum, bool sync)
+                        double *entropy_sum, bool sync, long long min_cov)
 {
     if (!h || !nonzero || !cov_sum || !entropy_sum) return BC_ERR_ARG;
     if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
@@ -780,7 +806,8 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
         h->d_partials = nullptr;
         h->d_part_off = nullptr;
         CU(h, cudaMalloc(&h->d_partials, need * sizeof(SummaryPartial)));
-        CU(h, cudaMalloc(&h->d_part_off, (size_t)R * sizeof(uint32_t)));
+        CU(h, cudaMalloc(&h->d_part_off, (size_t)R * 2 * sizeof(uint32_t)));       // offsets, then arrival counters
+        CU(h, cudaMemset(h->d_part_off, 0, (size_t)R * 2 * sizeof(uint32_t)));
         CU(h, cudaMemcpy(h->d_part_off, off.data(), (size_t)R * sizeof(uint32_t), cudaMemcpyHostToDevice));
         h->partials_cap = need;
         h->part_off_refs = R;
@@ -792,11 +819,11 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
     long long *d_cs = d_nz + R;
     double *d_es = (double *)(d_cs + R);
     const int K = show_n ? 6 : 5;
-    k2_summary_partials<<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride,
-                                                                               h->d_col_base, h->d_ref_len, K, norm, norm2,
-                                                                               h->d_part_off, h->d_partials);
-    k2_summary_final<<<R, 256, 0, h->compute>>>(h->d_partials, h->d_part_off, h->d_ref_len, d_nz, d_cs, d_es);
-    h->launches += 2;
+    (void)norm2;                                          // --summarise does not need the secondary entropy
+    k2_summary<<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride, h->d_col_base,
+                                                                      h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off, h->d_partials,
+                                                                      h->d_part_off + R, d_nz, d_cs, d_es);
+    h->launches += 1;
     h->pending.push_back({block, R, nonzero, cov_sum, entropy_sum});
     CU(h, cudaGetLastError());
     if (sync) {
@@ -888,6 +915,7 @@ int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len)
     if (!h) return BC_ERR_ARG;
     if (ref >= h->n_refs || new_len > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "bc_truncate: out of range");
     CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->side));               // an overflow check may still read the old length
     h->ref_len[ref] = new_len;
     h->part_off_refs = 0;
     CU(h, cudaMemcpyAsync(h->d_ref_len + ref, &h->ref_len[ref], sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
@@ -906,6 +934,7 @@ int bc_timer_start(bc_handle *h)
 int bc_timer_stop(bc_handle *h, float *ms)
 {
     if (!h || !ms) return BC_ERR_ARG;
+    CU(h, cudaStreamWaitEvent(h->compute, h->checked, 0));   // work forked to the side stream belongs to the timed region
     CU(h, cudaEventRecord(h->t1, h->compute));
     CU(h, cudaEventSynchronize(h->t1));
     CU(h, cudaEventElapsedTime(ms, h->t0, h->t1));

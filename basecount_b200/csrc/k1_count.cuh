@@ -565,7 +565,14 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             }
             fast = !__any_sync(kFull, bad);
             if (fast) {
-                for (uint32_t t = 0; t < sk_n; t++) atomicAdd(ds_plane + sk_pos + t, 1u);     // count.cpp:80-87
+                if (sk_n) {                                          // count.cpp:80-87; short deletions are the rule
+                    uint32_t *const dp = ds_plane + sk_pos;
+                    red_add(dp, 1u);
+                    if (sk_n > 1u) red_add(dp + 1, 1u);
+                    if (sk_n > 2u) red_add(dp + 2, 1u);
+#pragma unroll 1
+                    for (uint32_t t = 3u; t < sk_n; t++) red_add(dp + t, 1u);
+                }
                 cur = cend;                                          // the walker has nothing to do
             } else {
                 nA = 0u;

@@ -41,14 +41,47 @@ __device__ __forceinline__ double neumaier_entropy(const long long *c, int n, lo
     return hi;
 }
 
+// log2 of the integers below kLog2Tab, filled once per handle with the same log2() the exact path calls.
+constexpr int kLog2Tab = 16384;
+__global__ void k_fill_log2(double *__restrict__ tab)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kLog2Tab) tab[i] = i ? log2((double)i) : 0.0;
+}
+
+// The --summarise reductions only need sums of entropies, and K2 is bound by the FP64 pipe, almost all of it
+// log2.  For a minority class (2c <= coverage, so |log2 p| >= 1) log2(c / cov) is taken as tab[c] - tab[cov]:
+// two table loads instead of a ~60-instruction log2, relative error of the term <= ~4e-15 (no cancellation).
+// The majority class (p close to 1, where that difference would cancel) and anything beyond the table keep
+// the exact expression of main.py:11.  Per-position outputs (k2_stats_rows) never use the table.
+__device__ __forceinline__ double neumaier_entropy_tab(const long long *c, int n, long long total,
+                                                       const double *__restrict__ tab)
+{
+    double hi = 0.0, lo = 0.0;
+    const double tot = (double)total;
+    const bool in_tab = total < (long long)kLog2Tab;
+    const double ltot = in_tab ? tab[total] : 0.0;
+    for (int i = 0; i < n; i++) {
+        if (c[i] == 0 || c[i] == total) continue;
+        const double p = (double)c[i] / tot;
+        const double l = (in_tab && 2 * c[i] <= total) ? tab[c[i]] - ltot : log2(p);
+        const double x = -(p * l);
+        const double t = hi + x;
+        if (fabs(hi) >= fabs(x)) lo += (hi - t) + x; else lo += (x - t) + hi;
+        hi = t;
+    }
+    if (lo != 0.0 && isfinite(lo)) return hi + lo;
+    return hi;
+}
+
 // Coverage and entropy only (what the --summarise reductions need, main.py:479-485).
 __device__ __forceinline__ void position_cov_entropy(const long long *c, int K, double norm, long long &cov_out,
-                                                     double &ent_out)
+                                                     double &ent_out, const double *__restrict__ tab)
 {
     long long cov = 0;
     for (int i = 0; i < K; i++) cov += c[i];
     cov_out = cov;
-    ent_out = cov == 0 ? 1.0 : norm * neumaier_entropy(c, K, cov, -1);
+    ent_out = cov == 0 ? 1.0 : norm * neumaier_entropy_tab(c, K, cov, tab);
 }
 
 __device__ __forceinline__ void position_stats(const long long *c, int K, double norm, double norm2, PosStats &o)
@@ -125,13 +158,17 @@ __host__ __device__ inline uint32_t summary_blocks(uint32_t ref_len)
     return b < 1u ? 1u : (b > (uint32_t)kSummaryMaxBlocks ? (uint32_t)kSummaryMaxBlocks : b);
 }
 
-// Fused stats + summarise partials for ALL slots: grid = (max blocks over slots, n_refs); partials of slot r
-// sit at part_off[r] .. part_off[r] + summary_blocks(ref_len[r]).
+// Fused stats + summarise reduction for ALL slots in ONE launch: grid = (max blocks over slots, n_refs);
+// partials of slot r sit at part_off[r] .. part_off[r] + summary_blocks(ref_len[r]).  The CTA of a slot that
+// arrives last (arrive[r], reset for the next launch) sums the slot's partials: every thread its partials in
+// index order, then a fixed-order tree -- the result does not depend on which CTA was last.
+// min_cov < 0: nonzero = positions with coverage != 0, ent_sum over all positions; min_cov >= 0: nonzero =
+// positions with coverage >= min_cov, ent_sum over those (BaseCount.mean_entropy, main.py:342-359).
 __global__ void __launch_bounds__(256)
-k2_summary_partials(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64, uint64_t stride,
-                    const uint32_t *__restrict__ col_base, const uint32_t *__restrict__ ref_len, int K,
-                    double norm, double norm2, const uint32_t *__restrict__ part_off,
-                    SummaryPartial *__restrict__ partials)
+k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64, uint64_t stride,
+           const uint32_t *__restrict__ col_base, const uint32_t *__restrict__ ref_len, int K, double norm,
+           long long min_cov, const double *__restrict__ log2_tab, const uint32_t *__restrict__ part_off, SummaryPartial *partials, uint32_t *arrive,
+           long long *__restrict__ nonzero, long long *__restrict__ cov_sum, double *__restrict__ ent_sum)
 {
     const uint32_t r = blockIdx.y;
     const uint32_t L = ref_len[r];
@@ -145,68 +182,60 @@ k2_summary_partials(const uint32_t *__restrict__ c32, const unsigned long long *
         load_counts(c32, c64, stride, base + pos, K, c);
         long long cov;
         double ent;
-        position_cov_entropy(c, K, norm, cov, ent);
-        nz += (cov != 0);
+        position_cov_entropy(c, K, norm, cov, ent, log2_tab);
+        if (min_cov < 0) {                                 // --summarise (main.py:479-485)
+            nz += (cov != 0);
+            es += ent;
+        } else if (cov >= min_cov) {                       // mean_entropy(min_coverage) (main.py:342-359)
+            nz += 1;
+            es += ent;
+        }
         cs += cov;
-        es += ent;
     }
     __shared__ long long s_nz[256], s_cs[256];
     __shared__ double s_es[256];
-    s_nz[threadIdx.x] = nz;
-    s_cs[threadIdx.x] = cs;
-    s_es[threadIdx.x] = es;
-    __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-        if ((int)threadIdx.x < d) {
-            s_nz[threadIdx.x] += s_nz[threadIdx.x + d];
-            s_cs[threadIdx.x] += s_cs[threadIdx.x + d];
-            s_es[threadIdx.x] += s_es[threadIdx.x + d];
-        }
+    __shared__ uint32_t s_last;
+    auto tree = [&]() {
+        s_nz[threadIdx.x] = nz;
+        s_cs[threadIdx.x] = cs;
+        s_es[threadIdx.x] = es;
         __syncthreads();
-    }
+        for (int d = 128; d > 0; d >>= 1) {
+            if ((int)threadIdx.x < d) {
+                s_nz[threadIdx.x] += s_nz[threadIdx.x + d];
+                s_cs[threadIdx.x] += s_cs[threadIdx.x + d];
+                s_es[threadIdx.x] += s_es[threadIdx.x + d];
+            }
+            __syncthreads();
+        }
+    };
+    tree();
+    SummaryPartial *p = partials + part_off[r];
     if (threadIdx.x == 0) {
-        SummaryPartial p;
-        p.nonzero = s_nz[0];
-        p.cov_sum = s_cs[0];
-        p.ent_sum = s_es[0];
-        partials[(uint64_t)part_off[r] + blockIdx.x] = p;
+        p[blockIdx.x].nonzero = s_nz[0];
+        p[blockIdx.x].cov_sum = s_cs[0];
+        p[blockIdx.x].ent_sum = s_es[0];
+        __threadfence();                                   // the partial is visible before the arrival is
+        s_last = atomicAdd(arrive + r, 1u) == nb - 1u;
     }
-}
-
-// grid = n_refs, block = 256: every thread sums its partials in index order, then a fixed-order tree.
-__global__ void __launch_bounds__(256)
-k2_summary_final(const SummaryPartial *__restrict__ partials, const uint32_t *__restrict__ part_off,
-                 const uint32_t *__restrict__ ref_len, long long *__restrict__ nonzero, long long *__restrict__ cov_sum,
-                 double *__restrict__ ent_sum)
-{
-    __shared__ long long s_nz[256], s_cs[256];
-    __shared__ double s_es[256];
-    const uint32_t r = blockIdx.x;
-    const uint32_t nb = summary_blocks(ref_len[r]);
-    const SummaryPartial *p = partials + part_off[r];
-    long long nz = 0, cs = 0;
-    double es = 0.0;
-    for (uint32_t i = threadIdx.x; i < nb; i += 256u) {
-        nz += p[i].nonzero;
-        cs += p[i].cov_sum;
-        es += p[i].ent_sum;
-    }
-    s_nz[threadIdx.x] = nz;
-    s_cs[threadIdx.x] = cs;
-    s_es[threadIdx.x] = es;
     __syncthreads();
-    for (int d = 128; d > 0; d >>= 1) {
-        if ((int)threadIdx.x < d) {
-            s_nz[threadIdx.x] += s_nz[threadIdx.x + d];
-            s_cs[threadIdx.x] += s_cs[threadIdx.x + d];
-            s_es[threadIdx.x] += s_es[threadIdx.x + d];
-        }
-        __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const volatile SummaryPartial *vp = p;                 // written by other CTAs: no cached copies
+    nz = 0;
+    cs = 0;
+    es = 0.0;
+    for (uint32_t i = threadIdx.x; i < nb; i += 256u) {
+        nz += vp[i].nonzero;
+        cs += vp[i].cov_sum;
+        es += vp[i].ent_sum;
     }
+    tree();
     if (threadIdx.x == 0) {
         nonzero[r] = s_nz[0];
         cov_sum[r] = s_cs[0];
         ent_sum[r] = s_es[0];
+        arrive[r] = 0u;
     }
 }
 

@@ -123,6 +123,18 @@ class Engine:
         _lib.check(self._h, self._L.bc_summary(self._h, int(show_n_bases), n1, n2, _lib.ptr(nz), _lib.ptr(cs), _lib.ptr(es)))
         return nz, cs, es
 
+    def summary_min_coverage(self, min_coverage: int = 0, show_n_bases: bool = False):
+        """Per slot: positions with coverage >= min_coverage, coverage sum over all positions, entropy sum
+        over the selected positions (device reductions behind mean_coverage / mean_entropy)."""
+        r = len(self.ref_lens)
+        n1, _ = norm_factors(show_n_bases)
+        sel = np.empty(r, dtype=np.int64)
+        cs = np.empty(r, dtype=np.int64)
+        es = np.empty(r, dtype=np.float64)
+        _lib.check(self._h, self._L.bc_summary_min_coverage(self._h, int(show_n_bases), n1, int(min_coverage),
+                                                            _lib.ptr(sel), _lib.ptr(cs), _lib.ptr(es)))
+        return sel, cs, es
+
     def summary_async(self, out, show_n_bases: bool = False):
         """Queue the summarise reductions; `out` = (nonzero, cov_sum, ent_sum) pinned arrays
         (see _lib.pinned_empty), valid after sync()."""

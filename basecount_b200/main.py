@@ -338,23 +338,40 @@ class BaseCount:
             return sum(self._pile.num_reads)
         return self._pile.num_reads[self._index(reference)]
 
-    def _vectors(self, reference):
+    def _reduced(self, reference, min_coverage):
+        """Device reductions over the chosen references: (positions with coverage >= min_coverage,
+        coverage sum over all positions, entropy sum over the selected positions, positions)."""
         which = range(len(self.references)) if reference is None else [self._index(reference)]
-        rep = len(BASES[:6 if self._show_n else 5]) if self._long else 1       # long format repeats each position
-        cov = [np.repeat(self._pile.stats(i)["coverage"], rep) for i in which]
-        ent = [np.repeat(self._pile.stats(i)["entropy"], rep) for i in which]
-        return (np.concatenate(cov) if cov else np.zeros(0, np.int64),
-                np.concatenate(ent) if ent else np.zeros(0, np.float64))
+        key = int(min_coverage)
+        if not hasattr(self, "_red"):
+            self._red = {}
+        if key not in self._red:
+            self._red[key] = self._pile.engine.summary_min_coverage(key, self._show_n)
+        sel, cs, es = self._red[key]
+        n_sel = sum(int(sel[i]) for i in which)
+        cov_sum = sum(int(cs[i]) for i in which)
+        ent_sum = np.float64(0.0)
+        for i in which:
+            ent_sum = ent_sum + np.float64(es[i])
+        return n_sel, cov_sum, ent_sum, sum(self._pile.lengths[i] for i in which)
 
     def mean_coverage(self, reference=None):
-        """Mean coverage over all positions (np.mean of the coverage column, main.py:325-340)."""
-        cov, _ = self._vectors(reference)
-        return np.mean(cov)
+        """Mean coverage over all positions (np.mean of the coverage column, main.py:325-340), from the
+        device's integer coverage sum: sums of int64 below 2^53 are exact in np.mean's float64 accumulator,
+        so this is the reference's value bit for bit."""
+        _, cov_sum, _, n = self._reduced(reference, 0)
+        if n == 0:
+            return np.mean(np.zeros(0, np.int64))          # nan + RuntimeWarning, as the reference
+        rep = len(BASES[:6 if self._show_n else 5]) if self._long else 1       # long format repeats each position
+        return np.float64(cov_sum * rep) / (n * rep)
 
     def mean_entropy(self, reference=None, min_coverage=0):
-        """Mean entropy over positions with coverage >= min_coverage (main.py:342-359)."""
-        cov, ent = self._vectors(reference)
-        return np.mean(ent[cov >= min_coverage])
+        """Mean entropy over positions with coverage >= min_coverage (main.py:342-359), reduced on the
+        device (fixed-order tree; agrees with np.mean's pairwise order to ~1e-15 relative)."""
+        n_sel, _, ent_sum, _ = self._reduced(reference, max(int(np.ceil(min_coverage)), 0))
+        if n_sel == 0:
+            return np.mean(np.zeros(0, np.float64))        # nan + RuntimeWarning, as the reference
+        return ent_sum / n_sel
 
     # -- device-side reductions used by the CLI's summarise modes
     def summary(self, reference):

@@ -140,6 +140,12 @@ int bc_summary(bc_handle *h, int show_n, double norm, double norm2,
 int bc_summary_async(bc_handle *h, int show_n, double norm, double norm2,
                      int64_t *nonzero, int64_t *cov_sum, double *entropy_sum);
 
+/* BaseCount.mean_entropy(min_coverage) / mean_coverage (main.py:325-359) served from the device:
+ * per slot the number of positions with coverage >= min_coverage, the sum of their entropies and
+ * the sum of coverage over ALL positions.  Synchronous. */
+int bc_summary_min_coverage(bc_handle *h, int show_n, double norm, int64_t min_coverage,
+                            int64_t *selected, int64_t *cov_sum, double *entropy_sum_selected);
+
 /* --summarise-with-bed amplicon vectors (main.py:519-551) for one slot.
  * Window t covers 0-based positions lo[t]..hi[t] inclusive, clipped to the reference.
  * out[6*n_tiles]: rows mean_cov, median_cov, mean_ent, median_ent, mean_sec, median_sec;
