@@ -178,13 +178,21 @@ class NativeBam:
     index, and thread-parallel selections straight into ReadBatch arrays -- no per-read objects.
     Same results as `select_reads(read_bam(path), ...)` (tests/test_bamio.py)."""
 
-    def __init__(self, path: str, threads: int = 0):
+    def __init__(self, path: str, threads: int = 0, region=None, index: str | None = None):
+        """region = (reference id, beg, end): only the records of that reference STARTING in [beg, end)
+        (0-based, half open) are read, through the BAI index (`index`, default `path + ".bai"`)."""
         import ctypes
         from . import _lib
         self._h = None
         self._L = _lib.lib()
         h = ctypes.c_void_p()
-        if self._L.bc_bam_open(str(path).encode(), int(threads), ctypes.byref(h)) != 0 or not h.value:
+        if region is None:
+            rc = self._L.bc_bam_open(str(path).encode(), int(threads), ctypes.byref(h))
+        else:
+            rid, beg, end = region
+            rc = self._L.bc_bam_open_region(str(path).encode(), str(index or (str(path) + ".bai")).encode(), int(rid),
+                                            int(beg), int(end), int(threads), ctypes.byref(h))
+        if rc != 0 or not h.value:
             msg = self._L.bc_bam_last_error()
             raise ValueError(msg.decode() if msg else "cannot read BAM file")
         self._h = h
@@ -233,6 +241,18 @@ class NativeBam:
         self._L.bc_bam_select_fill(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), _lib.ptr(starts),
                                    _lib.ptr(cigar), _lib.ptr(cigar_off), _lib.ptr(seq), _lib.ptr(qual), _lib.ptr(seq_off))
         return ReadBatch(starts, cigar, cigar_off, seq, qual, seq_off)
+
+
+def write_bai(bam_path: str, bai_path: str | None = None, threads: int = 0) -> str:
+    """Index a coordinate-sorted BAM (what `pysam.index` does for the reference's tests,
+    tests/test_basecount.py:343-344); returns the path of the .bai."""
+    from . import _lib
+    L = _lib.lib()
+    bai_path = bai_path or (str(bam_path) + ".bai")
+    if L.bc_bam_index_build(str(bam_path).encode(), str(bai_path).encode(), int(threads)) != 0:
+        msg = L.bc_bam_last_error()
+        raise ValueError(msg.decode() if msg else "cannot index BAM file")
+    return bai_path
 
 
 # ----------------------------------------------------------------------------- Records -> BAM

@@ -11,6 +11,7 @@
 #include "k2_stats.cuh"
 #include "k3_reduce.cuh"
 #include "bam_decode.h"
+#include "bam_index.h"
 #include "tsv_format.h"
 
 #include <algorithm>
@@ -1075,6 +1076,22 @@ int bc_bam_open(const char *path, int threads, bc_bam **out)
     g_bam_err.clear();
     const int rc = bc_bam_open_impl(path, threads, out, g_bam_err);
     return rc == 0 ? BC_OK : BC_ERR_ARG;
+}
+
+int bc_bam_index_build(const char *bam_path, const char *bai_path, int threads)
+{
+    if (!bam_path || !bai_path) return BC_ERR_ARG;
+    g_bam_err.clear();
+    return bc_bam_index_build_impl(bam_path, bai_path, threads, g_bam_err) == 0 ? BC_OK : BC_ERR_ARG;
+}
+
+int bc_bam_open_region(const char *bam_path, const char *bai_path, int32_t ref_id, int64_t beg, int64_t end, int threads,
+                       bc_bam **out)
+{
+    if (!bam_path || !bai_path || !out) return BC_ERR_ARG;
+    *out = nullptr;
+    g_bam_err.clear();
+    return bc_bam_open_region_impl(bam_path, bai_path, ref_id, beg, end, threads, out, g_bam_err) == 0 ? BC_OK : BC_ERR_ARG;
 }
 
 const char *bc_bam_last_error(void) { return g_bam_err.c_str(); }

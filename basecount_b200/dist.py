@@ -151,6 +151,32 @@ def count_region_sharded(backend, dist, rank, world, batch: ReadBatch, ref_len: 
     return bounds
 
 
+def load_region_reads(bam_path: str, ref_id: int, lo: int, hi: int, min_mapping_quality: int = 0,
+                      index: str | None = None, threads: int = 0) -> ReadBatch:
+    """Kept reads of reference `ref_id` whose start lies in [lo, hi), starts relative to lo, decoded through
+    the BAI index (csrc/bam_index.h): only this region's BGZF blocks are read and inflated, so with one
+    process per GPU the host decode scales with the number of ranks instead of every rank reading the file."""
+    from .bamio import NativeBam
+    nb = NativeBam(bam_path, threads=threads, region=(ref_id, lo, hi), index=index)
+    try:
+        b = nb.select(ref_id, min_mapping_quality)
+    finally:
+        nb.close()
+    return ReadBatch((b.starts.astype(np.int64) - lo).astype(np.uint32), b.cigar, b.cigar_off, b.seq, b.qual, b.seq_off)
+
+
+def count_region_sharded_bam(backend, dist, rank, world, bam_path: str, ref_id: int, ref_len: int,
+                             min_base_quality: int = 0, min_mapping_quality: int = 0, index: str | None = None,
+                             threads: int = 0):
+    """count_region_sharded with every rank fetching its own region of an indexed, coordinate-sorted BAM.
+    Returns (bounds, number of reads this rank counted)."""
+    bounds = region_bounds(ref_len, world)
+    local = load_region_reads(bam_path, ref_id, int(bounds[rank]), int(bounds[rank + 1]), min_mapping_quality, index,
+                              threads)
+    count_region_sharded(backend, dist, rank, world, None, ref_len, min_base_quality, local_reads=local)
+    return bounds, local.n
+
+
 def summary_region_sharded(backend, dist, world, ref_len: int, show_n_bases: bool = False):
     """(pc_reference_coverage, avg_depth, avg_entropy) of the whole reference (main.py:479-485)
     from per-rank K3 partials: all-reduce of {nonzero, coverage sum} (int64) and entropy sum (f64)."""

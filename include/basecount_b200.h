@@ -216,6 +216,17 @@ int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t 
                        uint32_t *starts, uint32_t *cigar, uint64_t *cigar_off, uint8_t *seq, uint8_t *qual,
                        uint64_t *seq_off);
 
+/* ---- index-aware region fetch (host code) -----------------------------------
+ * The region-sharded path (config 5) gives each rank the reads that START in its region of the
+ * reference (the np.linspace split of tests/test_basecount.py:146-150).  bc_bam_index_build writes
+ * the BAI (SAM spec 5.2) of a coordinate-sorted BAM -- the job of `pysam.index`, which the
+ * reference's tests call at tests/test_basecount.py:343-344.  bc_bam_open_region reads and inflates
+ * only the BGZF blocks that hold the records of reference `ref_id` starting in [beg, end) (0-based,
+ * half open) and returns a handle that behaves like bc_bam_open on a file of just those records. */
+int bc_bam_index_build(const char *bam_path, const char *bai_path, int threads);
+int bc_bam_open_region(const char *bam_path, const char *bai_path, int32_t ref_id, int64_t beg, int64_t end,
+                       int threads, bc_bam **out);
+
 /* ---- exact native TSV rows (host code) --------------------------------------
  * Replaces the row loop of basecount/main.py:456-466: one line per position (wide) or per
  * position and base (long), cells joined by tabs, each cell `str(round(x, decimal_places))` --

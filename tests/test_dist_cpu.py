@@ -108,6 +108,44 @@ def test_region_sharding_matches_single_pass(tmp_path, world):
         assert s[2] == pytest.approx(float(avg_ent), rel=1e-12)
 
 
+def _bam_worker(rank, world, port, bam, ref_len, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        be = OracleBackend()
+        bounds, n = bdist.count_region_sharded_bam(be, dist, rank, world, bam, 0, ref_len, min_base_quality=0,
+                                                   min_mapping_quality=30, threads=2)
+        total = torch.tensor([n], dtype=torch.int64)
+        dist.all_reduce(total)
+        np.savez(os.path.join(out_dir, f"b{rank}.npz"), planes=be.planes, lo=bounds[rank], hi=bounds[rank + 1],
+                 total=int(total.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_region_sharding_from_an_indexed_bam(tmp_path, world):
+    """Every rank fetches only its own region through the BAI; the merged counts are
+    the single-pass counts of the whole file under the same MAPQ filter (main.py:165)."""
+    from basecount_b200 import bamio
+    from oracle import bcount as obc
+    ref_len = 50_000                                       # spans four 16 kbp index windows
+    rec = synth.uniform_short_read_sample(seed=9, ref_len=ref_len, n_reads=4000, read_len=150, ref_name="x")
+    bam = str(tmp_path / "x.bam")
+    bamio.write_bam(bam, rec)
+    bamio.write_bai(bam)
+    mp.spawn(_bam_worker, args=(world, _free_port(), bam, ref_len, str(tmp_path)), nprocs=world, join=True)
+    whole = select_reads(rec, 0, 30)
+    want = obc.bcount_flat(ref_len, 0, whole)
+    got = np.zeros_like(want)
+    for r in range(world):
+        z = np.load(tmp_path / f"b{r}.npz")
+        got[int(z["lo"]):int(z["hi"])] = z["planes"].T
+        assert int(z["total"]) == whole.n                  # num_reads: every kept read counted on exactly one rank
+    assert np.array_equal(got, want)
+
+
 def test_sample_sharding_covers_every_sample_once():
     for n, world in ((96, 8), (12, 5), (3, 8)):
         seen = sorted(i for r in range(world) for i in bdist.shard_samples(n, world, r))
