@@ -821,9 +821,14 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
     double *d_es = (double *)(d_cs + R);
     const int K = show_n ? 6 : 5;
     (void)norm2;                                          // --summarise does not need the secondary entropy
-    k2_summary<<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride, h->d_col_base,
-                                                                      h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off, h->d_partials,
-                                                                      h->d_part_off + R, d_nz, d_cs, d_es);
+    if (h->d_counts64)
+        k2_summary<true><<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(
+            h->d_counts, h->d_counts64, h->stride, h->d_col_base, h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off,
+            h->d_partials, h->d_part_off + R, d_nz, d_cs, d_es);
+    else
+        k2_summary<false><<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(
+            h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off,
+            h->d_partials, h->d_part_off + R, d_nz, d_cs, d_es);
     h->launches += 1;
     h->pending.push_back({block, R, nonzero, cov_sum, entropy_sum});
     CU(h, cudaGetLastError());

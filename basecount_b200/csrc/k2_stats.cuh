@@ -49,23 +49,40 @@ __global__ void k_fill_log2(double *__restrict__ tab)
     if (i < kLog2Tab) tab[i] = i ? log2((double)i) : 0.0;
 }
 
-// The --summarise reductions only need sums of entropies, and K2 is bound by the FP64 pipe, almost all of it
-// log2.  For a minority class (2c <= coverage, so |log2 p| >= 1) log2(c / cov) is taken as tab[c] - tab[cov]:
-// two table loads instead of a ~60-instruction log2, relative error of the term <= ~4e-15 (no cancellation).
-// The majority class (p close to 1, where that difference would cancel) and anything beyond the table keep
-// the exact expression of main.py:11.  Per-position outputs (k2_stats_rows) never use the table.
+// Entropy for the --summarise reductions (sums of entropies only; K2 is bound by the FP64 pipe and nearly all
+// of that was log2).  The largest class of a position keeps the exact expression of main.py:11 -- its p is close
+// to 1, where a difference of logs would cancel -- and it is computed ONCE, outside the class loop, so the lanes
+// of a warp call log2 together whatever letter their largest class is.  Every other class has 2c <= coverage
+// (|log2 p| >= 1), and log2(c / cov) is taken as tab[c] - tab[cov]: two table loads, relative error of the
+// term <= ~4e-15.  The terms are still added in class order with the Neumaier compensation of CPython's sum().
+// Coverage beyond the table takes the exact path for every class.  Per-position outputs (k2_stats_rows) never
+// use the table.
 __device__ __forceinline__ double neumaier_entropy_tab(const long long *c, int n, long long total,
                                                        const double *__restrict__ tab)
 {
-    double hi = 0.0, lo = 0.0;
+    if (total >= (long long)kLog2Tab) return neumaier_entropy(c, n, total, -1);
+    int top = 0;
+    long long ctop = c[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++)
+        if (i < n && c[i] > ctop) {
+            ctop = c[i];
+            top = i;
+        }
+    if (ctop == total) return 0.0;                         // one class only: -(1 * log2 1) contributes -0.0
     const double tot = (double)total;
-    const bool in_tab = total < (long long)kLog2Tab;
-    const double ltot = in_tab ? tab[total] : 0.0;
-    for (int i = 0; i < n; i++) {
-        if (c[i] == 0 || c[i] == total) continue;
-        const double p = (double)c[i] / tot;
-        const double l = (in_tab && 2 * c[i] <= total) ? tab[c[i]] - ltot : log2(p);
-        const double x = -(p * l);
+    const double ptop = (double)ctop / tot;
+    const double xtop = -(ptop * log2(ptop));
+    const double ltot = tab[total];
+    double hi = 0.0, lo = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (i >= n || c[i] == 0) continue;
+        double x = xtop;
+        if (i != top) {
+            const double p = (double)c[i] / tot;
+            x = -(p * (tab[c[i]] - ltot));
+        }
         const double t = hi + x;
         if (fabs(hi) >= fabs(x)) lo += (hi - t) + x; else lo += (x - t) + hi;
         hi = t;
@@ -79,7 +96,9 @@ __device__ __forceinline__ void position_cov_entropy(const long long *c, int K, 
                                                      double &ent_out, const double *__restrict__ tab)
 {
     long long cov = 0;
-    for (int i = 0; i < K; i++) cov += c[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+        if (i < K) cov += c[i];
     cov_out = cov;
     ent_out = cov == 0 ? 1.0 : norm * neumaier_entropy_tab(c, K, cov, tab);
 }
@@ -149,26 +168,60 @@ struct SummaryPartial {
     double ent_sum;
 };
 
-// Partials per slot: a fixed function of the slot length (-> deterministic reduction order), one
-// position per thread up to kSummaryMaxBlocks CTAs per slot.
+// Partials per slot: a fixed function of the slot length (-> deterministic reduction order): one CTA per
+// kSummaryPerCta positions (2 per thread), up to kSummaryMaxBlocks CTAs per slot.
 constexpr int kSummaryMaxBlocks = 2048;
+constexpr uint32_t kSummaryPerCta = 512;
 __host__ __device__ inline uint32_t summary_blocks(uint32_t ref_len)
 {
-    const uint32_t b = (ref_len + 255u) / 256u;
+    const uint32_t b = (ref_len + kSummaryPerCta - 1u) / kSummaryPerCta;
     return b < 1u ? 1u : (b > (uint32_t)kSummaryMaxBlocks ? (uint32_t)kSummaryMaxBlocks : b);
+}
+
+// Sum (nz, cs, es) over the CTA in a fixed order: xor-shuffle tree inside each warp, then thread 0 adds the
+// eight warp totals in warp order.  Result valid in thread 0.
+__device__ __forceinline__ void summary_cta_sum(long long &nz, long long &cs, double &es, long long *s_nz, long long *s_cs,
+                                                double *s_es)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        nz += __shfl_xor_sync(0xFFFFFFFFu, nz, d);
+        cs += __shfl_xor_sync(0xFFFFFFFFu, cs, d);
+        es += __shfl_xor_sync(0xFFFFFFFFu, es, d);
+    }
+    const int w = threadIdx.x >> 5;
+    __syncthreads();                                       // earlier readers of the staging arrays are done
+    if ((threadIdx.x & 31) == 0) {
+        s_nz[w] = nz;
+        s_cs[w] = cs;
+        s_es[w] = es;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        nz = s_nz[0];
+        cs = s_cs[0];
+        es = s_es[0];
+        for (int i = 1; i < 8; i++) {
+            nz += s_nz[i];
+            cs += s_cs[i];
+            es += s_es[i];
+        }
+    }
 }
 
 // Fused stats + summarise reduction for ALL slots in ONE launch: grid = (max blocks over slots, n_refs);
 // partials of slot r sit at part_off[r] .. part_off[r] + summary_blocks(ref_len[r]).  The CTA of a slot that
 // arrives last (arrive[r], reset for the next launch) sums the slot's partials: every thread its partials in
-// index order, then a fixed-order tree -- the result does not depend on which CTA was last.
+// index order, then the fixed-order CTA sum -- the result does not depend on which CTA was last.
 // min_cov < 0: nonzero = positions with coverage != 0, ent_sum over all positions; min_cov >= 0: nonzero =
 // positions with coverage >= min_cov, ent_sum over those (BaseCount.mean_entropy, main.py:342-359).
+template <bool HAS64>
 __global__ void __launch_bounds__(256)
 k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64, uint64_t stride,
            const uint32_t *__restrict__ col_base, const uint32_t *__restrict__ ref_len, int K, double norm,
-           long long min_cov, const double *__restrict__ log2_tab, const uint32_t *__restrict__ part_off, SummaryPartial *partials, uint32_t *arrive,
-           long long *__restrict__ nonzero, long long *__restrict__ cov_sum, double *__restrict__ ent_sum)
+           long long min_cov, const double *__restrict__ log2_tab, const uint32_t *__restrict__ part_off,
+           SummaryPartial *partials, uint32_t *arrive, long long *__restrict__ nonzero, long long *__restrict__ cov_sum,
+           double *__restrict__ ent_sum)
 {
     const uint32_t r = blockIdx.y;
     const uint32_t L = ref_len[r];
@@ -179,7 +232,15 @@ k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restric
     double es = 0.0;
     for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < L; pos += nb * blockDim.x) {
         long long c[6];
-        load_counts(c32, c64, stride, base + pos, K, c);
+#pragma unroll
+        for (int p = 0; p < kPlanes; p++) {
+            c[p] = 0;
+            if (p < K) {
+                const uint64_t a = (uint64_t)p * stride + base + pos;
+                c[p] = (long long)c32[a];
+                if (HAS64) c[p] += (long long)c64[a];
+            }
+        }
         long long cov;
         double ent;
         position_cov_entropy(c, K, norm, cov, ent, log2_tab);
@@ -192,29 +253,15 @@ k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restric
         }
         cs += cov;
     }
-    __shared__ long long s_nz[256], s_cs[256];
-    __shared__ double s_es[256];
+    __shared__ long long s_nz[8], s_cs[8];
+    __shared__ double s_es[8];
     __shared__ uint32_t s_last;
-    auto tree = [&]() {
-        s_nz[threadIdx.x] = nz;
-        s_cs[threadIdx.x] = cs;
-        s_es[threadIdx.x] = es;
-        __syncthreads();
-        for (int d = 128; d > 0; d >>= 1) {
-            if ((int)threadIdx.x < d) {
-                s_nz[threadIdx.x] += s_nz[threadIdx.x + d];
-                s_cs[threadIdx.x] += s_cs[threadIdx.x + d];
-                s_es[threadIdx.x] += s_es[threadIdx.x + d];
-            }
-            __syncthreads();
-        }
-    };
-    tree();
+    summary_cta_sum(nz, cs, es, s_nz, s_cs, s_es);
     SummaryPartial *p = partials + part_off[r];
     if (threadIdx.x == 0) {
-        p[blockIdx.x].nonzero = s_nz[0];
-        p[blockIdx.x].cov_sum = s_cs[0];
-        p[blockIdx.x].ent_sum = s_es[0];
+        p[blockIdx.x].nonzero = nz;
+        p[blockIdx.x].cov_sum = cs;
+        p[blockIdx.x].ent_sum = es;
         __threadfence();                                   // the partial is visible before the arrival is
         s_last = atomicAdd(arrive + r, 1u) == nb - 1u;
     }
@@ -230,11 +277,11 @@ k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restric
         cs += vp[i].cov_sum;
         es += vp[i].ent_sum;
     }
-    tree();
+    summary_cta_sum(nz, cs, es, s_nz, s_cs, s_es);
     if (threadIdx.x == 0) {
-        nonzero[r] = s_nz[0];
-        cov_sum[r] = s_cs[0];
-        ent_sum[r] = s_es[0];
+        nonzero[r] = nz;
+        cov_sum[r] = cs;
+        ent_sum[r] = es;
         arrive[r] = 0u;
     }
 }

@@ -55,31 +55,53 @@ def parse():
     ap.add_argument("--reads-per-sample", type=int, default=124_000)
     ap.add_argument("--cfg5-reads", type=int, default=12_888_833)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gen-samples", default=None, help="internal: synthesise these sample seeds into /tmp and exit")
     ap.add_argument("--variant", type=int, default=0, help="0 tiled bit-sliced K1, 1 per-base atomics K1")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------- workloads
-def make_samples(seeds, n_reads):
-    """Synthetic config-1/2 samples, filtered and trimmed as get_basecounts would (cached in /tmp
-    so repeated invocations on one box, e.g. plain run then ncu, do not regenerate)."""
+def _sample_path(seed, n_reads):
+    return f"/tmp/bc_bench_sample_{seed}_{n_reads}.npz"
+
+
+def _generate_sample(job):
+    """Worker: synthesise one config-1/2 sample into the /tmp cache (numpy only, no CUDA)."""
+    seed, n_reads = job
     from basecount_b200 import synth
-    from basecount_b200.records import ReadBatch, select_reads
+    from basecount_b200.records import select_reads
+    b = select_reads(synth.amplicon_sample(seed=seed, n_reads=n_reads), 0, 0)
+    path = _sample_path(seed, n_reads)
+    tmp = f"{path}.{os.getpid()}.tmp.npz"
+    np.savez(tmp, starts=b.starts, cigar=b.cigar, cigar_off=b.cigar_off, seq=b.seq, qual=b.qual, seq_off=b.seq_off)
+    os.replace(tmp, path)
+    return seed
+
+
+def make_samples(seeds, n_reads):
+    """Synthetic config-1/2 samples, filtered and trimmed as get_basecounts would.  Cached in /tmp so
+    repeated invocations on one box (plain run, then ncu; N = 1, 2, 4, 8 back to back) do not regenerate;
+    missing ones are synthesised by child processes of this script sharing the host cores between the ranks."""
+    from basecount_b200.records import ReadBatch
+    seeds = list(seeds)
+    missing = [(s, n_reads) for s in seeds if not os.path.exists(_sample_path(s, n_reads))]
+    if missing:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        workers = max(1, min(len(missing), (os.cpu_count() or 1) // max(world, 1), 12))
+        if workers > 1:                                  # plain child processes of this script (numpy only, no CUDA)
+            procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--gen-samples",
+                                       ",".join(str(j[0]) for j in missing[w::workers]), "--reads-per-sample", str(n_reads)])
+                     for w in range(workers)]
+            for pr in procs:
+                if pr.wait() != 0:
+                    raise RuntimeError("sample generation failed")
+        else:
+            for job in missing:
+                _generate_sample(job)
     out = []
     for s in seeds:
-        path = f"/tmp/bc_bench_sample_{s}_{n_reads}.npz"
-        if os.path.exists(path):
-            z = np.load(path)
-            out.append(ReadBatch(z["starts"], z["cigar"], z["cigar_off"], z["seq"], z["qual"], z["seq_off"]))
-            continue
-        b = select_reads(synth.amplicon_sample(seed=s, n_reads=n_reads), 0, 0)
-        try:
-            np.savez(path + ".tmp.npz", starts=b.starts, cigar=b.cigar, cigar_off=b.cigar_off, seq=b.seq, qual=b.qual,
-                     seq_off=b.seq_off)
-            os.replace(path + ".tmp.npz", path)
-        except OSError:
-            pass
-        out.append(b)
+        z = np.load(_sample_path(s, n_reads))
+        out.append(ReadBatch(z["starts"], z["cigar"], z["cigar_off"], z["seq"], z["qual"], z["seq_off"]))
     return out
 
 
@@ -412,6 +434,10 @@ def run_region_sharded(args, local_reads, ref_len, label, rank, world, local, ba
 # ----------------------------------------------------------------------------- our arm
 def main():
     args = parse()
+    if args.gen_samples:
+        for seed in args.gen_samples.split(","):
+            _generate_sample((int(seed), args.reads_per_sample))
+        return
     if args.impl == "reference":
         run_reference(args)
         return
