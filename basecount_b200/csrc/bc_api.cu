@@ -228,8 +228,8 @@ int bc_create(int device, bc_handle **out)
     }
     if ((e = cudaMalloc(&h->d_status, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(h->d_status, 0, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
-    if ((e = cudaMalloc(&h->d_log2_tab, kLog2Tab * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc");
-    k_fill_log2<<<(kLog2Tab + 255) / 256, 256, 0, h->compute>>>(h->d_log2_tab);
+    if ((e = cudaMalloc(&h->d_log2_tab, kSummaryTabDoubles * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc");
+    k_fill_log2<<<(kSummaryTabDoubles + 255) / 256, 256, 0, h->compute>>>(h->d_log2_tab);
     if ((e = cudaStreamSynchronize(h->compute)) != cudaSuccess) return bail(e, "k_fill_log2");
     if ((e = cudaHostAlloc((void **)&h->h_status, kStatWords * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail(e, "cudaHostAlloc");

@@ -43,10 +43,25 @@ __device__ __forceinline__ double neumaier_entropy(const long long *c, int n, lo
 
 // log2 of the integers below kLog2Tab, filled once per handle with the same log2() the exact path calls.
 constexpr int kLog2Tab = 16384;
+// ... followed by the exact entropy terms -(p * log2 p), p = c / cov, for every 0 < c < cov < kTermTab (the
+// very expression of main.py:11, so a looked-up term is bit-identical to a computed one): shallow coverage
+// (whole-genome 30x) then needs no division and no log2 at all.
+constexpr int kTermTab = 128;
+constexpr int kSummaryTabDoubles = kLog2Tab + kTermTab * kTermTab;
 __global__ void k_fill_log2(double *__restrict__ tab)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < kLog2Tab) tab[i] = i ? log2((double)i) : 0.0;
+    if (i < kLog2Tab) {
+        tab[i] = i ? log2((double)i) : 0.0;
+    } else if (i < kSummaryTabDoubles) {
+        const int cov = (i - kLog2Tab) / kTermTab, c = (i - kLog2Tab) % kTermTab;
+        double x = 0.0;
+        if (c > 0 && c < cov) {
+            const double p = (double)c / (double)cov;
+            x = -(p * log2(p));
+        }
+        tab[i] = x;
+    }
 }
 
 // Entropy for the --summarise reductions (sums of entropies only; K2 is bound by the FP64 pipe and nearly all
@@ -61,6 +76,20 @@ __device__ __forceinline__ double neumaier_entropy_tab(const long long *c, int n
                                                        const double *__restrict__ tab)
 {
     if (total >= (long long)kLog2Tab) return neumaier_entropy(c, n, total, -1);
+    if (total < (long long)kTermTab) {                     // shallow: every term straight from the table
+        const double *__restrict__ row = tab + kLog2Tab + (int)total * kTermTab;
+        double hi = 0.0, lo = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            if (i >= n || c[i] == 0 || c[i] == total) continue;
+            const double x = row[c[i]];
+            const double t = hi + x;
+            if (fabs(hi) >= fabs(x)) lo += (hi - t) + x; else lo += (x - t) + hi;
+            hi = t;
+        }
+        if (lo != 0.0 && isfinite(lo)) return hi + lo;
+        return hi;
+    }
     int top = 0;
     long long ctop = c[0];
 #pragma unroll
