@@ -42,6 +42,7 @@ _SIGNATURES = {
     "bc_destroy": (None, [ctypes.c_void_p]),
     "bc_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "bc_device_count": (ctypes.c_int, []),
+    "bc_device_pci_bus_id": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "bc_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "bc_host_free": (None, [ctypes.c_void_p]),
     "bc_begin": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),

@@ -180,6 +180,15 @@ int bc_device_count(void)
     return n;
 }
 
+int bc_device_pci_bus_id(int device, char *out, int len)
+{
+    if (!out || len < 16) return BC_ERR_ARG;
+    if (cudaDeviceGetPCIBusId(out, len, device) != cudaSuccess) return BC_ERR_CUDA;
+    for (char *p = out; *p; p++)
+        if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    return BC_OK;
+}
+
 const char *bc_last_error(bc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int bc_create(int device, bc_handle **out)

@@ -475,8 +475,10 @@ def main():
     import __graft_entry__ as ge
     ge.build()
     from basecount_b200.engine import Engine
+    from basecount_b200.hostbind import bind_to_device_node
     from basecount_b200.pack import pack_batches
 
+    numa = bind_to_device_node(local)              # pinned buffers on the GPU's NUMA node (matters for e2e at N > 1)
     sets, ref_lens, label = build_workload(args, rank)
     if args.workload == "cfg5" and world > 1:
         run_region_sharded(args, sets[0][0], ref_lens[0], label, rank, world, local, barrier, max_over_ranks, sum_over_ranks)
@@ -605,7 +607,8 @@ def main():
         "config": {"workload": label, "samples_per_gpu": len(ref_lens), "reads_per_step_per_gpu": packed[0].n_reads,
                    "aligned_bases_per_step_per_gpu": bases_per_step[0], "ref_len": ref_lens[0],
                    "l2": f"inputs {packed[0].h2d_bytes() / 1e6:.0f} MB per step > 126 MB L2; two resident batches alternate",
-                   "timing": "CUDA events on the engine's compute stream; max over ranks", "k1_variant": args.variant},
+                   "timing": "CUDA events on the engine's compute stream; max over ranks", "k1_variant": args.variant,
+                   "host_numa": numa},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": 1e3 * e2e_s / args.steps, "timing": "host wall clock, device-synchronised both sides"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

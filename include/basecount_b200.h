@@ -92,6 +92,9 @@ int bc_create(int device, bc_handle **out);
 void bc_destroy(bc_handle *h);
 const char *bc_last_error(bc_handle *h);     /* h may be NULL: last create error */
 int bc_device_count(void);
+/* PCI bus id of a device ("0000:1b:00.0", lower case as under /sys/bus/pci/devices) so the host can
+ * place its threads and pinned buffers on the device's NUMA node.  len >= 16. */
+int bc_device_pci_bus_id(int device, char *out, int len);
 
 /* Pinned host memory for batches and results (cudaHostAlloc). */
 int bc_host_alloc(size_t bytes, void **out);
