@@ -76,11 +76,13 @@ struct bc_handle {
     DevBuf scratch_cov, scratch_pc, scratch_ent, scratch_sec, scratch_flags, scratch_i64, scratch_misc;
     SummaryPartial *d_partials = nullptr;
     size_t partials_cap = 0;
-    // asynchronous summaries: k2_summary writes into a pinned host block (zero-copy), the
-    // values are handed to the caller's arrays at the next synchronisation
-    struct PendingSummary { char *block; uint32_t n; int64_t *nonzero; int64_t *cov_sum; double *entropy_sum; };
+    // asynchronous summaries: k2_summary writes its scalars into a device arena (a write to mapped host
+    // memory kept every launch waiting ~15 us for the PCIe round trip); the arena comes back in ONE copy at
+    // the next synchronisation and the values are handed to the callers' arrays there
+    struct PendingSummary { size_t off; uint32_t n; int64_t *nonzero; int64_t *cov_sum; double *entropy_sum; };
     std::vector<PendingSummary> pending;
-    std::vector<std::pair<char *, size_t>> free_blocks;      // pinned blocks to reuse (ptr, bytes)
+    char *d_results = nullptr, *h_results = nullptr;         // device arena and its pinned mirror
+    size_t results_cap = 0, results_used = 0;
     double *d_log2_tab = nullptr;         // log2 of small integers for the summarise reductions (k2_stats.cuh)
     uint32_t *d_part_off = nullptr;       // first partial of every slot (see summary_blocks)
     uint32_t part_off_refs = 0;           // 0 = stale (slot lengths changed)
@@ -124,31 +126,50 @@ static int ensure(bc_handle *h, DevBuf &b, size_t bytes)
     return BC_OK;
 }
 
-static char *take_block(bc_handle *h, size_t bytes)
+// Queue the copy of the result arena to its pinned mirror (no-op without pending summaries).
+static int fetch_summaries(bc_handle *h)
 {
-    for (size_t i = 0; i < h->free_blocks.size(); i++) {
-        if (h->free_blocks[i].second >= bytes) {
-            char *p = h->free_blocks[i].first;
-            h->free_blocks.erase(h->free_blocks.begin() + (long)i);
-            return p;
-        }
-    }
-    char *p = nullptr;
-    if (cudaHostAlloc((void **)&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-    return p;
+    if (h->pending.empty()) return BC_OK;
+    CU(h, cudaMemcpyAsync(h->h_results, h->d_results, h->results_used, cudaMemcpyDeviceToHost, h->compute));
+    return BC_OK;
 }
 
-// Call after the compute stream has been synchronised: hands finished summaries to their callers.
+// Call after fetch_summaries and a synchronisation of the compute stream: hands the values to their callers.
 static void deliver_summaries(bc_handle *h)
 {
     for (auto &p : h->pending) {
         const size_t n = p.n;
-        std::memcpy(p.nonzero, p.block, n * 8);
-        std::memcpy(p.cov_sum, p.block + n * 8, n * 8);
-        std::memcpy(p.entropy_sum, p.block + n * 16, n * 8);
-        h->free_blocks.push_back({p.block, n * 24});
+        const char *src = h->h_results + p.off;
+        std::memcpy(p.nonzero, src, n * 8);
+        std::memcpy(p.cov_sum, src + n * 8, n * 8);
+        std::memcpy(p.entropy_sum, src + n * 16, n * 8);
     }
     h->pending.clear();
+    h->results_used = 0;
+}
+
+// Room for `bytes` more in the arena; when it is full the pending summaries are delivered early.
+static int reserve_results(bc_handle *h, size_t bytes, size_t *off)
+{
+    if (h->results_used + bytes > h->results_cap) {
+        int rc = fetch_summaries(h);
+        if (rc) return rc;
+        CU(h, cudaStreamSynchronize(h->compute));
+        deliver_summaries(h);
+        if (bytes > h->results_cap) {
+            if (h->d_results) CU(h, cudaFree(h->d_results));
+            if (h->h_results) CU(h, cudaFreeHost(h->h_results));
+            h->d_results = h->h_results = nullptr;
+            h->results_cap = 0;
+            const size_t want = std::max<size_t>(bytes * 4, 1u << 16);
+            CU(h, cudaMalloc((void **)&h->d_results, want));
+            CU(h, cudaHostAlloc((void **)&h->h_results, want, cudaHostAllocDefault));
+            h->results_cap = want;
+        }
+    }
+    *off = h->results_used;
+    h->results_used += bytes;
+    return BC_OK;
 }
 
 static void release(DevBuf &b)
@@ -263,8 +284,8 @@ void bc_destroy(bc_handle *h)
         release(*b);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_part_off) cudaFree(h->d_part_off);
-    for (auto &p : h->pending) cudaFreeHost(p.block);
-    for (auto &p : h->free_blocks) cudaFreeHost(p.first);
+    if (h->d_results) cudaFree(h->d_results);
+    if (h->h_results) cudaFreeHost(h->h_results);
     if (h->d_counts) cudaFree(h->d_counts);
     if (h->d_counts64) cudaFree(h->d_counts64);
     if (h->d_col_base) cudaFree(h->d_col_base);
@@ -652,6 +673,10 @@ int bc_sync(bc_handle *h)
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->copy));
     CU(h, cudaStreamSynchronize(h->side));               // the overflow checks have written their status words
+    {
+        int rcf = fetch_summaries(h);
+        if (rcf) return rcf;
+    }
     CU(h, cudaMemcpyAsync(h->h_status, h->d_status, kStatWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
     deliver_summaries(h);
@@ -823,9 +848,12 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
         h->part_off_refs = R;
         h->summary_max_blocks = maxb;
     }
-    char *block = take_block(h, (size_t)R * 24);
-    if (!block) return fail(h, BC_ERR_CUDA, "pinned allocation for the summary failed");
-    long long *d_nz = (long long *)block;                 // pinned host memory, written by the kernel over PCIe
+    size_t off = 0;
+    {
+        int rcr = reserve_results(h, (size_t)R * 24, &off);
+        if (rcr) return rcr;
+    }
+    long long *d_nz = (long long *)(h->d_results + off);   // device arena, fetched at the next synchronisation
     long long *d_cs = d_nz + R;
     double *d_es = (double *)(d_cs + R);
     const int K = show_n ? 6 : 5;
@@ -839,9 +867,11 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
             h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off,
             h->d_partials, h->d_part_off + R, d_nz, d_cs, d_es);
     h->launches += 1;
-    h->pending.push_back({block, R, nonzero, cov_sum, entropy_sum});
+    h->pending.push_back({off, R, nonzero, cov_sum, entropy_sum});
     CU(h, cudaGetLastError());
     if (sync) {
+        int rcf = fetch_summaries(h);
+        if (rcf) return rcf;
         CU(h, cudaStreamSynchronize(h->compute));
         deliver_summaries(h);
     }

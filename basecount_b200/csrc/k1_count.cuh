@@ -35,8 +35,16 @@
 
 namespace bc {
 
-constexpr int kK1WarpsPerCta = 4;
-constexpr int kK1MinCtas = 3;
+#ifndef BC_K1_SEQCAP
+#define BC_K1_SEQCAP 448
+#define BC_K1_CIGCAP 96
+#endif
+#ifndef BC_K1_WARPS
+#define BC_K1_WARPS 4
+#define BC_K1_MINCTAS 3
+#endif
+constexpr int kK1WarpsPerCta = BC_K1_WARPS;
+constexpr int kK1MinCtas = BC_K1_MINCTAS;
 constexpr int kK1Threads = kK1WarpsPerCta * 32;
 constexpr int kNB = 8;                        // bit planes per vertical counter (counts to 255)
 constexpr int kNR = 5;                        // planes 0..4 live in registers; planes 5..7 and the weight-16 pending
@@ -46,8 +54,8 @@ constexpr int kNC = 4;                        // counted quantities per window w
 constexpr int kW = 2;                         // window words per lane
 constexpr int kStages = 3;                    // TMA pipeline depth (blocks of reads)
 constexpr uint32_t kFull = 0xFFFFFFFFu;
-constexpr uint32_t kSeqCap = 448;             // staged 64-bit plane words per stage (31 reads x 13 words + slack)
-constexpr uint32_t kCigCap = 96;              // staged CIGAR words per stage; the rest is read from HBM
+constexpr uint32_t kSeqCap = BC_K1_SEQCAP;             // staged 64-bit plane words per stage (31 reads x 13 words + slack)
+constexpr uint32_t kCigCap = BC_K1_CIGCAP;              // staged CIGAR words per stage; the rest is read from HBM
 constexpr uint32_t kCntMax = 252;             // pieces per slot between flushes (8-plane counters, 4 per trip)
 constexpr uint32_t kFlushStride = 34;         // uint16 per staged window word (32 + 2 pad: conflict-free stores)
 constexpr uint32_t kMaxRpb = 31;              // reads per block: lane i+1 holds the end offsets of read i
@@ -343,7 +351,11 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
 // The counting kernel.  One warp = one chunk of consecutive reads, processed in blocks of
 // `rpb` <= 31 reads, one read per lane.
 template <int G, bool HAS_OK>
+#ifdef BC_K1_MAXNREG
+__global__ void __maxnreg__(BC_K1_MAXNREG)
+#else
 __global__ void __launch_bounds__(kK1Threads, kK1MinCtas)
+#endif
 k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb)
 {
     using C = K1Cfg<G, HAS_OK>;
@@ -914,19 +926,34 @@ __device__ __forceinline__ bool read_pos_to_col(const BatchView &bv, uint32_t i,
     return false;
 }
 
-// Sparse corrections for letters outside ACGT (see bc_batch.exc_* in the header).
-__global__ void k1_exceptions(BatchView bv, CountView cv)
+// Sparse corrections for letters outside ACGT (see bc_batch.exc_* in the header).  One thread per
+// exception; the chain of dependent loads is what it costs, so the slot tables (a binary search plus two
+// look-ups per thread) are staged in shared memory when they fit.
+constexpr uint32_t kExcSlotsInSmem = 256;
+__global__ void __launch_bounds__(128)
+k1_exceptions(BatchView bv, CountView cv)
 {
+    __shared__ uint32_t s_off[kExcSlotsInSmem + 1], s_base[kExcSlotsInSmem], s_len[kExcSlotsInSmem];
+    const bool staged = bv.n_refs <= kExcSlotsInSmem;
+    if (staged) {
+        for (uint32_t t = threadIdx.x; t <= bv.n_refs; t += blockDim.x) s_off[t] = bv.ref_read_off[t];
+        for (uint32_t t = threadIdx.x; t < bv.n_refs; t += blockDim.x) {
+            s_base[t] = cv.col_base[t];
+            s_len[t] = cv.ref_len[t];
+        }
+        __syncthreads();
+    }
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= bv.n_exc) return;
     const uint32_t i = bv.exc_read[e];
-    const uint32_t pos = bv.exc_pos[e] >> 2, flags = bv.exc_pos[e] & 3u;
+    const uint32_t ep = bv.exc_pos[e];
+    const uint32_t pos = ep >> 2, flags = ep & 3u;
     if (i >= bv.n_reads) return;
     uint32_t col;
     if (!read_pos_to_col(bv, i, pos, &col)) return;
-    const uint32_t r = slot_of_read(bv.ref_read_off, bv.n_refs, i);
-    const uint64_t base = cv.col_base[r];
-    if (col >= cv.ref_len[r]) {
+    const uint32_t r = slot_of_read(staged ? s_off : bv.ref_read_off, bv.n_refs, i);
+    const uint64_t base = staged ? s_base[r] : cv.col_base[r];
+    if (col >= (staged ? s_len[r] : cv.ref_len[r])) {
         if (flags & 1u) cv.status[kStatIndexError] = 1u;   // an N that counts, past the end (count.cpp:64)
         return;                                            // flag 2: the main pass clipped it already
     }
