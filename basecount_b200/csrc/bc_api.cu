@@ -79,8 +79,8 @@ struct bc_handle {
     // asynchronous summaries: k2_summary writes its scalars into a device arena (a write to mapped host
     // memory kept every launch waiting ~15 us for the PCIe round trip); the arena comes back in ONE copy at
     // the next synchronisation and the values are handed to the callers' arrays there
-    struct PendingSummary { size_t off; uint32_t n; int64_t *nonzero; int64_t *cov_sum; double *entropy_sum; };
-    std::vector<PendingSummary> pending;
+    struct PendingCopy { size_t off; size_t bytes; void *dst; };   // arena bytes owed to a caller's array
+    std::vector<PendingCopy> pending;
     char *d_results = nullptr, *h_results = nullptr;         // device arena and its pinned mirror
     size_t results_cap = 0, results_used = 0;
     double *d_log2_tab = nullptr;         // log2 of small integers for the summarise reductions (k2_stats.cuh)
@@ -137,13 +137,7 @@ static int fetch_summaries(bc_handle *h)
 // Call after fetch_summaries and a synchronisation of the compute stream: hands the values to their callers.
 static void deliver_summaries(bc_handle *h)
 {
-    for (auto &p : h->pending) {
-        const size_t n = p.n;
-        const char *src = h->h_results + p.off;
-        std::memcpy(p.nonzero, src, n * 8);
-        std::memcpy(p.cov_sum, src + n * 8, n * 8);
-        std::memcpy(p.entropy_sum, src + n * 16, n * 8);
-    }
+    for (auto &p : h->pending) std::memcpy(p.dst, h->h_results + p.off, p.bytes);
     h->pending.clear();
     h->results_used = 0;
 }
@@ -161,7 +155,7 @@ static int reserve_results(bc_handle *h, size_t bytes, size_t *off)
             if (h->h_results) CU(h, cudaFreeHost(h->h_results));
             h->d_results = h->h_results = nullptr;
             h->results_cap = 0;
-            const size_t want = std::max<size_t>(bytes * 4, 1u << 16);
+            const size_t want = std::max<size_t>(bytes * 4, 1u << 20);
             CU(h, cudaMalloc((void **)&h->d_results, want));
             CU(h, cudaHostAlloc((void **)&h->h_results, want, cudaHostAllocDefault));
             h->results_cap = want;
@@ -867,7 +861,9 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
             h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off,
             h->d_partials, h->d_part_off + R, d_nz, d_cs, d_es);
     h->launches += 1;
-    h->pending.push_back({off, R, nonzero, cov_sum, entropy_sum});
+    h->pending.push_back({off, (size_t)R * 8, nonzero});
+    h->pending.push_back({off + (size_t)R * 8, (size_t)R * 8, cov_sum});
+    h->pending.push_back({off + (size_t)R * 16, (size_t)R * 8, entropy_sum});
     CU(h, cudaGetLastError());
     if (sync) {
         int rcf = fetch_summaries(h);
@@ -878,8 +874,23 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
     return BC_OK;
 }
 
+static int amplicons_impl(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, uint32_t n_tiles,
+                          const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty, bool sync);
+
 int bc_amplicons(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, uint32_t n_tiles,
                  const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty)
+{
+    return amplicons_impl(h, ref, show_n, norm, norm2, n_tiles, lo, hi, out, empty, true);
+}
+
+int bc_amplicons_async(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, uint32_t n_tiles,
+                       const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty)
+{
+    return amplicons_impl(h, ref, show_n, norm, norm2, n_tiles, lo, hi, out, empty, false);
+}
+
+static int amplicons_impl(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, uint32_t n_tiles,
+                          const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty, bool sync)
 {
     if (!h) return BC_ERR_ARG;
     if (ref >= h->n_refs) return fail(h, BC_ERR_ARG, "reference slot out of range");
@@ -891,14 +902,15 @@ int bc_amplicons(bc_handle *h, uint32_t ref, int show_n, double norm, double nor
     int rc = BC_OK;
     if (L) rc = run_rows(h, ref, K, norm, norm2, true, false, true, true, false);
     if (rc) return rc;
-    // device scratch: lo[T] hi[T] out[6T] empty[T]
-    const size_t bytes = (size_t)n_tiles * (4 + 4 + 48 + 1) + 64;
-    if ((rc = ensure(h, h->scratch_misc, bytes))) return rc;
-    char *base = (char *)h->scratch_misc.p;
-    double *d_out = (double *)base;
-    int32_t *d_lo = (int32_t *)(base + (size_t)n_tiles * 48);
+    // results in the arena (fetched at the next synchronisation): out[6T] empty[T]; device scratch: lo[T] hi[T]
+    const size_t out_bytes = ((size_t)n_tiles * 49 + 7) / 8 * 8;
+    size_t off = 0;
+    if ((rc = reserve_results(h, out_bytes, &off))) return rc;
+    if ((rc = ensure(h, h->scratch_misc, (size_t)n_tiles * 8 + 64))) return rc;
+    double *d_out = (double *)(h->d_results + off);
+    uint8_t *d_empty = (uint8_t *)(h->d_results + off + (size_t)n_tiles * 48);
+    int32_t *d_lo = (int32_t *)h->scratch_misc.p;
     int32_t *d_hi = d_lo + n_tiles;
-    uint8_t *d_empty = (uint8_t *)(d_hi + n_tiles);
     CU(h, cudaMemcpyAsync(d_lo, lo, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, h->compute));
     CU(h, cudaMemcpyAsync(d_hi, hi, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, h->compute));
     uint32_t cap = 4096;                        // doubles staged per window (32 KB)
@@ -907,9 +919,13 @@ int bc_amplicons(bc_handle *h, uint32_t ref, int show_n, double norm, double nor
         d_lo, d_hi, n_tiles, cap, d_out, d_empty);
     h->launches++;
     CU(h, cudaGetLastError());
-    CU(h, cudaMemcpyAsync(out, d_out, (size_t)n_tiles * 48, cudaMemcpyDeviceToHost, h->compute));
-    CU(h, cudaMemcpyAsync(empty, d_empty, (size_t)n_tiles, cudaMemcpyDeviceToHost, h->compute));
-    CU(h, cudaStreamSynchronize(h->compute));
+    h->pending.push_back({off, (size_t)n_tiles * 48, out});
+    h->pending.push_back({off + (size_t)n_tiles * 48, (size_t)n_tiles, empty});
+    if (sync) {
+        if ((rc = fetch_summaries(h))) return rc;
+        CU(h, cudaStreamSynchronize(h->compute));
+        deliver_summaries(h);
+    }
     return BC_OK;
 }
 

@@ -153,6 +153,17 @@ class Engine:
                                                  _lib.ptr(out), _lib.ptr(empty)))
         return out, empty
 
+    def amplicons_async(self, ref: int, lo, hi, out, empty, show_n_bases: bool = False):
+        """Queue the amplicon reductions; `out` (6 x T float64) and `empty` (T uint8) are caller-owned
+        arrays that hold the results after sync()."""
+        lo = np.ascontiguousarray(lo, dtype=np.int32)
+        hi = np.ascontiguousarray(hi, dtype=np.int32)
+        t = int(lo.shape[0])
+        assert out.dtype == np.float64 and out.size == 6 * t and empty.dtype == np.uint8 and empty.size == t
+        n1, n2 = norm_factors(show_n_bases)
+        _lib.check(self._h, self._L.bc_amplicons_async(self._h, ref, int(show_n_bases), n1, n2, t, _lib.ptr(lo),
+                                                       _lib.ptr(hi), _lib.ptr(out), _lib.ptr(empty)))
+
     # -- region sharding
     def halo_export(self, ref: int, col_lo: int, n_cols: int, dev_ptr: int):
         _lib.check(self._h, self._L.bc_halo_export(self._h, ref, col_lo, n_cols, ctypes.c_void_p(dev_ptr)))

@@ -156,6 +156,11 @@ int bc_summary_min_coverage(bc_handle *h, int show_n, double norm, int64_t min_c
 int bc_amplicons(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
                  uint32_t n_tiles, const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty);
 
+/* Same, without waiting: out / empty (any host memory) are filled in by the next bc_sync and must stay
+ * alive until then; lo / hi are consumed before the call returns. */
+int bc_amplicons_async(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
+                       uint32_t n_tiles, const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty);
+
 /* ---- region sharding (config 5): boundary-column halo exchange --------------- */
 /* Copy / add the u32 counts of columns [col_lo, col_lo + n_cols) of a slot, all six
  * planes (6 * n_cols values, plane-major).  buf is a DEVICE pointer (e.g. a torch tensor

@@ -123,3 +123,31 @@ def test_amplicon_window_larger_than_staging(eng):
                 assert got[k, t] == float(want[k][t])               # medians are exact selections
             else:
                 assert got[k, t] == pytest.approx(float(want[k][t]), rel=TIGHT)
+
+
+def test_queued_results_are_delivered_at_sync(eng):
+    """bc_summary_async / bc_amplicons_async park their results in a device arena; several queued calls
+    (more than the arena's first allocation holds between two syncs is exercised by the tile count) all
+    land in the callers' arrays at the next sync and equal the synchronous calls."""
+    from basecount_b200.pack import pack_batches
+    rec = synth.amplicon_sample(seed=33, n_reads=1200, ref_len=5000, ref_name="toy")
+    b = select_reads(rec, 0, 0)
+    eng.begin([5000])
+    eng.push(pack_batches(b, 0))
+    eng.sync()
+    lo = list(range(0, 4900, 7))
+    hi = [x + 399 for x in lo]
+    want, want_empty = eng.amplicons(0, lo, hi)
+    want_sum = eng.summary(False)
+    queued = []
+    for _ in range(40):                                   # 40 x (700 windows x 49 B + 24 B) > 1 MB: forces an early delivery
+        out = np.full((6, len(lo)), np.nan)
+        empty = np.full(len(lo), 7, dtype=np.uint8)
+        s = (np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.float64))
+        eng.summary_async(s, False)
+        eng.amplicons_async(0, lo, hi, out, empty)
+        queued.append((out, empty, s))
+    eng.sync()
+    for out, empty, s in queued:
+        assert np.array_equal(out, want) and np.array_equal(empty, want_empty)
+        assert int(s[0][0]) == int(want_sum[0][0]) and int(s[1][0]) == int(want_sum[1][0]) and float(s[2][0]) == float(want_sum[2][0])
