@@ -60,7 +60,7 @@ struct bc_handle {
     std::string err;
 
     uint32_t n_refs = 0;
-    std::vector<uint32_t> ref_len, col_base;
+    std::vector<uint32_t> ref_len, col_base, slot_cap;      // slot_cap: a slot's length at bc_begin (bc_truncate may not exceed it)
     uint64_t stride = 0;
     uint32_t *d_counts = nullptr;
     unsigned long long *d_counts64 = nullptr;
@@ -86,6 +86,7 @@ struct bc_handle {
     double *d_log2_tab = nullptr;         // log2 of small integers for the summarise reductions (k2_stats.cuh)
     uint32_t *d_part_off = nullptr;       // first partial of every slot (see summary_blocks)
     uint32_t part_off_refs = 0;           // 0 = stale (slot lengths changed)
+    uint32_t part_off_cap = 0;            // slots the offset / arrival arrays were allocated for
     uint32_t summary_max_blocks = 1;
 
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -352,6 +353,7 @@ int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens)
     h->n_refs = n_refs;
     h->part_off_refs = 0;
     h->ref_len = rl;
+    h->slot_cap = rl;
     h->col_base = cb;
     h->reads_since_fold = 0;
     CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)total * kPlanes * sizeof(uint32_t), h->compute));
@@ -829,16 +831,19 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
             need += nb;
             maxb = std::max(maxb, nb);
         }
-        CU(h, cudaDeviceSynchronize());
-        if (h->d_partials) CU(h, cudaFree(h->d_partials));
-        if (h->d_part_off) CU(h, cudaFree(h->d_part_off));
-        h->d_partials = nullptr;
-        h->d_part_off = nullptr;
-        CU(h, cudaMalloc(&h->d_partials, need * sizeof(SummaryPartial)));
-        CU(h, cudaMalloc(&h->d_part_off, (size_t)R * 2 * sizeof(uint32_t)));       // offsets, then arrival counters
-        CU(h, cudaMemset(h->d_part_off, 0, (size_t)R * 2 * sizeof(uint32_t)));
+        CU(h, cudaStreamSynchronize(h->compute));         // earlier summaries still read the old offsets
+        if (need > h->partials_cap || R != h->part_off_cap || !h->d_part_off) {
+            if (h->d_partials) CU(h, cudaFree(h->d_partials));
+            if (h->d_part_off) CU(h, cudaFree(h->d_part_off));
+            h->d_partials = nullptr;
+            h->d_part_off = nullptr;
+            CU(h, cudaMalloc(&h->d_partials, need * sizeof(SummaryPartial)));
+            CU(h, cudaMalloc(&h->d_part_off, (size_t)R * 2 * sizeof(uint32_t)));   // offsets, then arrival counters
+            CU(h, cudaMemset(h->d_part_off, 0, (size_t)R * 2 * sizeof(uint32_t)));
+            h->partials_cap = need;
+            h->part_off_cap = R;
+        }
         CU(h, cudaMemcpy(h->d_part_off, off.data(), (size_t)R * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        h->partials_cap = need;
         h->part_off_refs = R;
         h->summary_max_blocks = maxb;
     }
@@ -974,7 +979,7 @@ int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, co
 int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len)
 {
     if (!h) return BC_ERR_ARG;
-    if (ref >= h->n_refs || new_len > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "bc_truncate: out of range");
+    if (ref >= h->n_refs || new_len > h->slot_cap[ref]) return fail(h, BC_ERR_ARG, "bc_truncate: out of range");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->side));               // an overflow check may still read the old length
     h->ref_len[ref] = new_len;

@@ -182,10 +182,10 @@ def summary_region_sharded(backend, dist, world, ref_len: int, show_n_bases: boo
     from per-rank K3 partials: all-reduce of {nonzero, coverage sum} (int64) and entropy sum (f64)."""
     import torch
     nz, cs, es = backend.summary(show_n_bases)
-    ints = backend.scalar_tensor([int(nz[0]), int(cs[0])], torch.int64)
-    flt = backend.scalar_tensor([float(es[0])], torch.float64)
+    # one collective: the two integers ride as float64 (sums below 2^53 are exact)
+    assert int(cs[0]) < 2 ** 53 // max(world, 1)
+    t = backend.scalar_tensor([float(int(nz[0])), float(int(cs[0])), float(es[0])], torch.float64)
     if world > 1:
-        dist.all_reduce(ints, op=dist.ReduceOp.SUM)
-        dist.all_reduce(flt, op=dist.ReduceOp.SUM)
-    nonzero, cov_sum = int(ints[0].item()), int(ints[1].item())
-    return 100 * (nonzero / ref_len), np.float64(cov_sum) / ref_len, np.float64(flt[0].item()) / ref_len
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    nonzero, cov_sum, ent_sum = t.tolist()
+    return 100 * (int(nonzero) / ref_len), np.float64(int(cov_sum)) / ref_len, np.float64(ent_sum) / ref_len

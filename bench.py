@@ -356,7 +356,8 @@ def run_region_sharded(args, local_reads, ref_len, label, rank, world, local, ba
     bases = packed.aligned_bases
 
     def step():
-        eng.begin([hi - lo + h])
+        eng.truncate(0, hi - lo + h)                          # the halo columns are back
+        eng.reset()
         eng.push(resident)
         eng.sync()
         bdist.exchange_halos(be, dist, rank, world, bounds, halos)
@@ -392,7 +393,8 @@ def run_region_sharded(args, local_reads, ref_len, label, rank, world, local, ba
     k1_ms = max_over_ranks(float(np.mean(hist)))
     # e2e: the same step from pinned host buffers (H2D inside), result read back every step
     def step_e2e():
-        eng.begin([hi - lo + h])
+        eng.truncate(0, hi - lo + h)
+        eng.reset()
         eng.push(packed)
         eng.sync()
         bdist.exchange_halos(be, dist, rank, world, bounds, halos)

@@ -167,8 +167,9 @@ int bc_amplicons_async(bc_handle *h, uint32_t ref, int show_n, double norm, doub
  * handed to torch.distributed send/recv over NCCL). */
 int bc_halo_export(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, uint32_t *dev_buf);
 int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, const uint32_t *dev_buf);
-/* Shrink a slot to its first new_len columns (drops the halo columns once they have been
- * sent to the neighbour, so statistics cover only the columns this GPU owns). */
+/* Set a slot's length to its first new_len columns, new_len <= its length at bc_begin: drops the halo
+ * columns once they have been sent to the neighbour, so statistics cover only the columns this GPU
+ * owns (and restores them before the next batch of a stream of samples).  Counts are not touched. */
 int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len);
 
 /* ---- host-side packer (replaces pybind11's list -> std::vector casters) -------- */
