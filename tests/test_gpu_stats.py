@@ -151,3 +151,41 @@ def test_queued_results_are_delivered_at_sync(eng):
     for out, empty, s in queued:
         assert np.array_equal(out, want) and np.array_equal(empty, want_empty)
         assert int(s[0][0]) == int(want_sum[0][0]) and int(s[1][0]) == int(want_sum[1][0]) and float(s[2][0]) == float(want_sum[2][0])
+
+
+@pytest.mark.parametrize("shape", ["shallow", "medium", "deep"])
+def test_summarise_entropy_paths_vs_oracle(eng, shape):
+    """k2_summary takes its entropy terms from three places: a table of exact terms (coverage < 128), the
+    exact log2 for the largest class plus a log2 table for the others (coverage < 16384), and the exact
+    expression for everything (deeper).  Each against the oracle's get_stats restatement, and the
+    coverage-threshold reduction behind BaseCount.mean_entropy against numpy on the oracle's vectors."""
+    from basecount_b200.pack import pack_batches
+    from oracle import bcount as obc
+    from oracle import stats as ost
+    if shape == "shallow":
+        rec = synth.uniform_short_read_sample(seed=41, ref_len=6000, n_reads=1200, read_len=150, ref_name="s")
+        L = 6000
+    elif shape == "medium":
+        rec = synth.amplicon_sample(seed=42, n_reads=4000, ref_len=1500, ref_name="m")
+        L = 1500
+    else:
+        rec = synth.uniform_short_read_sample(seed=43, ref_len=400, n_reads=60000, read_len=150, ref_name="d")
+        L = 400
+    b = select_reads(rec, 0, 0)
+    counts = obc.bcount_flat(L, 0, b).astype(np.int64)
+    cmax = int(counts[:, :5].sum(axis=1).max())
+    assert {"shallow": cmax < 128, "medium": 128 < cmax < 16384, "deep": cmax > 16384}[shape], cmax
+    eng.begin([L])
+    eng.push(pack_batches(b, 0))
+    eng.sync()
+    for show_n in (False, True):
+        cov, ent, _ = ost.per_position_vectors(counts.tolist(), show_n)
+        nz, cs, es = eng.summary(show_n)
+        assert int(nz[0]) == sum(1 for x in cov if x != 0) and int(cs[0]) == sum(cov)
+        assert float(es[0]) == pytest.approx(float(np.sum(np.asarray(ent, dtype=np.float64))), rel=TIGHT)
+        cov_a, ent_a = np.asarray(cov), np.asarray(ent, dtype=np.float64)
+        for thr in (0, 1, int(np.median(cov_a)), cmax, cmax + 1):
+            sel, cs2, es2 = eng.summary_min_coverage(thr, show_n)
+            keep = cov_a >= thr
+            assert int(sel[0]) == int(keep.sum()) and int(cs2[0]) == int(cov_a.sum())
+            assert float(es2[0]) == pytest.approx(float(ent_a[keep].sum()), rel=TIGHT, abs=1e-300)
