@@ -222,8 +222,10 @@ class NativeBam:
             self._core = (ref_id, pos, mapq, flag)
         return self._core
 
-    def select(self, ref_id: int, min_mapping_quality: int = 0, rec_a: int = 0, rec_b: int | None = None):
-        """ReadBatch of the kept reads of one reference among records [rec_a, rec_b)."""
+    def select(self, ref_id: int, min_mapping_quality: int = 0, rec_a: int = 0, rec_b: int | None = None,
+               want_qual: bool = True):
+        """ReadBatch of the kept reads of one reference among records [rec_a, rec_b).  want_qual=False leaves
+        the qualities out (an empty array): with min_base_quality 0 nothing reads them (count.cpp:56)."""
         import ctypes
         from . import _lib
         from .records import ReadBatch
@@ -236,10 +238,11 @@ class NativeBam:
         cigar = np.empty(nc.value, np.uint32)
         cigar_off = np.empty(n + 1, np.uint64)
         seq = np.empty(nb.value, np.uint8)
-        qual = np.empty(nb.value, np.uint8)
+        qual = np.empty(nb.value if want_qual else 0, np.uint8)
         seq_off = np.empty(n + 1, np.uint64)
         self._L.bc_bam_select_fill(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), _lib.ptr(starts),
-                                   _lib.ptr(cigar), _lib.ptr(cigar_off), _lib.ptr(seq), _lib.ptr(qual), _lib.ptr(seq_off))
+                                   _lib.ptr(cigar), _lib.ptr(cigar_off), _lib.ptr(seq), _lib.ptr(qual) if want_qual else None,
+                                   _lib.ptr(seq_off))
         return ReadBatch(starts, cigar, cigar_off, seq, qual, seq_off)
 
 

@@ -14,16 +14,38 @@
 #include <stdint.h>
 #include <zlib.h>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
 
+namespace bcbam {
+// Byte buffers that are NOT zero-filled on resize: a 150 MB memset (and its page faults, on one thread) cost
+// as much as the parallel inflate that overwrites every byte; the inflating threads touch the pages instead.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U, class... A>
+    void construct(U *p, A &&...a)
+    {
+        if constexpr (sizeof...(A) == 0) ::new ((void *)p) U;
+        else ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+};
+using ByteVec = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+}  // namespace bcbam
+
 struct bc_bam {
-    std::vector<uint8_t> raw;               // the inflated BAM stream
+    bcbam::ByteVec raw;                     // the inflated BAM stream
     std::vector<std::string> ref_names;
     std::vector<uint32_t> ref_lens;
     std::vector<uint64_t> rec_off;          // offset of every record's block_size field, plus the end
@@ -62,10 +84,9 @@ inline void parallel_for(int threads, uint64_t n, uint64_t grain, F f)
 }
 
 // Every BGZF block of the file (SAM spec 4.1: gzip member with a 'BC' extra subfield holding BSIZE-1).
-inline bool scan_blocks(const std::vector<uint8_t> &d, std::vector<Block> &out, uint64_t &total, std::string &err)
+inline bool scan_blocks(const uint8_t *d, uint64_t n, std::vector<Block> &out, uint64_t &total, std::string &err)
 {
     uint64_t off = 0;
-    const uint64_t n = d.size();
     total = 0;
     while (off < n) {
         if (n - off < 18 || d[off] != 31 || d[off + 1] != 139 || d[off + 2] != 8 || !(d[off + 3] & 4)) {
@@ -156,33 +177,37 @@ inline bool keep(const RecView &v, int32_t ref_id, uint32_t min_mapq)
 inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::string &err)
 {
     using namespace bcbam;
-    FILE *fh = std::fopen(path, "rb");
-    if (!fh) {
+    // the compressed file is mapped, not copied: the inflating threads read it straight from the page cache
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) {
         err = std::string("cannot open ") + path;
         return 1;
     }
-    std::vector<uint8_t> file;
-    std::fseek(fh, 0, SEEK_END);
-    const long sz = std::ftell(fh);
-    std::fseek(fh, 0, SEEK_SET);
-    if (sz < 0) {
-        std::fclose(fh);
+    struct stat st;
+    if (::fstat(fd, &st) != 0 || st.st_size < 0) {
+        ::close(fd);
         err = "cannot size the file";
         return 1;
     }
-    file.resize((size_t)sz);
-    if (sz && std::fread(file.data(), 1, (size_t)sz, fh) != (size_t)sz) {
-        std::fclose(fh);
-        err = "short read";
+    const uint64_t fsize = (uint64_t)st.st_size;
+    void *map = fsize ? ::mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    ::close(fd);
+    if (fsize && map == MAP_FAILED) {
+        err = "cannot map the file";
         return 1;
     }
-    std::fclose(fh);
+    struct Unmap {
+        void *p;
+        uint64_t n;
+        ~Unmap() { if (p && n) ::munmap(p, n); }
+    } unmap{map, fsize};
+    const uint8_t *file = static_cast<const uint8_t *>(map);
 
     bc_bam *b = new bc_bam();
     b->threads = threads > 0 ? threads : (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
     std::vector<Block> blocks;
     uint64_t total = 0;
-    if (!scan_blocks(file, blocks, total, err)) {
+    if (!scan_blocks(file, fsize, blocks, total, err)) {
         delete b;
         return 2;
     }
@@ -199,7 +224,7 @@ inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::st
             const Block &k = blocks[i];
             if (k.isize == 0) continue;
             inflateReset(&zs);
-            zs.next_in = const_cast<Bytef *>(file.data() + k.c0);
+            zs.next_in = const_cast<Bytef *>(file + k.c0);
             zs.avail_in = (uInt)(k.c1 - k.c0);
             zs.next_out = b->raw.data() + k.u0;
             zs.avail_out = k.isize;
@@ -216,7 +241,7 @@ inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::st
         return 2;
     }
     // header (SAM spec 4.2)
-    const std::vector<uint8_t> &r = b->raw;
+    const ByteVec &r = b->raw;
     if (r.size() < 12 || std::memcmp(r.data(), "BAM\1", 4) != 0) {
         err = "not a BAM file (bad magic)";
         delete b;
@@ -369,7 +394,7 @@ inline void bc_bam_select_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t re
                 const uint8_t byte = v.seq[q >> 1];
                 seq[s + (q - s0)] = (uint8_t)kNib[(q & 1) ? (byte & 15) : (byte >> 4)];
             }
-            std::memcpy(qual + s, v.qual + s0, s1 - s0);
+            if (qual) std::memcpy(qual + s, v.qual + s0, s1 - s0);   // NULL: the caller filters nothing by base quality
             r++;
             c += v.n_cigar;
             s += s1 - s0;

@@ -33,11 +33,11 @@ inline uint32_t reg2bin(int64_t beg, int64_t end)          // SAM spec 5.3
 constexpr uint32_t kMetaBin = 37450;                       // samtools' pseudo-bin: offsets and read counts
 constexpr uint64_t kNoOffset = ~0ull;
 
-inline void wr32(std::vector<uint8_t> &o, uint32_t v) { for (int i = 0; i < 4; i++) o.push_back((uint8_t)(v >> (8 * i))); }
-inline void wr64(std::vector<uint8_t> &o, uint64_t v) { for (int i = 0; i < 8; i++) o.push_back((uint8_t)(v >> (8 * i))); }
+inline void wr32(ByteVec &o, uint32_t v) { for (int i = 0; i < 4; i++) o.push_back((uint8_t)(v >> (8 * i))); }
+inline void wr64(ByteVec &o, uint64_t v) { for (int i = 0; i < 8; i++) o.push_back((uint8_t)(v >> (8 * i))); }
 inline uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
 
-inline bool load_file(const char *path, std::vector<uint8_t> &out, std::string &err)
+inline bool load_file(const char *path, ByteVec &out, std::string &err)
 {
     FILE *fh = std::fopen(path, "rb");
     if (!fh) {
@@ -61,7 +61,7 @@ inline bool load_file(const char *path, std::vector<uint8_t> &out, std::string &
 
 // Complete BGZF blocks inside buf (which starts at file offset `base`); a truncated block at the end is
 // left alone.  Block::c0 / c1 index buf, Block::u0 continues from `total`; fpos receives file offsets.
-inline bool scan_blocks_partial(const std::vector<uint8_t> &d, uint64_t from, uint64_t base, std::vector<Block> &out,
+inline bool scan_blocks_partial(const ByteVec &d, uint64_t from, uint64_t base, std::vector<Block> &out,
                                 std::vector<uint64_t> &fpos, uint64_t &total, uint64_t &consumed, std::string &err)
 {
     uint64_t off = from;
@@ -103,7 +103,7 @@ inline bool scan_blocks_partial(const std::vector<uint8_t> &d, uint64_t from, ui
 }
 
 // Inflate blocks [a, e) of `src` into dst (dst already sized); false on a bad block.
-inline bool inflate_blocks(int threads, const std::vector<uint8_t> &src, const std::vector<Block> &blocks, uint64_t a,
+inline bool inflate_blocks(int threads, const ByteVec &src, const std::vector<Block> &blocks, uint64_t a,
                            uint64_t e, uint8_t *dst, uint64_t dst_u0)
 {
     std::atomic<int> bad(0);
@@ -134,7 +134,7 @@ inline bool inflate_blocks(int threads, const std::vector<uint8_t> &src, const s
 
 // BAM header (SAM spec 4.2) at the start of `r`; `p` = offset of the first record.  Returns 0 ok,
 // 1 need more data, 2 not a BAM.
-inline int parse_header(const std::vector<uint8_t> &r, std::vector<std::string> &names, std::vector<uint32_t> &lens,
+inline int parse_header(const ByteVec &r, std::vector<std::string> &names, std::vector<uint32_t> &lens,
                         uint64_t &p)
 {
     names.clear();
@@ -179,7 +179,7 @@ struct Bai {
     uint64_t n_no_coor = 0;
 };
 
-inline bool parse_bai(const std::vector<uint8_t> &d, Bai &out, std::string &err)
+inline bool parse_bai(const ByteVec &d, Bai &out, std::string &err)
 {
     auto bad = [&]() {
         err = "truncated or malformed BAI index";
@@ -243,7 +243,7 @@ inline bool parse_bai(const std::vector<uint8_t> &d, Bai &out, std::string &err)
 inline int bc_bam_index_build_impl(const char *bam_path, const char *bai_path, int threads, std::string &err)
 {
     using namespace bcbam;
-    std::vector<uint8_t> file;
+    ByteVec file;
     if (!load_file(bam_path, file, err)) return 1;
     std::vector<Block> blocks;
     std::vector<uint64_t> fpos;
@@ -254,7 +254,7 @@ inline int bc_bam_index_build_impl(const char *bam_path, const char *bai_path, i
         return 2;
     }
     const int nt = threads > 0 ? threads : (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-    std::vector<uint8_t> raw(total);
+    ByteVec raw(total);
     if (!inflate_blocks(nt, file, blocks, 0, blocks.size(), raw.data(), 0)) {
         err = "corrupt BGZF block (inflate or CRC failed)";
         return 2;
@@ -325,7 +325,7 @@ inline int bc_bam_index_build_impl(const char *bam_path, const char *bai_path, i
         err = "truncated BAM record";
         return 2;
     }
-    std::vector<uint8_t> out;
+    ByteVec out;
     out.insert(out.end(), {'B', 'A', 'I', 1});
     wr32(out, (uint32_t)bai.refs.size());
     for (RefIndex &ri : bai.refs) {
@@ -373,7 +373,7 @@ inline int bc_bam_open_region_impl(const char *bam_path, const char *bai_path, i
                                    int threads, bc_bam **out, std::string &err)
 {
     using namespace bcbam;
-    std::vector<uint8_t> idx;
+    ByteVec idx;
     if (!load_file(bai_path, idx, err)) return 1;
     Bai bai;
     if (!parse_bai(idx, bai, err)) return 2;
@@ -390,7 +390,7 @@ inline int bc_bam_open_region_impl(const char *bam_path, const char *bai_path, i
         return 1;
     }
     const uint64_t fsize = (uint64_t)fsz;
-    auto read_at = [&](uint64_t off, uint64_t len, std::vector<uint8_t> &buf) -> bool {
+    auto read_at = [&](uint64_t off, uint64_t len, ByteVec &buf) -> bool {
         len = std::min(len, fsize > off ? fsize - off : 0);
         const size_t old = buf.size();
         buf.resize(old + len);
@@ -408,7 +408,7 @@ inline int bc_bam_open_region_impl(const char *bam_path, const char *bai_path, i
     };
     // ---- header: inflate leading blocks until it is complete
     {
-        std::vector<uint8_t> buf, raw;
+        ByteVec buf, raw;
         std::vector<Block> blocks;
         std::vector<uint64_t> fpos;
         uint64_t total = 0, consumed = 0, have = 0, done_blocks = 0, p = 0;
@@ -446,7 +446,7 @@ inline int bc_bam_open_region_impl(const char *bam_path, const char *bai_path, i
     const uint64_t c_first = v0 >> 16;
     uint64_t c_next = c_first;                     // file offset of the first block not read yet
     uint64_t want_to = std::min<uint64_t>(fsize, (v1 >> 16) + 0x10000ull);
-    std::vector<uint8_t> buf;
+    ByteVec buf;
     std::vector<Block> blocks;
     std::vector<uint64_t> fpos;
     uint64_t total = 0, consumed = 0, done_blocks = 0;
@@ -467,7 +467,7 @@ inline int bc_bam_open_region_impl(const char *bam_path, const char *bai_path, i
             const auto it = std::lower_bound(fpos.begin(), fpos.end(), ri.off_end >> 16);
             if (it != fpos.end() && *it == (ri.off_end >> 16)) u_end = blocks[(size_t)(it - fpos.begin())].u0 + (ri.off_end & 0xFFFFull);
         }
-        const std::vector<uint8_t> &r = b->raw;
+        const ByteVec &r = b->raw;
         bool starved = false;
         while (true) {
             if (p >= u_end) {                      // behind the reference's last record

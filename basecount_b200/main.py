@@ -112,9 +112,9 @@ class _RecordSource:
             self.ref_names, self.ref_lengths, self.n = r.ref_names, r.ref_lengths, r.n
             self.ref_id, self.mapq, self.flag = r.ref_id, r.mapq, r.flag
 
-    def select(self, a, b, rid, min_mapping_quality):
+    def select(self, a, b, rid, min_mapping_quality, want_qual=True):
         if self.native is not None:
-            return self.native.select(rid, min_mapping_quality, a, b)
+            return self.native.select(rid, min_mapping_quality, a, b, want_qual=want_qual)
         part = _slice_records(self.rec, a, b) if (a, b) != (0, self.rec.n) else self.rec
         return select_reads(part, rid, min_mapping_quality)
 
@@ -190,7 +190,7 @@ def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quali
         for a, b in zip(cuts[:-1], cuts[1:]):
             if b <= a:
                 continue
-            batches = [rec.select(a, b, rid, min_mapping_quality) for rid in ids]
+            batches = [rec.select(a, b, rid, min_mapping_quality, want_qual=min_base_quality > 0) for rid in ids]
             for j, bt in enumerate(batches):
                 num_reads[j] += bt.n
             eng.push(pack_batches(batches, min_base_quality))

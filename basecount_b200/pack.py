@@ -118,7 +118,8 @@ def pack_batches(batches, min_base_quality: int = 0, pinned: bool = False) -> Pa
         raise TypeError("more than 2^32-1 CIGAR operations in one batch")
     seq = np.ascontiguousarray(seq, dtype=np.uint8)
     qual = np.ascontiguousarray(qual, dtype=np.uint8)
-    if qual.shape[0] != seq.shape[0]:
+    no_qual = min_base_quality == 0 and qual.shape[0] == 0          # nothing reads qualities at threshold 0 (count.cpp:56)
+    if qual.shape[0] != seq.shape[0] and not no_qual:
         raise TypeError("qualities and reads differ in length")
 
     starts = _alloc(n, np.uint32, pinned)
@@ -139,7 +140,8 @@ def pack_batches(batches, min_base_quality: int = 0, pinned: bool = False) -> Pa
     while True:
         exc_read = _alloc(exc_cap, np.uint32, pinned)
         exc_pos = _alloc(exc_cap, np.uint32, pinned)
-        rc = L.bc_pack_reads(n, _lib.ptr(seq), _lib.ptr(qual), _lib.ptr(seq_off), _lib.ptr(cigar), _lib.ptr(cigar_off),
+        rc = L.bc_pack_reads(n, _lib.ptr(seq), None if no_qual else _lib.ptr(qual), _lib.ptr(seq_off), _lib.ptr(cigar),
+                             _lib.ptr(cigar_off),
                              int(min_base_quality), _lib.ptr(seq_woff), _lib.ptr(planes), _lib.ptr(okmask),
                              _lib.ptr(exc_read), _lib.ptr(exc_pos), exc_cap, ctypes.byref(n_exc))
         if rc == _lib.BC_ERR_READ_OVERRUN:

@@ -218,7 +218,8 @@ uint32_t bc_bam_ref_len(const bc_bam *b, uint32_t i);
 int bc_bam_core(const bc_bam *b, int32_t *ref_id, int32_t *pos, uint8_t *mapq, uint16_t *flag);
 /* Selection = records [rec_a, rec_b) with refID == ref_id, FLAG & 4 == 0 and MAPQ >= min_mapq.
  * Sizes first, then fill: starts[n], cigar[n_cigar] (BAM-native len << 4 | op), cigar_off[n + 1],
- * seq[n_bases] (ASCII, soft clips trimmed), qual[n_bases] (phred bytes), seq_off[n + 1]. */
+ * seq[n_bases] (ASCII, soft clips trimmed), qual[n_bases] (phred bytes; may be NULL when
+ * min_base_quality is 0 and nothing reads them), seq_off[n + 1]. */
 int bc_bam_select_sizes(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
                         uint64_t *n_reads, uint64_t *n_cigar, uint64_t *n_bases);
 int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
