@@ -346,6 +346,11 @@ inline void bc_bam_select_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t re
 {
     using namespace bcbam;
     static const char kNib[] = "=ACMGRSVTWYHKDBN";
+    uint16_t pair[256];                                     // packed byte -> its two letters, in memory order
+    for (int x = 0; x < 256; x++) {
+        const uint8_t two[2] = {(uint8_t)kNib[x >> 4], (uint8_t)kNib[x & 15]};
+        std::memcpy(&pair[x], two, 2);
+    }
     const uint64_t n = rec_b - rec_a;
     const uint64_t grain = 1 << 13;
     const uint64_t chunks = (n + grain - 1) / grain;
@@ -390,9 +395,15 @@ inline void bc_bam_select_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t re
             const uint64_t s1 = std::max<uint64_t>(s0, (uint64_t)v.l_seq > trail ? v.l_seq - trail : 0);
             starts[r] = (uint32_t)v.pos;
             for (uint32_t t = 0; t < v.n_cigar; t++) cigar[c + t] = rd32(v.cig + 4 * t);
-            for (uint64_t q = s0; q < s1; q++) {
-                const uint8_t byte = v.seq[q >> 1];
-                seq[s + (q - s0)] = (uint8_t)kNib[(q & 1) ? (byte & 15) : (byte >> 4)];
+            {
+                uint64_t q = s0;
+                uint8_t *dst = seq + s;
+                if ((q & 1) && q < s1) {                                // odd start (an odd-length soft clip): one nibble
+                    *dst++ = (uint8_t)kNib[v.seq[q >> 1] & 15];
+                    q++;
+                }
+                for (; q + 2 <= s1; q += 2, dst += 2) std::memcpy(dst, &pair[v.seq[q >> 1]], 2);   // two bases per byte
+                if (q < s1) *dst = (uint8_t)kNib[v.seq[q >> 1] >> 4];
             }
             if (qual) std::memcpy(qual + s, v.qual + s0, s1 - s0);   // NULL: the caller filters nothing by base quality
             r++;
