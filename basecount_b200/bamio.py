@@ -246,6 +246,54 @@ class NativeBam:
         return ReadBatch(starts, cigar, cigar_off, seq, qual, seq_off)
 
 
+def _native_pack(self, ref_id: int, min_mapping_quality: int = 0, min_base_quality: int = 0, rec_a: int = 0,
+                 rec_b: int | None = None, pinned: bool = False):
+    """PackedBatch (one reference slot) of the kept reads among records [rec_a, rec_b): selection, soft-clip
+    trimming and 2-bit packing in one native pass -- the same arrays as pack_batches(self.select(...))."""
+    import ctypes
+    from . import _lib
+    from .pack import PackedBatch, _alloc
+    if min_base_quality < 0:
+        raise TypeError("min_base_quality must be unsigned")
+    rec_b = self.n if rec_b is None else rec_b
+    z = np.zeros(6, np.uint64)
+    if self._L.bc_bam_pack_sizes(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), _lib.ptr(z)) != 0:
+        raise TypeError("bc_bam_pack_sizes failed")
+    n, n_cigar, n_words, n_bases, aligned, is_sorted = (int(x) for x in z)
+    if n >= 2 ** 32 or n_cigar >= 2 ** 32 or n_words >= 2 ** 32:
+        raise TypeError("batch does not fit 32-bit offsets")
+    ref_read_off = _alloc(2, np.uint32, pinned)
+    ref_read_off[0], ref_read_off[1] = 0, n
+    starts = _alloc(n, np.uint32, pinned)
+    cigar = _alloc(n_cigar, np.uint32, pinned)
+    cigar_off = _alloc(n + 1, np.uint32, pinned)
+    seq_woff = _alloc(n + 1, np.uint32, pinned)
+    planes = _alloc(n_words, np.uint64, pinned)
+    okmask = _alloc(n_words, np.uint32, pinned) if min_base_quality > 0 else None
+    exc_cap = max(1024, n_bases // 256)
+    n_exc = ctypes.c_uint64(0)
+    while True:
+        exc_read = _alloc(exc_cap, np.uint32, pinned)
+        exc_pos = _alloc(exc_cap, np.uint32, pinned)
+        rc = self._L.bc_bam_pack_fill(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), int(min_base_quality),
+                                      _lib.ptr(starts), _lib.ptr(cigar), _lib.ptr(cigar_off), _lib.ptr(seq_woff),
+                                      _lib.ptr(planes), _lib.ptr(okmask), _lib.ptr(exc_read), _lib.ptr(exc_pos), exc_cap,
+                                      ctypes.byref(n_exc))
+        if rc == _lib.BC_ERR_READ_OVERRUN:
+            raise ValueError("a CIGAR consumes more bases than its read holds")
+        if rc != _lib.BC_OK:
+            raise TypeError(f"bc_bam_pack_fill failed with status {rc}")
+        if n_exc.value <= exc_cap:
+            break
+        exc_cap = int(n_exc.value)
+    ne = int(n_exc.value)
+    return PackedBatch(n, 1, ref_read_off, starts, cigar_off, cigar, seq_woff, planes, okmask, exc_read[:ne], exc_pos[:ne],
+                       bool(is_sorted), (n_bases // n) if n else 0, aligned, n_bases)
+
+
+NativeBam.pack = _native_pack
+
+
 def write_bai(bam_path: str, bai_path: str | None = None, threads: int = 0) -> str:
     """Index a coordinate-sorted BAM (what `pysam.index` does for the reference's tests,
     tests/test_basecount.py:343-344); returns the path of the .bai."""

@@ -14,6 +14,9 @@
 #include <stdint.h>
 #include <zlib.h>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -271,10 +274,18 @@ inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::st
         b->ref_lens.push_back(rd32(&r[p + 4 + l_name]));
         p += 8ull + l_name;
     }
-    // record index
+    // record index.  The walk is a chain of dependent loads (a record's size gives the next record's offset),
+    // one cache miss each; records of one file are about the same size, so the lines a few records ahead are
+    // prefetched on that guess.  The second pass (validation) is independent per record and runs in parallel.
+    b->rec_off.reserve((size_t)(r.size() / 256 + 16));
     while (p + 4 <= r.size()) {
         b->rec_off.push_back(p);
-        p += 4ull + rd32(&r[p]);
+        const uint64_t step = 4ull + rd32(&r[p]);
+        if (p + 8 * step < r.size()) {
+            __builtin_prefetch(&r[p + 4 * step]);
+            __builtin_prefetch(&r[p + 8 * step]);
+        }
+        p += step;
     }
     if (p != r.size()) {
         err = "truncated BAM record";
@@ -282,13 +293,17 @@ inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::st
         return 2;
     }
     b->rec_off.push_back(p);
-    RecView v;
-    for (uint64_t i = 0; i + 1 < b->rec_off.size(); i++)
-        if (!view(b, i, v)) {
-            err = "malformed BAM record";
-            delete b;
-            return 2;
-        }
+    std::atomic<int> malformed(0);
+    parallel_for(b->threads, b->rec_off.size() - 1, 1 << 13, [&](uint64_t a, uint64_t e) {
+        RecView v;
+        for (uint64_t i = a; i < e; i++)
+            if (!view(b, i, v)) malformed = 1;
+    });
+    if (malformed) {
+        err = "malformed BAM record";
+        delete b;
+        return 2;
+    }
     *out = b;
     return 0;
 }
@@ -413,4 +428,216 @@ inline void bc_bam_select_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t re
             seq_off[r] = s;
         }
     });
+}
+
+// ---- selection straight into the device's packed batch (one reference slot) -------------------
+// bc_bam_select_fill + bc_pack_reads in one pass over the records: the 4-bit bases of a kept read go
+// directly to the 2-bit bit-planar words (struct bc_batch), without the ASCII copy in between.  Same
+// arrays as the two-step path (tests/test_bamio.py compares them).
+struct bc_pack_sizes {
+    uint64_t n_reads, n_cigar, n_words, n_bases, aligned_bases;
+    uint32_t sorted;                         // starts are non-decreasing
+};
+
+namespace bcbam {
+
+// Nibble -> class: 0..3 = A,C,G,T; 4 = N; 5 = anything else (never counted, count.cpp:58-65).
+inline const uint8_t *nibble_class()
+{
+    static const uint8_t k[16] = {5, 0, 1, 5, 2, 5, 5, 5, 3, 5, 5, 5, 5, 5, 5, 4};   // "=ACMGRSVTWYHKDBN"
+    return k;
+}
+
+struct Trim { uint64_t s0, s1; };
+inline Trim trimmed(const RecView &v)
+{
+    uint32_t lead, trail;
+    clips(v.cig, v.n_cigar, lead, trail);
+    Trim t;
+    t.s0 = std::min<uint64_t>(lead, v.l_seq);
+    t.s1 = std::max<uint64_t>(t.s0, (uint64_t)v.l_seq > trail ? v.l_seq - trail : 0);
+    return t;
+}
+
+}  // namespace bcbam
+
+inline void bc_bam_pack_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                                   bc_pack_sizes *out)
+{
+    using namespace bcbam;
+    const uint64_t n = rec_b - rec_a, grain = 1 << 13, chunks = (n + grain - 1) / grain;
+    struct Part { uint64_t r, c, w, s, al; int32_t first, last; bool sorted, any; };
+    std::vector<Part> parts(chunks ? chunks : 1);
+    parallel_for(b->threads, n, grain, [&](uint64_t a, uint64_t e) {
+        Part p = {0, 0, 0, 0, 0, 0, 0, true, false};
+        RecView v;
+        for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
+            view(b, i, v);
+            if (!keep(v, ref_id, min_mapq)) continue;
+            const Trim t = trimmed(v);
+            p.r++;
+            p.c += v.n_cigar;
+            p.s += t.s1 - t.s0;
+            p.w += (t.s1 - t.s0 + 31) / 32;
+            for (uint32_t k = 0; k < v.n_cigar; k++) {
+                const uint32_t w = rd32(v.cig + 4 * k), op = w & 15u;
+                if (op == 0u || op == 2u || op == 3u || op == 7u || op == 8u) p.al += w >> 4;
+            }
+            if (!p.any) p.first = v.pos;
+            else if (v.pos < p.last) p.sorted = false;
+            p.last = v.pos;
+            p.any = true;
+        }
+        parts[a / grain] = p;
+    });
+    bc_pack_sizes z = {0, 0, 0, 0, 0, 1};
+    bool any = false;
+    int32_t last = 0;
+    for (uint64_t k = 0; k < chunks; k++) {
+        const Part &p = parts[k];
+        z.n_reads += p.r;
+        z.n_cigar += p.c;
+        z.n_words += p.w;
+        z.n_bases += p.s;
+        z.aligned_bases += p.al;
+        if (!p.any) continue;
+        if (!p.sorted || (any && p.first < last)) z.sorted = 0;
+        last = p.last;
+        any = true;
+    }
+    *out = z;
+}
+
+// Arrays sized from bc_bam_pack_sizes: starts[n], cigar[n_cigar], cigar_off[n+1], seq_woff[n+1], planes[n_words],
+// okmask[n_words] (NULL unless min_base_quality > 0).  Exceptions as in bc_pack_reads: (read, pos << 2 | flags),
+// sorted by (read, pos); *n_exc may exceed exc_cap (then only the first exc_cap were written: call again).
+// Returns 0, or 5 (BC_ERR_READ_OVERRUN) when a CIGAR consumes more bases than its read holds.
+inline int bc_bam_pack_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                                 uint32_t min_base_quality, uint32_t *starts, uint32_t *cigar, uint32_t *cigar_off,
+                                 uint32_t *seq_woff, uint64_t *planes, uint32_t *okmask, uint32_t *exc_read,
+                                 uint32_t *exc_pos, uint64_t exc_cap, uint64_t *n_exc)
+{
+    using namespace bcbam;
+    const uint8_t *cls = nibble_class();
+    const uint64_t n = rec_b - rec_a, grain = 1 << 12, chunks = (n + grain - 1) / grain;
+    std::vector<uint64_t> cr(chunks + 1, 0), cc(chunks + 1, 0), cw(chunks + 1, 0);
+    parallel_for(b->threads, n, grain, [&](uint64_t a, uint64_t e) {
+        uint64_t r = 0, c = 0, w = 0;
+        RecView v;
+        for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
+            view(b, i, v);
+            if (!keep(v, ref_id, min_mapq)) continue;
+            const Trim t = trimmed(v);
+            r++;
+            c += v.n_cigar;
+            w += (t.s1 - t.s0 + 31) / 32;
+        }
+        const uint64_t k = a / grain;
+        cr[k + 1] = r;
+        cc[k + 1] = c;
+        cw[k + 1] = w;
+    });
+    for (uint64_t k = 0; k < chunks; k++) {
+        cr[k + 1] += cr[k];
+        cc[k + 1] += cc[k];
+        cw[k + 1] += cw[k];
+    }
+    if (cr[chunks] > 0xFFFFFFFFull || cc[chunks] > 0xFFFFFFFFull || cw[chunks] > 0xFFFFFFFFull) return 1;
+    cigar_off[0] = 0;
+    seq_woff[0] = 0;
+    std::vector<std::vector<uint32_t>> exc(chunks ? chunks : 1);
+    std::atomic<int> overrun(0);
+    parallel_for(b->threads, n, grain, [&](uint64_t a, uint64_t e) {
+        const uint64_t k = a / grain;
+        uint64_t r = cr[k], c = cc[k], w = cw[k];
+        std::vector<uint32_t> &ex = exc[k];
+        RecView v;
+        for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
+            view(b, i, v);
+            if (!keep(v, ref_id, min_mapq)) continue;
+            const Trim t = trimmed(v);
+            const uint64_t len = t.s1 - t.s0;
+            starts[r] = (uint32_t)v.pos;
+            uint64_t rp = 0;                                             // count.cpp:56,58 index the read unchecked
+            for (uint32_t q = 0; q < v.n_cigar; q++) {
+                const uint32_t word = rd32(v.cig + 4 * q), op = word & 15u, l = word >> 4;
+                cigar[c + q] = word;
+                if (op == 0u || op == 7u || op == 8u) {
+                    if (l && rp + l > len) overrun = 1;
+                    rp += l;
+                } else if (op == 1u) {
+                    rp += l;
+                }
+            }
+            for (uint64_t j0 = 0; j0 < len; j0 += 32, w++) {
+                const uint32_t m = (uint32_t)std::min<uint64_t>(32, len - j0);
+                const uint64_t q0 = t.s0 + j0;                           // first base of this word in the record
+                uint32_t lo = 0, hi = 0, odd = 0, ok = 0;
+#if defined(__SSE2__)
+                if (m == 32 && !(q0 & 1)) {                              // 16 packed bytes -> 32 nibbles in order
+                    const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i *>(v.seq + (q0 >> 1)));
+                    const __m128i f = _mm_set1_epi8(0x0F);
+                    const __m128i hn = _mm_and_si128(_mm_srli_epi16(x, 4), f), ln = _mm_and_si128(x, f);
+                    const __m128i h[2] = {_mm_unpacklo_epi8(hn, ln), _mm_unpackhi_epi8(hn, ln)};
+                    uint32_t ma = 0, mc = 0, mg = 0, mt = 0;
+                    for (int z = 0; z < 2; z++) {
+                        ma |= (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(h[z], _mm_set1_epi8(1))) << (16 * z);
+                        mc |= (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(h[z], _mm_set1_epi8(2))) << (16 * z);
+                        mg |= (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(h[z], _mm_set1_epi8(4))) << (16 * z);
+                        mt |= (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(h[z], _mm_set1_epi8(8))) << (16 * z);
+                    }
+                    lo = mc | mt;
+                    hi = mg | mt;
+                    odd = ~(ma | mc | mg | mt);
+                } else
+#endif
+                {
+                    for (uint32_t j = 0; j < m; j++) {
+                        const uint64_t q = q0 + j;
+                        const uint8_t byte = v.seq[q >> 1];
+                        const uint32_t cl = cls[(q & 1) ? (byte & 15) : (byte >> 4)];
+                        lo |= (cl & 1u) << j;
+                        hi |= ((cl >> 1) & 1u) << j;
+                        odd |= (cl >> 2) << j;
+                    }
+                    lo &= ~odd;
+                    hi &= ~odd;
+                }
+                if (min_base_quality > 0) {
+                    const uint8_t *qp = v.qual + q0;
+                    for (uint32_t j = 0; j < m; j++) ok |= (uint32_t)(qp[j] >= min_base_quality) << j;
+                } else {
+                    ok = m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+                }
+                for (uint32_t rest = odd & (m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1u)); rest; rest &= rest - 1u) {
+                    const uint32_t j = (uint32_t)__builtin_ctz(rest);
+                    const uint64_t q = q0 + j;
+                    const uint8_t byte = v.seq[q >> 1];
+                    const bool is_n = cls[(q & 1) ? (byte & 15) : (byte >> 4)] == 4;
+                    uint32_t flags = 0;
+                    if (min_base_quality == 0) flags = is_n ? 3u : 2u;             // undo the 'A', maybe count N
+                    else if (is_n && ((ok >> j) & 1u)) flags = 1u;                  // masked out already; count N
+                    if (flags) {
+                        ex.push_back((uint32_t)r);
+                        ex.push_back((uint32_t)((j0 + j) << 2) | flags);
+                    }
+                }
+                planes[w] = (uint64_t)lo | ((uint64_t)hi << 32);
+                if (okmask) okmask[w] = ok & ~odd;
+            }
+            r++;
+            c += v.n_cigar;
+            cigar_off[r] = (uint32_t)c;
+            seq_woff[r] = (uint32_t)w;
+        }
+    });
+    uint64_t ne = 0;
+    for (const auto &ex : exc)
+        for (size_t k = 0; k + 1 < ex.size(); k += 2, ne++)
+            if (ne < exc_cap && exc_read && exc_pos) {
+                exc_read[ne] = ex[k];
+                exc_pos[ne] = ex[k + 1];
+            }
+    *n_exc = ne;
+    return overrun ? 5 : 0;
 }

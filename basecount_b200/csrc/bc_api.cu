@@ -1248,6 +1248,32 @@ int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t 
     return BC_OK;
 }
 
+int bc_bam_pack_sizes(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq, uint64_t *out6)
+{
+    if (!b || !out6 || rec_a > rec_b || rec_b > b->rec_off.size() - 1) return BC_ERR_ARG;
+    bc_pack_sizes z;
+    bc_bam_pack_sizes_impl(b, rec_a, rec_b, ref_id, min_mapq, &z);
+    out6[0] = z.n_reads;
+    out6[1] = z.n_cigar;
+    out6[2] = z.n_words;
+    out6[3] = z.n_bases;
+    out6[4] = z.aligned_bases;
+    out6[5] = z.sorted;
+    return BC_OK;
+}
+
+int bc_bam_pack_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                     uint32_t min_base_quality, uint32_t *starts, uint32_t *cigar, uint32_t *cigar_off, uint32_t *seq_woff,
+                     uint64_t *planes, uint32_t *okmask, uint32_t *exc_read, uint32_t *exc_pos, uint64_t exc_cap,
+                     uint64_t *n_exc)
+{
+    if (!b || !cigar_off || !seq_woff || !n_exc || rec_a > rec_b || rec_b > b->rec_off.size() - 1) return BC_ERR_ARG;
+    if (min_base_quality > 0 && !okmask) return BC_ERR_ARG;
+    const int rc = bc_bam_pack_fill_impl(b, rec_a, rec_b, ref_id, min_mapq, min_base_quality, starts, cigar, cigar_off,
+                                         seq_woff, planes, okmask, exc_read, exc_pos, exc_cap, n_exc);
+    return rc == 0 ? BC_OK : (rc == 5 ? BC_ERR_READ_OVERRUN : BC_ERR_ARG);
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------ exact TSV rows (tsv_format.h)

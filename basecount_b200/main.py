@@ -190,10 +190,16 @@ def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quali
         for a, b in zip(cuts[:-1], cuts[1:]):
             if b <= a:
                 continue
-            batches = [rec.select(a, b, rid, min_mapping_quality, want_qual=min_base_quality > 0) for rid in ids]
-            for j, bt in enumerate(batches):
-                num_reads[j] += bt.n
-            eng.push(pack_batches(batches, min_base_quality))
+            if rec.native is not None and len(ids) == 1:
+                # one native pass: selection (main.py:165-166), soft-clip trimming and 2-bit packing
+                packed = rec.native.pack(ids[0], min_mapping_quality, min_base_quality, a, b)
+                num_reads[0] += packed.n_reads
+            else:
+                batches = [rec.select(a, b, rid, min_mapping_quality, want_qual=min_base_quality > 0) for rid in ids]
+                for j, bt in enumerate(batches):
+                    num_reads[j] += bt.n
+                packed = pack_batches(batches, min_base_quality)
+            eng.push(packed)
             eng.sync()
     rec.close()
     return Pileup(eng, refs, lengths, num_reads, show_n_bases)

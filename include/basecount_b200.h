@@ -226,6 +226,17 @@ int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t 
                        uint32_t *starts, uint32_t *cigar, uint64_t *cigar_off, uint8_t *seq, uint8_t *qual,
                        uint64_t *seq_off);
 
+/* The same selection straight into the packed batch of ONE reference slot (bc_bam_select_fill + bc_pack_reads
+ * in one pass: the 4-bit bases go directly to the 2-bit bit-planar words).  out6 = {n_reads, n_cigar, n_words,
+ * n_bases, aligned_bases, starts_sorted}.  Arrays: starts[n], cigar[n_cigar], cigar_off[n + 1], seq_woff[n + 1],
+ * planes[n_words], okmask[n_words] (NULL unless min_base_quality > 0), exc_read / exc_pos [exc_cap];
+ * *n_exc may exceed exc_cap (call again with room).  BC_ERR_READ_OVERRUN as bc_pack_reads. */
+int bc_bam_pack_sizes(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq, uint64_t *out6);
+int bc_bam_pack_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+                     uint32_t min_base_quality, uint32_t *starts, uint32_t *cigar, uint32_t *cigar_off,
+                     uint32_t *seq_woff, uint64_t *planes, uint32_t *okmask, uint32_t *exc_read, uint32_t *exc_pos,
+                     uint64_t exc_cap, uint64_t *n_exc);
+
 /* ---- index-aware region fetch (host code) -----------------------------------
  * The region-sharded path (config 5) gives each rank the reads that START in its region of the
  * reference (the np.linspace split of tests/test_basecount.py:146-150).  bc_bam_index_build writes

@@ -3,6 +3,7 @@ import struct
 import zlib
 
 import numpy as np
+import pytest
 
 from basecount_b200 import bamio, synth
 from basecount_b200.records import select_reads
@@ -171,3 +172,61 @@ def test_native_decoder_rejects_damaged_files(tmp_path):
             bamio.NativeBam(bad)
     with pytest.raises(ValueError):
         bamio.NativeBam(str(tmp_path / "missing.bam"))
+
+
+def _same_packed(a, b):
+    assert a.n_reads == b.n_reads and a.n_refs == b.n_refs == 1
+    for f in ("ref_read_off", "starts", "cigar_off", "cigar", "seq_woff", "planes", "exc_read", "exc_pos"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert (a.okmask is None) == (b.okmask is None)
+    if a.okmask is not None:
+        assert np.array_equal(a.okmask, b.okmask)
+    assert (a.sorted_hint, a.mean_read_len, a.aligned_bases, a.query_bases) == \
+           (b.sorted_hint, b.mean_read_len, b.aligned_bases, b.query_bases)
+
+
+def test_one_pass_native_pack_matches_select_then_pack(tmp_path):
+    """NativeBam.pack (4-bit bases straight to the 2-bit planes, one native pass) against
+    pack_batches(NativeBam.select(...)): identical arrays, including the sparse exception list, the
+    quality mask, odd-length soft clips (the packed bytes are then read at an odd nibble), IUPAC letters,
+    and the error for a CIGAR that consumes more bases than the read holds."""
+    from basecount_b200.pack import pack_batches
+    from basecount_b200.records import Records
+    rec = synth.amplicon_sample(seed=9, n_reads=3000, ref_len=4000, ref_name="chrT")
+    # a copy of the torture set without the records whose CIGAR overruns the read (those are checked below)
+    tort = _clip_torture_records()
+    cases = [rec, synth.uniform_short_read_sample(seed=3, ref_len=3000, n_reads=800, read_len=33, ref_name="u")]
+    for ci, r in enumerate(cases):
+        p = str(tmp_path / f"p{ci}.bam")
+        bamio.write_bam(p, r)
+        for threads in (1, 0):
+            nb = bamio.NativeBam(p, threads)
+            for mbq in (0, 20, 41):
+                for mmq in (0, 30):
+                    _same_packed(nb.pack(0, mmq, mbq), pack_batches([nb.select(0, mmq)], mbq))
+            a, b = r.n // 4, 3 * r.n // 4
+            _same_packed(nb.pack(0, 0, 0, a, b), pack_batches([nb.select(0, 0, a, b, want_qual=False)], 0))
+            nb.close()
+    p = str(tmp_path / "tort.bam")
+    bamio.write_bam(p, tort)
+    nb = bamio.NativeBam(p)
+    for rid in (0, 1):
+        for mbq in (0, 15):
+            try:
+                want = pack_batches([nb.select(rid, 0)], mbq)
+            except ValueError:
+                with pytest.raises(ValueError):
+                    nb.pack(rid, 0, mbq)
+                continue
+            _same_packed(nb.pack(rid, 0, mbq), want)
+    # record ranges of the torture file that hold no overrunning CIGAR must agree exactly
+    checked = 0
+    for a in range(0, nb.n - 12, 12):
+        try:
+            want = pack_batches([nb.select(0, 0, a, a + 12)], 7)
+        except ValueError:
+            continue
+        _same_packed(nb.pack(0, 0, 7, a, a + 12), want)
+        checked += 1
+    assert checked > 5
+    nb.close()

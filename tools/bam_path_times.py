@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Where the BAM-path-to-summary wall clock goes for one config-1 sample (124,000 reads x 400 bp):
-inflate + record index (bc_bam_open), selection into flat arrays, 2-bit packing, push + summarise.
+inflate + record index (bc_bam_open), selection + 2-bit packing (bc_bam_pack_*), push + summarise.
     python tools/bam_path_times.py
 """
 import os
@@ -16,7 +16,6 @@ sys.path.insert(0, ROOT)
 def main():
     from basecount_b200 import bamio, synth
     from basecount_b200.build import build
-    from basecount_b200.pack import pack_batches
     build()
     path = "/tmp/bc_bench_cfg1_seed100.bam"
     if not os.path.exists(path):
@@ -34,10 +33,9 @@ def main():
         nb = bamio.NativeBam(path)
         t1 = time.perf_counter()
         nb.core()
-        b = nb.select(0, 0, want_qual=False)             # min_base_quality 0: nothing reads the qualities
         t2 = time.perf_counter()
+        p = nb.pack(0, 0, 0)                               # selection + trimming + 2-bit packing, one native pass
         nb.close()
-        p = pack_batches([b], 0)
         t3 = time.perf_counter()
         t4 = t3
         if eng is not None:
@@ -46,7 +44,7 @@ def main():
             eng.sync()
             eng.summary(False)
             t4 = time.perf_counter()
-        print(f"open {1e3 * (t1 - t0):6.1f}  select {1e3 * (t2 - t1):6.1f}  pack {1e3 * (t3 - t2):6.1f}  "
+        print(f"open {1e3 * (t1 - t0):6.1f}  core {1e3 * (t2 - t1):6.1f}  select+pack {1e3 * (t3 - t2):6.1f}  "
               f"count+summarise {1e3 * (t4 - t3):6.1f}  total {1e3 * (t4 - t0):6.1f} ms")
 
 
