@@ -25,8 +25,10 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -37,6 +39,22 @@ namespace bcbam {
 template <class T>
 struct NoInitAlloc : std::allocator<T> {
     template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    // big buffers: 2 MB aligned and advised for transparent huge pages (512 x fewer first-touch faults)
+    T *allocate(std::size_t n)
+    {
+        const std::size_t bytes = n * sizeof(T);
+        if (bytes >= (8u << 20)) {
+            void *p = nullptr;
+            const std::size_t round = (bytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+            if (::posix_memalign(&p, 2u << 20, round) != 0 || !p) throw std::bad_alloc();
+            ::madvise(p, round, MADV_HUGEPAGE);
+            return static_cast<T *>(p);
+        }
+        void *p = std::malloc(bytes ? bytes : 1);
+        if (!p) throw std::bad_alloc();
+        return static_cast<T *>(p);
+    }
+    void deallocate(T *p, std::size_t) noexcept { std::free(p); }
     template <class U, class... A>
     void construct(U *p, A &&...a)
     {
