@@ -309,7 +309,7 @@ def bam_end_to_end(eng, with_reference):
     b = select_reads(bamio.read_bam(path), 0, 0)
     bases = b.aligned_bases()
     out = {"seconds": best, "aligned_bases": bases, "reads": int(pile.num_reads[0]), "value": bases / best, "unit": UNIT,
-           "decoder": "native (csrc/bam_decode.h: block-parallel inflate + thread-parallel select), best of 3",
+           "decoder": "native (csrc/bam_decode.h: block-parallel inflate, one pass from records to the packed batch), best of 3",
            "bam_mb": os.path.getsize(path) / 1e6}
     if with_reference:
         from oracle import bcount as obc
