@@ -41,7 +41,7 @@ UNIT = "aligned bases/s"
 SAMPLES_PER_GPU = 12
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 # DRAM bytes per K1 launch from the committed ncu capture (workload, variant, samples, reads/sample)
-NCU_TRAFFIC_BYTES = {("cfg2x12", 0, 12, 124_000): 189_081_088 + 7_133_696}
+NCU_TRAFFIC_BYTES = {("cfg2x12", 0, 12, 124_000): 190_132_480 + 7_092_736}      # capture r2g (profiles/r2_g_k1_summary.md)
 
 
 def parse():
@@ -618,7 +618,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant, args.samples_per_gpu, args.reads_per_sample)),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                       "kernel on this workload (profiles/r1_g_k1_v6_summary.md); null if not captured",
+                                       "kernel on this workload (profiles/r2_g_k1_summary.md); null if not captured",
                      "kernel": "k1_count_tiled" if args.variant == 0 else "k1_count_per_base",
                      "kernel_ms": k1_avg_ms, "algorithmic_bytes_per_launch": k1_bytes,
                      "bytes_per_aligned_base": k1_bytes / k1_bases, "kernel_aligned_bases_per_s": k1_bases / (k1_avg_ms * 1e-3),
