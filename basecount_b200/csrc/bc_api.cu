@@ -8,6 +8,7 @@
 #include "../../include/basecount_b200.h"
 #include "bc_common.cuh"
 #include "k1_count.cuh"
+#include "k1_split.cuh"
 #include "k2_stats.cuh"
 #include "k3_reduce.cuh"
 #include "bam_decode.h"
@@ -98,6 +99,7 @@ struct bc_handle {
     uint64_t k_count = 0;
     uint64_t launches = 0;
     int variant = 0;
+    int default_variant = 0;     // what variant 0 means: 0 = k1_count_tiled, 2 = k1_count_split (BASECOUNT_B200_K1=split)
 };
 
 #define CU(h, expr)                                                                              \
@@ -236,6 +238,11 @@ int bc_create(int device, bc_handle **out)
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     h->sm_count = prop.multiProcessorCount;
+    if (const char *k1 = std::getenv("BASECOUNT_B200_K1")) {       // experiments: which tiled kernel "variant 0" runs
+        if (std::strcmp(k1, "split") == 0) h->default_variant = 2;
+        else if (std::strcmp(k1, "tiled") != 0) return bail(cudaErrorInvalidValue, "BASECOUNT_B200_K1 must be tiled or split");
+        h->variant = h->default_variant;
+    }
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
     {
         // K1 is one resident wave whose three CTAs per SM hold 96 % of the register file: whatever shares
@@ -438,12 +445,24 @@ static int k1_prepare(size_t *smem, int *ctas_per_sm)
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k1_count_tiled<G, OK>, kK1Threads, *smem);
 }
 
-// Warps of the chosen K1 instance that are resident on the whole GPU at once.
+template <int G, bool OK>
+static int k1_split_prepare(size_t *smem, int *ctas_per_sm)
+{
+    *smem = (size_t)k1_split_cta_smem_bytes<G, OK>();
+    cudaError_t e = cudaFuncSetAttribute(k1_count_split<G, OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k1_count_split<G, OK>, kSplitThreads, *smem);
+}
+
+// Warps (variant 2: warp pairs) of the chosen K1 instance that are resident on the whole GPU at once.
 static int k1_resident_warps(bc_handle *h, int G, bool ok, uint32_t *out)
 {
     size_t smem = 0;
     int ctas = 0, e = 0;
-#define K1_PREP(GG) e = ok ? k1_prepare<GG, true>(&smem, &ctas) : k1_prepare<GG, false>(&smem, &ctas)
+    const bool split = h->variant == 2;
+#define K1_PREP(GG)                                                                                          \
+    e = split ? (ok ? k1_split_prepare<GG, true>(&smem, &ctas) : k1_split_prepare<GG, false>(&smem, &ctas)) \
+              : (ok ? k1_prepare<GG, true>(&smem, &ctas) : k1_prepare<GG, false>(&smem, &ctas))
     if (G == 4) K1_PREP(4);
     else if (G == 8) K1_PREP(8);
     else if (G == 16) K1_PREP(16);
@@ -453,7 +472,7 @@ static int k1_resident_warps(bc_handle *h, int G, bool ok, uint32_t *out)
         h->err = std::string("k1 occupancy query: ") + cudaGetErrorString((cudaError_t)e);
         return BC_ERR_CUDA;
     }
-    *out = (uint32_t)std::max(1, ctas) * kK1WarpsPerCta * (uint32_t)h->sm_count;
+    *out = (uint32_t)std::max(1, ctas) * (split ? kSplitPairs : kK1WarpsPerCta) * (uint32_t)h->sm_count;
     return BC_OK;
 }
 
@@ -533,6 +552,26 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     CU(h, cudaEventRecord(h->k0[ki], h->compute));
     if (h->variant == 1) {
         k1_count_per_base<<<(v.n_reads + 127) / 128, 128, 0, h->compute>>>(v, cv);
+    } else if (h->variant == 2) {
+        const unsigned grid = (n_chunks + kSplitPairs - 1) / kSplitPairs;
+        const bool ok = v.okmask != nullptr;
+        const uint32_t words_per_read = std::max<uint32_t>(1, mean_words);
+        const uint32_t rpb = std::max<uint32_t>(1, std::min<uint32_t>(kMaxRpb, (kSeqCap - 8) / words_per_read));
+#define K1S_LAUNCH(GG)                                                                                          \
+    do {                                                                                                        \
+        if (ok) {                                                                                               \
+            const size_t smem = (size_t)k1_split_cta_smem_bytes<GG, true>();                                    \
+            k1_count_split<GG, true><<<grid, kSplitThreads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb);  \
+        } else {                                                                                                \
+            const size_t smem = (size_t)k1_split_cta_smem_bytes<GG, false>();                                   \
+            k1_count_split<GG, false><<<grid, kSplitThreads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb); \
+        }                                                                                                       \
+    } while (0)
+        if (G == 4) K1S_LAUNCH(4);
+        else if (G == 8) K1S_LAUNCH(8);
+        else if (G == 16) K1S_LAUNCH(16);
+        else K1S_LAUNCH(32);
+#undef K1S_LAUNCH
     } else {
         const unsigned grid = (n_chunks + kK1WarpsPerCta - 1) / kK1WarpsPerCta;
         const bool ok = v.okmask != nullptr;
@@ -1048,8 +1087,8 @@ uint64_t bc_kernel_launches(bc_handle *h) { return h ? h->launches : 0; }
 
 int bc_set_count_variant(bc_handle *h, int variant)
 {
-    if (!h || variant < 0 || variant > 1) return BC_ERR_ARG;
-    h->variant = variant;
+    if (!h || variant < 0 || variant > 2) return BC_ERR_ARG;
+    h->variant = variant == 0 ? h->default_variant : variant;
     return BC_OK;
 }
 
