@@ -108,11 +108,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // sequence stages sit between the ring / flush rows (below) and the CIGAR stages (above), so the
 // unclamped word index of a piece (up to 64*G columns before or after its data) always lands in
 // the CTA's own shared memory; whatever it reads there is masked away.
-template <int G, bool HAS_OK>
+template <int G, bool HAS_OK, uint32_t RING = 0>
 struct K1Cfg {
     static constexpr int S = 32 / G;                        // read slots per warp
     static constexpr int Q = 4 * S;                         // ring entries consumed per trip
-    static constexpr uint32_t kRing = Q >= 32 ? 128u : 64u; // piece ring entries (uint4 each): a leftover + one block
+    static constexpr uint32_t kRing = RING ? RING : (Q >= 32 ? 128u : 64u); // piece ring entries (uint4 each): a leftover + one block
     static constexpr uint32_t kWin = 32u * kW * G;          // window columns
     static constexpr uint32_t kMaxFit = kWin - 31u;         // a piece this long fits a fresh window at any alignment
     static constexpr uint32_t kCols = kFlushStride * kW * G;   // uint16 per flush row

@@ -24,9 +24,12 @@
 namespace bc {
 
 #ifndef BC_K1S_MINCTAS
-#define BC_K1S_MINCTAS 2          // CTAs per SM the register split below is sized for
+#define BC_K1S_MINCTAS 3          // CTAs per SM the register split below is sized for: 12 warp pairs per SM
 #define BC_K1S_REG_WALK 64        // registers per thread of a walking warp
-#define BC_K1S_REG_COUNT 192      // ... of a counting warp: 4 x 32 x (64 + 192) = 256 x 128 = a CTA's launch allocation
+#define BC_K1S_REG_COUNT 96       // ... of a counting warp: 4 x 32 x (64 + 96) = 256 x 80 = a CTA's launch allocation
+#endif
+#ifndef BC_K1S_TRIPS
+#define BC_K1S_TRIPS 4            // trip slots in the ring (how far the walker may run ahead)
 #endif
 constexpr int kSplitPairs = 4;                    // setmaxnreg works on warpgroups: 4 walkers + 4 counters
 constexpr int kSplitThreads = 64 * kSplitPairs;
@@ -34,8 +37,8 @@ constexpr int kSplitMinCtas = BC_K1S_MINCTAS;
 
 template <int G, bool HAS_OK>
 struct K1SplitCfg {
-    using C = K1Cfg<G, HAS_OK>;
-    static constexpr uint32_t NS = C::kRing / (uint32_t)C::Q;      // trips the ring holds
+    static constexpr uint32_t NS = BC_K1S_TRIPS > (32 / (4 * (32 / G))) ? BC_K1S_TRIPS : 32 / (4 * (32 / G)) * 2;  // trip slots
+    using C = K1Cfg<G, HAS_OK, NS * 4u * (32u / G)>;
     static constexpr uint32_t full_off = C::warp_bytes;            // NS mbarriers: trip published
     static constexpr uint32_t empty_off = full_off + NS * 8u;      // NS mbarriers: trip consumed
     static constexpr uint32_t desc_off = empty_off + NS * 8u;      // NS x uint4 {command, new window, stage to refill + 1, -}
@@ -53,27 +56,83 @@ __host__ __device__ constexpr uint32_t k1_split_cta_smem_bytes()
 
 enum SplitCommand : uint32_t { kCmdNone = 0u, kCmdMove = 1u, kCmdEnd = 2u };
 
+// Shared-memory accessors with the region offset as an IMMEDIATE of the instruction: every address below is
+// "the pair's base + a small index", so no register holds a per-array base (the walker has 64 registers).
+template <uint32_t O> __device__ __forceinline__ uint32_t lds32o(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(O));
+    return v;
+}
+template <uint32_t O> __device__ __forceinline__ uint2 lds64o(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(O));
+    return v;
+}
+template <uint32_t O> __device__ __forceinline__ uint4 lds128o(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a), "n"(O));
+    return v;
+}
+template <uint32_t O> __device__ __forceinline__ void sts32o(uint32_t a, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(O) : "memory");
+}
+template <uint32_t O> __device__ __forceinline__ void sts64o(uint32_t a, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0+%3], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y), "n"(O) : "memory");
+}
+template <uint32_t O> __device__ __forceinline__ void sts128o(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0+%5], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "n"(O) : "memory");
+}
+template <uint32_t O> __device__ __forceinline__ void mbar_arrive_o(uint32_t a)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0+%1];" ::"r"(a), "n"(O) : "memory");
+}
+template <uint32_t O> __device__ __forceinline__ void mbar_wait_o(uint32_t a, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0+%2], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity), "n"(O)
+        : "memory");
+}
+template <uint32_t O> __device__ __forceinline__ void cp_async4o(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0+%2], [%1], 4;" ::"r"(dst), "l"(src), "n"(O) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // Masked words of one piece for a lane's two window words (the `piece` of k1_count_tiled).
-template <bool HAS_OK>
+//   e.w: the pair's base + byte offset INSIDE the sequence stages of the plane word that holds window column 0
+template <bool HAS_OK, uint32_t SEQ_OFF, uint32_t OK_OFF>
 __device__ __forceinline__ void split_piece(const uint4 e, uint32_t (&x)[kW][kNC], int L0, uint32_t lutb,
-                                            uint32_t lane_seq_off, uint32_t seqb, uint32_t okb)
+                                            uint32_t lane_seq_off, uint32_t wb)
 {
     const int a_c = __viaddmin_s32_relu((int)e.x, -L0, 64);
     const int e_c = __viaddmin_s32_relu((int)e.y, -L0, 64);
     const uint2 ga = lds64(lutb + 8u * (uint32_t)a_c), ge = lds64(lutb + 8u * (uint32_t)e_c);
     uint32_t m[kW] = {ga.x & ~ge.x, ga.y & ~ge.y};
     const uint32_t wa = e.w + lane_seq_off;
-    const uint2 r0 = lds64(wa), r1 = lds64(wa + 8u), r2 = lds64(wa + 16u);
+    const uint2 r0 = lds64o<SEQ_OFF>(wa), r1 = lds64o<SEQ_OFF + 8u>(wa), r2 = lds64o<SEQ_OFF + 16u>(wa);
     const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, e.z), __funnelshift_r(r1.x, r2.x, e.z)};
     const uint32_t hi[kW] = {__funnelshift_r(r0.y, r1.y, e.z), __funnelshift_r(r1.y, r2.y, e.z)};
     if (HAS_OK) {
-        const uint32_t oa = okb + (uint32_t)((int)(wa - seqb) >> 1);
-        const uint32_t o0 = lds32(oa), o1 = lds32(oa + 4u), o2 = lds32(oa + 8u);
+        const uint32_t oa = wb + (uint32_t)((int)(wa - wb) >> 1);
+        const uint32_t o0 = lds32o<OK_OFF>(oa), o1 = lds32o<OK_OFF + 4u>(oa), o2 = lds32o<OK_OFF + 8u>(oa);
         m[0] &= __funnelshift_r(o0, o1, e.z);
         m[1] &= __funnelshift_r(o1, o2, e.z);
     }
@@ -165,8 +224,8 @@ template <int G, bool HAS_OK>
 __global__ void __launch_bounds__(kSplitThreads, kSplitMinCtas)
 k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb)
 {
-    using C = K1Cfg<G, HAS_OK>;
     using P = K1SplitCfg<G, HAS_OK>;
+    using C = typename P::C;
     constexpr int S = C::S;
     constexpr uint32_t Q = (uint32_t)C::Q, NS = P::NS;
     constexpr uint32_t kWin = C::kWin, kRing = C::kRing;
@@ -187,16 +246,14 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     uint16_t *frow = reinterpret_cast<uint16_t *>(wsm + C::frow_off);
     const uint32_t lutb = opaque(smem_u32(k1_smem));
     const uint32_t wb = opaque(smem_u32(wsm));                                 // the pair's region
-    const uint32_t ringb = wb + C::ring_off, seqb = wb + C::seq_off, okb = wb + C::ok_off, cigb = wb + C::cig_off,
-                   barb = wb + C::bar_off, rngb = wb + C::rng_off, fullb = wb + P::full_off, emptyb = wb + P::empty_off,
-                   descb = wb + P::desc_off, metab = wb + P::meta_off;
+    static_assert(C::ring_off == 0u, "ring entries are addressed from the pair's base");
     if (!counting && lane == 0) {                                              // the walker sets up its pair's barriers
 #pragma unroll
-        for (int s = 0; s < kStages; s++) mbar_init_s(barb + 8u * s, 1);
+        for (int s = 0; s < kStages; s++) mbar_init_s(wb + C::bar_off + 8u * s, 1);
         for (uint32_t s = 0; s < NS; s++) {
-            mbar_init_s(fullb + 8u * s, 1);
-            mbar_init_s(emptyb + 8u * s, 1);
-            sts128(descb + 16u * s, make_uint4(kCmdNone, 0u, 0u, 0u));
+            mbar_init_s(wb + P::full_off + 8u * s, 1);
+            mbar_init_s(wb + P::empty_off + 8u * s, 1);
+            sts128(wb + P::desc_off + 16u * s, make_uint4(kCmdNone, 0u, 0u, 0u));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -219,7 +276,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         const int slot = lane / G, wl = lane % G;
         const int L0 = 32 * kW * wl;
         const uint32_t spb = opaque(wb + C::frow_off + 4u * (uint32_t)lane);
-        const uint32_t trip_ringb = opaque(ringb + 16u * (uint32_t)slot);
+        const uint32_t trip_ringb = opaque(wb + 16u * (uint32_t)slot);
         const uint32_t lane_seq_off = 8u * kW * (uint32_t)wl;
         uint32_t pl[kW][kNC][kNR], pa[kW][kNC], pb[kW][kNC];
 #pragma unroll
@@ -235,8 +292,8 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         uint32_t cnt = 0, win_lo = 0;
         for (uint32_t t = 0;; t++) {
             const uint32_t s = t & (NS - 1u);
-            mbar_wait_s(fullb + 8u * s, (t / NS) & 1u);
-            const uint4 d = lds128(descb + 16u * s);
+            mbar_wait_o<P::full_off>(wb + 8u * s, (t / NS) & 1u);
+            const uint4 d = lds128o<P::desc_off>(wb + 16u * s);
             if (d.x != kCmdNone || cnt == kCntMax) {                           // rare: everything but a plain trip
                 if (cnt != 0u) {
                     flush_counters<G>(pl, pa, pb, cnt, frow, plane0 + win_lo, cv.stride, lane);
@@ -251,18 +308,19 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             for (int q = 0; q < 4; q++) e[q] = lds128(ea + 16u * (uint32_t)(q * S));
             uint32_t x[4][kW][kNC];
 #pragma unroll
-            for (int q = 0; q < 4; q++) split_piece<HAS_OK>(e[q], x[q], L0, lutb, lane_seq_off, seqb, okb);
+            for (int q = 0; q < 4; q++) split_piece<HAS_OK, C::seq_off, C::ok_off>(e[q], x[q], L0, lutb, lane_seq_off, wb);
             split_trip_add(pl, pa, pb, x, cnt, spb);
             __syncwarp();                                                      // every lane is through with the trip's entries and data
             if (lane == 0) {
-                if ((d.x | d.z) != 0u) sts128(descb + 16u * s, make_uint4(kCmdNone, 0u, 0u, 0u));
+                if ((d.x | d.z) != 0u) sts128o<P::desc_off>(wb + 16u * s, make_uint4(kCmdNone, 0u, 0u, 0u));
                 if (d.z != 0u) {
                     // this was the last trip that reads stage d.z - 1: refill it with the block whose ranges the
                     // walker left beside the stage (the walker waits on the stage's own barrier as before)
                     const uint32_t stg = d.z - 1u;
-                    const uint4 rg = lds128(rngb + 16u * stg);                 // s_lo, s_n, c_lo, c_n
+                    const uint4 rg = lds128o<C::rng_off>(wb + 16u * stg);      // s_lo, s_n, c_lo, c_n
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    const uint32_t bar = barb + 8u * stg;
+                    const uint32_t bar = wb + C::bar_off + 8u * stg;
+                    const uint32_t seqb = wb + C::seq_off, okb = wb + C::ok_off, cigb = wb + C::cig_off;
                     mbar_expect_tx_s(bar, rg.y * 8u + (HAS_OK ? rg.y * 4u : 0u) + rg.w * 4u);
                     if (rg.y) {
                         bulk_g2s_s(seqb + stg * (kSeqCap * 8u), bv.planes + rg.x, rg.y * 8u, bar);
@@ -270,7 +328,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                     }
                     if (rg.w) bulk_g2s_s(cigb + stg * (kCigCap * 4u), bv.cigar + rg.z, rg.w * 4u, bar);
                 }
-                mbar_arrive_s(emptyb + 8u * s);
+                mbar_arrive_o<P::empty_off>(wb + 8u * s);
             }
             cnt += 4u;
         }
@@ -288,19 +346,19 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     // small shared-memory ring with cp.async (no register is held while the loads are in flight), three
     // blocks ahead; word l + 1 of an offset array is read l's end.
     auto fetch_meta = [&](uint32_t blk, uint32_t slot) {
-        const uint32_t a = metab + slot * 384u + 4u * (uint32_t)lane;
+        const uint32_t a = wb + slot * 384u + 4u * (uint32_t)lane;
         const uint32_t idx = rb + blk * rpb + (uint32_t)lane;
         if (blk < nblk && idx <= re) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(bv.cigar_off + idx) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a + 128u), "l"(bv.seq_woff + idx) : "memory");
+            cp_async4o<P::meta_off>(a, bv.cigar_off + idx);
+            cp_async4o<P::meta_off + 128u>(a, bv.seq_woff + idx);
             if (idx < re)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a + 256u), "l"(bv.starts + idx) : "memory");
+                cp_async4o<P::meta_off + 256u>(a, bv.starts + idx);
             else
-                sts32(a + 256u, 0u);
+                sts32o<P::meta_off + 256u>(a, 0u);
         } else {
-            sts32(a, 0u);
-            sts32(a + 128u, 0u);
-            sts32(a + 256u, 0u);
+            sts32o<P::meta_off>(a, 0u);
+            sts32o<P::meta_off + 128u>(a, 0u);
+            sts32o<P::meta_off + 256u>(a, 0u);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -313,15 +371,16 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     auto issue_block = [&](uint32_t blk, uint32_t stg, bool now) {
         if (lane == 0) {
             const uint32_t nvalid = min(rpb, re - (rb + blk * rpb));
-            const uint32_t ma = metab + stg * 384u;                  // (a block's metadata slot is its stage number)
-            const uint32_t c0 = lds32(ma), c1 = lds32(ma + 4u * nvalid);
-            const uint32_t s0 = lds32(ma + 128u), s1 = lds32(ma + 128u + 4u * nvalid);
+            const uint32_t ma = wb + stg * 384u;                     // (a block's metadata slot is its stage number)
+            const uint32_t c0 = lds32o<P::meta_off>(ma), c1 = lds32o<P::meta_off>(ma + 4u * nvalid);
+            const uint32_t s0 = lds32o<P::meta_off + 128u>(ma), s1 = lds32o<P::meta_off + 128u>(ma + 4u * nvalid);
             const uint32_t s_lo = s0 & ~3u, s_n = min(((s1 + 3u) & ~3u) - s_lo, kSeqCap);
             const uint32_t c_lo = c0 & ~3u, c_n = min(((c1 + 3u) & ~3u) - c_lo, kCigCap);
-            sts128(rngb + 16u * stg, make_uint4(s_lo, s_n, c_lo, c_n));
+            sts128o<C::rng_off>(wb + 16u * stg, make_uint4(s_lo, s_n, c_lo, c_n));
             if (now) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                const uint32_t bar = barb + 8u * stg;
+                const uint32_t bar = wb + C::bar_off + 8u * stg;
+                const uint32_t seqb = wb + C::seq_off, okb = wb + C::ok_off, cigb = wb + C::cig_off;
                 mbar_expect_tx_s(bar, s_n * 8u + (HAS_OK ? s_n * 4u : 0u) + c_n * 4u);
                 if (s_n) {
                     bulk_g2s_s(seqb + stg * (kSeqCap * 8u), bv.planes + s_lo, s_n * 8u, bar);
@@ -351,7 +410,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
 
     auto acquire_through = [&](uint32_t trip) {     // wait until trips <= trip may be written, i.e. trip - NS is consumed
         while (acq <= trip) {
-            mbar_wait_s(emptyb + 8u * (acq & (NS - 1u)), ((acq / NS) - 1u) & 1u);
+            mbar_wait_o<P::empty_off>(wb + 8u * (acq & (NS - 1u)), ((acq / NS) - 1u) & 1u);
             acq++;
         }
     };
@@ -360,21 +419,21 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         if (np != pub) {
             __syncwarp();                           // all lanes' entries (and lane 0's command) come before the arrive
             if (lane == 0)
-                for (uint32_t t = pub; t < np; t++) mbar_arrive_s(fullb + 8u * (t & (NS - 1u)));
+                for (uint32_t t = pub; t < np; t++) mbar_arrive_o<P::full_off>(wb + 8u * (t & (NS - 1u)));
             pub = np;
         }
     };
     auto open_for = [&](uint32_t n) {               // room for n more entries; a pending window move rides on their first trip
         acquire_through((tail + n - 1u) / Q);
         if (pend_move) {                            // (a move pads, so tail is a trip boundary here)
-            if (lane == 0) sts64(descb + 16u * ((tail / Q) & (NS - 1u)), make_uint2(kCmdMove, pend_lo));
+            if (lane == 0) sts64o<P::desc_off>(wb + 16u * ((tail / Q) & (NS - 1u)), make_uint2(kCmdMove, pend_lo));
             pend_move = false;
         }
     };
     auto pad = [&]() {                              // fill the open trip with empty pieces and publish it
         const uint32_t r = tail & (Q - 1u);
         if (r != 0u) {
-            if ((uint32_t)lane < Q - r) sts128(ringb + 16u * ((tail + lane) & (kRing - 1u)), make_uint4(0u, 0u, 0u, seqb));
+            if ((uint32_t)lane < Q - r) sts128(wb + 16u * ((tail + lane) & (kRing - 1u)), make_uint4(0u, 0u, 0u, wb));
             tail += Q - r;
             publish();
         }
@@ -392,23 +451,23 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     };
     auto make_entry = [&](uint32_t rel, uint32_t n, int qbit) {
         const int z = qbit - (int)rel;
-        return make_uint4(rel, rel + n, (uint32_t)z, seqb + (uint32_t)((z >> 5) * 8));
+        return make_uint4(rel, rel + n, (uint32_t)z, wb + (uint32_t)((z >> 5) * 8));
     };
 
     for (uint32_t j = 0; j < nblk; j++) {
         // this block's metadata out of its slot, then the slot goes to block j+3
-        const uint32_t ma = metab + st * 384u + 4u * (uint32_t)lane, ma1 = metab + st * 384u + 4u * (uint32_t)((lane + 1) & 31);
-        const uint32_t cbase = lds32(ma), cend_all = lds32(ma1);
-        const uint32_t wbase = lds32(ma + 128u), wend = lds32(ma1 + 128u);
-        const uint32_t start0 = lds32(ma + 256u);
+        const uint32_t ma = wb + st * 384u + 4u * (uint32_t)lane, ma1 = wb + st * 384u + 4u * (uint32_t)((lane + 1) & 31);
+        const uint32_t cbase = lds32o<P::meta_off>(ma), cend_all = lds32o<P::meta_off>(ma1);
+        const uint32_t wbase = lds32o<P::meta_off + 128u>(ma), wend = lds32o<P::meta_off + 128u>(ma1);
+        const uint32_t start0 = lds32o<P::meta_off + 256u>(ma);
         __syncwarp();
         fetch_meta(j + 3u, st);
-        mbar_wait_s(barb + 8u * st, (phases >> st) & 1u);
+        mbar_wait_o<C::bar_off>(wb + 8u * st, (phases >> st) & 1u);
         phases ^= 1u << st;
         const uint32_t nvalid = min(rpb, re - (rb + j * rpb));
         __syncwarp();
-        const uint4 rg = lds128(rngb + 16u * st);
-        const uint32_t cg = cigb + st * (kCigCap * 4u) - rg.z * 4u;
+        const uint4 rg = lds128o<C::rng_off>(wb + 16u * st);
+        const uint32_t cg = wb + st * (kCigCap * 4u) - rg.z * 4u;       // (+ C::cig_off in the loads) CIGAR word 0
         const int seg_bit0 = (int)(st * kSeqCap * 32u);
 
         // ---- per-lane read state (count.cpp:35-38)
@@ -434,9 +493,9 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             if (staged) {
                 const uint32_t ca = cg + cbase * 4u;
                 uint32_t cw[3];
-                cw[0] = ncig > 0u ? lds32(ca) : 0u;
-                cw[1] = ncig > 1u ? lds32(ca + 4u) : 0u;
-                cw[2] = ncig > 2u ? lds32(ca + 8u) : 0u;
+                cw[0] = ncig > 0u ? lds32o<C::cig_off>(ca) : 0u;
+                cw[1] = ncig > 1u ? lds32o<C::cig_off + 4u>(ca) : 0u;
+                cw[2] = ncig > 2u ? lds32o<C::cig_off + 8u>(ca) : 0u;
                 uint32_t r[4], q[4], mlen[3], dlen[3];
                 bool brk[3];
                 r[0] = rpos;
@@ -488,7 +547,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 if (mA) {
                     open_for(__popc(mA));
                     if (fitA) {
-                        sts128(ringb + 16u * ((tail + __popc(mA & lt_mask)) & (kRing - 1u)), make_entry(relA, nA, qb));
+                        sts128(wb + 16u * ((tail + __popc(mA & lt_mask)) & (kRing - 1u)), make_entry(relA, nA, qb));
                         nA = 0u;
                     }
                     tail += __popc(mA);
@@ -497,7 +556,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 if (mB) {
                     open_for(__popc(mB));
                     if (fitB) {
-                        sts128(ringb + 16u * ((tail + __popc(mB & lt_mask)) & (kRing - 1u)), make_entry(relB, nB, pqB));
+                        sts128(wb + 16u * ((tail + __popc(mB & lt_mask)) & (kRing - 1u)), make_entry(relB, nB, pqB));
                         nB = 0u;
                     }
                     tail += __popc(mB);
@@ -511,7 +570,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 // ---- F: fetch CIGAR ops until an M/=/X run is open (count.cpp:40-96)
                 bool moved = false;
                 while (rem == 0u && ds_n == 0u && cur < cend) {
-                    const uint32_t cw = (cur - rg.z) < rg.w ? lds32(cg + cur * 4u) : __ldg(bv.cigar + cur);
+                    const uint32_t cw = (cur - rg.z) < rg.w ? lds32o<C::cig_off>(cg + cur * 4u) : __ldg(bv.cigar + cur);
                     cur++;
                     moved = true;
                     const uint32_t len = cw >> 4;
@@ -552,7 +611,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 if (pm) {
                     open_for(__popc(pm));
                     if (n1) {
-                        sts128(ringb + 16u * ((tail + __popc(pm & lt_mask)) & (kRing - 1u)), make_entry(relp, n1, qb));
+                        sts128(wb + 16u * ((tail + __popc(pm & lt_mask)) & (kRing - 1u)), make_entry(relp, n1, qb));
                         rpos += n1;
                         qb += (int)n1;
                         rem -= n1;
@@ -605,8 +664,8 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 {
                     const uint32_t nw = min(seg_end - seg_w, kSeqCap);
                     for (uint32_t i = lane; i < nw; i += 32u) {
-                        sts64(seqb + (st * kSeqCap + i) * 8u, __ldg(bv.planes + seg_w + i));
-                        if (HAS_OK) sts32(okb + (st * kSeqCap + i) * 4u, __ldg(bv.okmask + seg_w + i));
+                        sts64o<C::seq_off>(wb + (st * kSeqCap + i) * 8u, __ldg(bv.planes + seg_w + i));
+                        if (HAS_OK) sts32o<C::ok_off>(wb + (st * kSeqCap + i) * 4u, __ldg(bv.okmask + seg_w + i));
                     }
                     if (lane == slow_lane) qend = seg_bit0 + (int)(nw * 32u);
                     __syncwarp();
@@ -628,7 +687,7 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
             meta_landed();
             issue_block(j + 3u, st, !open);
             if (open) {
-                if (lane == 0) sts32(descb + 16u * (pub & (NS - 1u)) + 8u, st + 1u);
+                if (lane == 0) sts32o<P::desc_off + 8u>(wb + 16u * (pub & (NS - 1u)), st + 1u);
                 refill_trip = pub;
             }
         }
@@ -640,8 +699,8 @@ k1_count_split(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     pad();
     acquire_through(pub);
     if (lane == 0) {
-        sts64(descb + 16u * (pub & (NS - 1u)), make_uint2(kCmdEnd, 0u));
-        mbar_arrive_s(fullb + 8u * (pub & (NS - 1u)));
+        sts64o<P::desc_off>(wb + 16u * (pub & (NS - 1u)), make_uint2(kCmdEnd, 0u));
+        mbar_arrive_o<P::full_off>(wb + 8u * (pub & (NS - 1u)));
     }
 }
 

@@ -56,7 +56,7 @@ def parse():
     ap.add_argument("--cfg5-reads", type=int, default=12_888_833)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gen-samples", default=None, help="internal: synthesise these sample seeds into /tmp and exit")
-    ap.add_argument("--variant", type=int, default=0, help="0 tiled bit-sliced K1, 1 per-base atomics K1")
+    ap.add_argument("--variant", type=int, default=0, help="0 tiled bit-sliced K1, 1 per-base atomics K1, 2 tiled K1 with walk and count in different warps")
     return ap.parse_args()
 
 
@@ -619,7 +619,7 @@ def main():
                      "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant, args.samples_per_gpu, args.reads_per_sample)),
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
                                        "kernel on this workload (profiles/r2_g_k1_summary.md); null if not captured",
-                     "kernel": "k1_count_tiled" if args.variant == 0 else "k1_count_per_base",
+                     "kernel": {0: "k1_count_tiled", 1: "k1_count_per_base", 2: "k1_count_split"}[args.variant],
                      "kernel_ms": k1_avg_ms, "algorithmic_bytes_per_launch": k1_bytes,
                      "bytes_per_aligned_base": k1_bytes / k1_bases, "kernel_aligned_bases_per_s": k1_bases / (k1_avg_ms * 1e-3),
                      "peak_source": peak_src},

@@ -44,7 +44,7 @@ def test_reference_kats_through_bcount():
             assert bcount(*args) == case["counts"]
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])      # tiled (default), per-base atomics, walk / count in different warps
 @pytest.mark.parametrize("mbq", [0, 20, 40])
 def test_fuzz_vs_oracle(eng, mbq, variant):
     for seed in range(40, 52):
@@ -61,6 +61,20 @@ def test_group_widths_vs_oracle(eng, read_len, n_reads, mbq):
     b = select_reads(rec, 0, 0)
     got = gpu_counts(eng, b, [20000], mbq)[0]
     assert np.array_equal(got, oracle_counts(b, 20000, mbq))
+
+
+@pytest.mark.parametrize("read_len,n_reads", [(150, 6000), (400, 4000), (1000, 1500), (5000, 300)])
+def test_split_kernel_vs_oracle(eng, read_len, n_reads):
+    """Count variant 2 (csrc/k1_split.cuh): every group width, quality masks on and off, the sample-batch shape."""
+    rec = synth.uniform_short_read_sample(seed=read_len + 1, ref_len=20000, n_reads=n_reads, read_len=read_len, ref_name="x")
+    b = select_reads(rec, 0, 0)
+    for mbq in (0, 20):
+        got = gpu_counts(eng, b, [20000], mbq, variant=2)[0]
+        assert np.array_equal(got, oracle_counts(b, 20000, mbq)), mbq
+    amp = [select_reads(synth.amplicon_sample(seed=40 + s, n_reads=9000, ref_len=6000, ref_name="x"), 0, 0) for s in range(3)]
+    got = gpu_counts(eng, amp, [6000] * 3, 0, variant=2)
+    for s in range(3):
+        assert np.array_equal(got[s], oracle_counts(amp[s], 6000)), s
 
 
 def test_amplicon_shapes_and_filter_matrix(eng):
