@@ -43,6 +43,9 @@ namespace bc {
 #define BC_K1_WARPS 4
 #define BC_K1_MINCTAS 3
 #endif
+#ifndef BC_K1_META_SMEM
+#define BC_K1_META_SMEM 0       // 1: block metadata through cp.async into a shared-memory ring instead of registers
+#endif
 constexpr int kK1WarpsPerCta = BC_K1_WARPS;
 constexpr int kK1MinCtas = BC_K1_MINCTAS;
 constexpr int kK1Threads = kK1WarpsPerCta * 32;
@@ -125,7 +128,8 @@ struct K1Cfg {
     static constexpr uint32_t cig_off = ok_off + (HAS_OK ? kStages * kSeqCap * 4u : 0u);
     static constexpr uint32_t bar_off = cig_off + kStages * kCigCap * 4u;
     static constexpr uint32_t rng_off = bar_off + 32u;      // per stage: what it holds (uint4)
-    static constexpr uint32_t warp_bytes = rng_off + kStages * 16u;
+    static constexpr uint32_t meta_off = rng_off + kStages * 16u;   // BC_K1_META_SMEM: kStages x {cigar_off, seq_woff, start} x 32 lanes
+    static constexpr uint32_t warp_bytes = meta_off + (BC_K1_META_SMEM ? kStages * 384u : 0u);
     static constexpr uint32_t cta_bytes = lut_bytes + kK1WarpsPerCta * warp_bytes;
     static_assert(seq_off % 16 == 0 && ok_off % 16 == 0 && cig_off % 16 == 0 && bar_off % 16 == 0 && warp_bytes % 16 == 0,
                   "TMA destinations are 16-byte aligned");
@@ -406,6 +410,59 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     }
     __syncwarp();
 
+#if BC_K1_META_SMEM
+    // ---- block metadata: {cigar_off, seq_woff, start} of block b go to slot b % kStages of a small shared-memory
+    //      ring with cp.async (no register is held while the loads are in flight), three blocks ahead; word l + 1
+    //      of an offset array is read l's end.  A block's metadata slot is its stage number.
+    const uint32_t metab = wb + C::meta_off;
+    auto fetch_meta = [&](uint32_t blk, uint32_t slot) {
+        const uint32_t a = metab + slot * 384u + 4u * (uint32_t)lane;
+        const uint32_t idx = rb + blk * rpb + (uint32_t)lane;         // (the host keeps n_reads < 2^32 - 64)
+        if (blk < nblk && idx <= re) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(bv.cigar_off + idx) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a + 128u), "l"(bv.seq_woff + idx) : "memory");
+            if (idx < re)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a + 256u), "l"(bv.starts + idx) : "memory");
+            else
+                sts32(a + 256u, 0u);
+        } else {
+            sts32(a, 0u);
+            sts32(a + 128u, 0u);
+            sts32(a + 256u, 0u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto meta_landed = [&]() {                      // every lane's copies are done and visible to the warp
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+    };
+    auto issue_block = [&](uint32_t blk, uint32_t stg) {
+        if (lane == 0) {
+            const uint32_t nvalid = min(rpb, re - (rb + blk * rpb));
+            const uint32_t ma = metab + stg * 384u;
+            const uint32_t c0 = lds32(ma), c1 = lds32(ma + 4u * nvalid);
+            const uint32_t s0 = lds32(ma + 128u), s1 = lds32(ma + 128u + 4u * nvalid);
+            const uint32_t s_lo = s0 & ~3u, s_n = min(((s1 + 3u) & ~3u) - s_lo, kSeqCap);     // 32 B / 16 B aligned sources
+            const uint32_t c_lo = c0 & ~3u, c_n = min(((c1 + 3u) & ~3u) - c_lo, kCigCap);
+            sts128(rngb + 16u * stg, make_uint4(s_lo, s_n, c_lo, c_n));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this stage
+            const uint32_t bar = barb + 8u * stg;
+            mbar_expect_tx_s(bar, s_n * 8u + (HAS_OK ? s_n * 4u : 0u) + c_n * 4u);
+            if (s_n) {
+                bulk_g2s_s(seqb + stg * (kSeqCap * 8u), bv.planes + s_lo, s_n * 8u, bar);
+                if (HAS_OK) bulk_g2s_s(okb + stg * (kSeqCap * 4u), bv.okmask + s_lo, s_n * 4u, bar);
+            }
+            if (c_n) bulk_g2s_s(cigb + stg * (kCigCap * 4u), bv.cigar + c_lo, c_n * 4u, bar);
+        }
+    };
+    fetch_meta(0, 0);
+    fetch_meta(1, 1);
+    fetch_meta(2, 2);
+    meta_landed();
+    issue_block(0, 0);
+    if (nblk > 1) issue_block(1, 1);
+    if (nblk > 2) issue_block(2, 2);
+#else
     // ---- block metadata: lane l holds read (block_first + l); lane l+1's offsets are read l's ends
     struct Meta { uint32_t start, cbase, wbase; };
     auto load_meta = [&](uint32_t blk) {
@@ -443,6 +500,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     issue_block(0, m0, 0);
     if (nblk > 1) issue_block(1, m1, 1);
     if (nblk > 2) issue_block(2, m2, 2);
+#endif
     uint32_t phases = 0;                            // bit s: parity to wait for on stage s
     uint32_t st = 0;                                // stage of the current block
 
@@ -498,7 +556,18 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     // same (single) trip / flush code as everything else.
     for (uint32_t j = 0; j <= nblk; j++) {
         const bool last = (j == nblk);
+#if BC_K1_META_SMEM
+        // this block's metadata out of its slot, then the slot goes to block j+3
+        meta_landed();
+        const uint32_t ma = metab + st * 384u + 4u * (uint32_t)lane, ma1 = metab + st * 384u + 4u * (uint32_t)((lane + 1) & 31);
+        const uint32_t cbase = lds32(ma), cend_all = lds32(ma1);
+        const uint32_t wbase = lds32(ma + 128u), wend = lds32(ma1 + 128u);
+        const uint32_t start0 = lds32(ma + 256u);
+        __syncwarp();
+        fetch_meta(j + 3u, st);
+#else
         const Meta m4 = load_meta(j + 4u);                           // rotated in at the end of this block
+#endif
         uint32_t nvalid = 0;
         uint4 rg = make_uint4(0u, 0u, 0u, 0u);                       // s_lo, s_n, c_lo, c_n of this stage
         if (!last) {
@@ -513,13 +582,16 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
 
         // ---- per-lane read state (count.cpp:35-38)
         const bool valid = (uint32_t)lane < nvalid;
+#if !BC_K1_META_SMEM
         const uint32_t cbase = m0.cbase, cend_all = __shfl_down_sync(kFull, m0.cbase, 1);
         const uint32_t wbase = m0.wbase, wend = __shfl_down_sync(kFull, m0.wbase, 1);
+        const uint32_t start0 = m0.start;
+#endif
         const bool staged = valid && (wend - rg.x) <= rg.y;
         const bool cig_staged = (cend_all - rg.z) <= rg.w;           // this read's CIGAR words are in shared memory
         uint32_t unst = __ballot_sync(kFull, valid && !staged && cend_all > cbase);   // reads to stage by hand
         uint32_t cur = cbase, cend = staged ? cend_all : cbase;
-        uint32_t rpos = min(m0.start, ref_len), rem = 0u, ds_pos = 0u, ds_n = 0u;
+        uint32_t rpos = min(start0, ref_len), rem = 0u, ds_pos = 0u, ds_n = 0u;
         int qb = seg_bit0 + (int)((wbase - rg.x) * 32u);             // bit index of the next read base
         int qend = qb + (int)((wend - wbase) * 32u);                 // end of the staged data of this read
         bool issue_pending = (j >= 1u) && (j + 2u < nblk);           // block j+2 goes into block j-1's stage
@@ -801,7 +873,11 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 cnt += 4u;
             }
             if (issue_pending && (int)(ring_head - mark) >= 0) {     // block j-1's pieces are all counted
+#if BC_K1_META_SMEM
+                issue_block(j + 2u, st == 0u ? 2u : st - 1u);        // (its metadata landed before this block started)
+#else
                 issue_block(j + 2u, m2, st == 0u ? 2u : st - 1u);
+#endif
                 issue_pending = false;
             }
             if (action == 1) {
@@ -836,7 +912,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 if (lane == slow_lane) {
                     cur = cbase;
                     cend = cend_all;
-                    rpos = min(m0.start, ref_len);
+                    rpos = min(start0, ref_len);
                     rem = 0u;
                     qb = seg_bit0;
                 }
@@ -855,10 +931,12 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         // ---- rotate the pipelines
         mark = ring_tail;
         st = (st == (uint32_t)kStages - 1u) ? 0u : st + 1u;
+#if !BC_K1_META_SMEM
         m0 = m1;
         m1 = m2;
         m2 = m3;
         m3 = m4;
+#endif
     }
 }
 

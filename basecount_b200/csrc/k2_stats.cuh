@@ -200,7 +200,10 @@ struct SummaryPartial {
 // Partials per slot: a fixed function of the slot length (-> deterministic reduction order): one CTA per
 // kSummaryPerCta positions (4 per thread: one resident wave for a batch of viral samples), up to kSummaryMaxBlocks CTAs per slot.
 constexpr int kSummaryMaxBlocks = 2048;
-constexpr uint32_t kSummaryPerCta = 1024;
+#ifndef BC_K2_PER_CTA
+#define BC_K2_PER_CTA 1024
+#endif
+constexpr uint32_t kSummaryPerCta = BC_K2_PER_CTA;
 __host__ __device__ inline uint32_t summary_blocks(uint32_t ref_len)
 {
     const uint32_t b = (ref_len + kSummaryPerCta - 1u) / kSummaryPerCta;
