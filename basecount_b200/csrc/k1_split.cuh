@@ -28,6 +28,9 @@ namespace bc {
 #define BC_K1S_REG_WALK 64        // registers per thread of a walking warp
 #define BC_K1S_REG_COUNT 96       // ... of a counting warp: 4 x 32 x (64 + 96) = 256 x 80 = a CTA's launch allocation
 #endif
+#ifndef BC_K1S_WAIT_HINT
+#define BC_K1S_WAIT_HINT 0        // > 0: suspend-time hint (ns) of the barrier waits instead of a plain spin
+#endif
 #ifndef BC_K1S_TRIPS
 #define BC_K1S_TRIPS 4            // trip slots in the ring (how far the walker may run ahead)
 #endif
@@ -94,6 +97,19 @@ template <uint32_t O> __device__ __forceinline__ void mbar_arrive_o(uint32_t a)
 }
 template <uint32_t O> __device__ __forceinline__ void mbar_wait_o(uint32_t a, uint32_t parity)
 {
+#if BC_K1S_WAIT_HINT > 0
+    asm volatile(                                     // the waiting warp may sleep up to the hint (ns) per attempt
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0+%2], %1, %3;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity), "n"(O), "n"(BC_K1S_WAIT_HINT)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -105,6 +121,7 @@ template <uint32_t O> __device__ __forceinline__ void mbar_wait_o(uint32_t a, ui
         "}\n" ::"r"(a),
         "r"(parity), "n"(O)
         : "memory");
+#endif
 }
 template <uint32_t O> __device__ __forceinline__ void cp_async4o(uint32_t dst, const void *src)
 {
