@@ -162,3 +162,59 @@ def test_region_shards_and_halos_add_up(r, world):
         part = obc.bcount_flat(hi - lo + h, 0, local)          # raises if the halo were too small
         merged[lo:hi + h] += part
     assert n == batch.n and np.array_equal(merged, whole)
+
+
+# ----------------------------------------------------------------------------- statistics, against the reference live
+def reference_get_stats():
+    """get_stats of the unmodified reference (main.py:14-79), imported from where it lies when this container has
+    it; `import pysam` / `from count import bcount` (main.py:2,5) are satisfied by stand-ins for the import only."""
+    import os
+    import sys
+    import types
+    if not os.path.exists("/root/reference/basecount/main.py"):
+        return None
+    saved = {k: sys.modules.get(k) for k in ("pysam", "count")}
+    stub = types.ModuleType("pysam")
+    stub.set_verbosity = lambda v: 0
+    cnt = types.ModuleType("count")
+    cnt.bcount = compiled_reference()
+    sys.modules["pysam"], sys.modules["count"] = stub, cnt
+    sys.path.insert(0, "/root/reference")
+    try:
+        import basecount.main as refmain
+        fn = refmain.get_stats
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [m for m in sys.modules if m == "basecount" or m.startswith("basecount.")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return fn
+
+
+_GET_STATS = []
+
+count_rows = st.lists(st.lists(st.one_of(st.integers(0, 6), st.integers(0, 3000), st.integers(0, 2 ** 40)),
+                               min_size=6, max_size=6), min_size=1, max_size=8)
+
+
+@settings(max_examples=300, **SETTINGS)
+@given(count_rows, st.booleans(), st.booleans())
+def test_stats_oracle_matches_reference_get_stats(rows6, show_n, long_format):
+    """oracle/stats.py against the reference's own get_stats on arbitrary count rows: same values bit for bit
+    and the same Python types (the int sentinels -1 / 1 / 1 of zero-coverage positions print differently)."""
+    from conftest import typed_equal
+    from oracle import stats as ost
+    if not _GET_STATS:
+        _GET_STATS.append(reference_get_stats())
+    get_stats = _GET_STATS[0]
+    if get_stats is None:
+        pytest.skip("/root/reference is not mounted here")
+    want = get_stats([list(r) for r in rows6], "ref", show_n, long_format)      # (get_stats pops from its input)
+    got = ost.rows(rows6, "ref", show_n, long_format)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert typed_equal(a, b), (a, b)
