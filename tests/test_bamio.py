@@ -230,3 +230,64 @@ def test_one_pass_native_pack_matches_select_then_pack(tmp_path):
         checked += 1
     assert checked > 5
     nb.close()
+
+
+# ----------------------------------------------------------------------------- random records (hypothesis)
+def _random_records(draw):
+    from hypothesis import strategies as st
+    from basecount_b200.records import Records
+    letters = np.frombuffer(b"ACGTNRYKMSWBDHV=", dtype=np.uint8)
+    n = draw(st.integers(0, 12))
+    ref_id, pos, mapq, flag, cigar, coff, seq, qual, soff = [], [], [], [], [], [0], [], [], [0]
+    for _ in range(n):
+        lead = draw(st.lists(st.tuples(st.sampled_from([4, 5]), st.integers(0, 9)), max_size=2))
+        body = draw(st.lists(st.tuples(st.sampled_from([0, 1, 2, 3, 6, 7, 8]), st.integers(0, 35)), max_size=5))
+        tail = draw(st.lists(st.tuples(st.sampled_from([4, 5]), st.integers(0, 9)), max_size=2))
+        ct = lead + body + tail
+        qn = sum(l for o, l in ct if o in (0, 1, 4, 7, 8))
+        if draw(st.integers(0, 9)) == 0:
+            qn = 0                                        # SEQ '*'
+        mapped = draw(st.integers(0, 7)) != 0
+        ref_id.append(draw(st.integers(0, 1)) if mapped or draw(st.booleans()) else -1)
+        pos.append(draw(st.integers(0, 600)))
+        mapq.append(draw(st.integers(0, 60)))
+        flag.append(0 if mapped else 4)
+        cigar += [(l << 4) | o for o, l in ct]
+        coff.append(len(cigar))
+        idx = draw(st.lists(st.integers(0, letters.size - 1), min_size=qn, max_size=qn))
+        seq.append(letters[np.asarray(idx, dtype=np.int64)] if qn else np.zeros(0, np.uint8))
+        if qn and draw(st.integers(0, 5)) == 0:
+            qual.append(np.full(qn, 0xFF, np.uint8))      # QUAL '*'
+        else:
+            qual.append(np.asarray(draw(st.lists(st.integers(0, 60), min_size=qn, max_size=qn)), dtype=np.uint8))
+        soff.append(soff[-1] + qn)
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.uint8)
+    return Records(["r0", "r1"], [1000, 700], np.asarray(ref_id, np.int32), np.asarray(pos, np.int32),
+                   np.asarray(mapq, np.uint8), np.asarray(flag, np.uint16), np.asarray(cigar, np.uint32),
+                   np.asarray(coff, np.int64), cat(seq), cat(qual), np.asarray(soff, np.int64))
+
+
+def test_random_records_roundtrip_and_native_selection(tmp_path):
+    """Arbitrary clip layouts, op mixes, missing SEQ / QUAL, unmapped records: writer -> numpy reader gives the
+    records back, and the native decoder's filter + soft-clip trimming agrees with the numpy path."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+    p = str(tmp_path / "h.bam")
+
+    @settings(max_examples=80, deadline=None, derandomize=True,
+              suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large, HealthCheck.function_scoped_fixture])
+    @given(st.composite(_random_records)())
+    def run(rec):
+        bamio.write_bam(p, rec)
+        back = bamio.read_bam(p)
+        _same(rec, back)
+        nb = bamio.NativeBam(p, 2)
+        try:
+            assert nb.n == rec.n
+            for rid in (0, 1):
+                for mmq in (0, 30):
+                    _same_batch(nb.select(rid, mmq), select_reads(back, rid, mmq))
+        finally:
+            nb.close()
+
+    run()
