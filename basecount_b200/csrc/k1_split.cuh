@@ -12,12 +12,16 @@
 //   * the counting warp (warps 4..7) owns the bit-sliced counters, consumes the ring one trip at a
 //     time and flushes (setmaxnreg.inc takes the registers the walkers gave back).
 // The two meet in the same shared-memory ring k1_count_tiled uses, cut into NS = ring / Q trip slots
-// with a full / empty mbarrier pair per slot.  Window moves and the end of the chunk travel in band:
-// a command word per trip slot ("flush, then this window" / "flush and leave"), written by the walker
-// before it publishes the first trip of the new window.  The walker refills a TMA stage only after
-// the counting warp has finished the last trip that reads it (it waits on that slot's empty barrier).
+// with a full / empty mbarrier pair per slot.  Window moves, the end of the chunk and the stage refills
+// travel in band: a 16-byte descriptor per trip slot ("flush, then this window" / "flush and leave" /
+// "after this trip refill stage s"), written by the walker before it publishes the trip.  A TMA stage is
+// refilled by the COUNTING warp the moment the last trip that reads it is in registers, from the ranges the
+// walker left beside the stage; the walker only waits for ring space and for its own stage's data.
+// Block metadata reaches the walker through cp.async into a small shared-memory ring, and every
+// shared-memory access is "pair base + index" with the array offset as an instruction immediate.
 //
 // Semantics are those of k1_count_tiled (same decode, same pieces, same flush); only who runs them changed.
+// Measured: bit-exact, 103-107 us against 90 us on the bench workload (profiles/r3_b_k1_split_summary.md).
 #pragma once
 #include "k1_count.cuh"
 
@@ -126,11 +130,6 @@ template <uint32_t O> __device__ __forceinline__ void mbar_wait_o(uint32_t a, ui
 template <uint32_t O> __device__ __forceinline__ void cp_async4o(uint32_t dst, const void *src)
 {
     asm volatile("cp.async.ca.shared.global [%0+%2], [%1], 4;" ::"r"(dst), "l"(src), "n"(O) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_s(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // Masked words of one piece for a lane's two window words (the `piece` of k1_count_tiled).
