@@ -16,6 +16,9 @@
 
 #if defined(__SSE2__)
 #include <emmintrin.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #endif
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -34,6 +37,106 @@
 #include <vector>
 
 namespace bcbam {
+
+// CRC-32 of a BGZF block's payload (RFC 1952, the gzip polynomial, reflected).  zlib's table-driven crc32 runs at
+// ~1.3 GB/s per thread, a quarter of what a block costs to open next to zlib's inflate; folding with carry-less
+// multiplies (Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ", the 4 x 128-bit
+// fold zlib-ng / Chromium use) runs an order of magnitude faster.  Used when the CPU has PCLMULQDQ; zlib's
+// crc32 finishes the tail and is the fallback (and the reference tests/test_bamio.py holds this to).
+#if defined(__x86_64__)
+__attribute__((target("pclmul,sse4.1"))) inline uint32_t crc32_fold_clmul(const uint8_t *buf, size_t len, uint32_t crc)
+{
+    // len >= 64 and a multiple of 16; crc comes in and goes out in the register convention (bit-inverted)
+    alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};     // x^(512+-32) mod P, fold by 4
+    alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};     // x^(128+-32) mod P, fold by 1
+    alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0x0000000000ull};     // x^64 mod P
+    alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};     // P and the Barrett constant
+    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+    x1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x00));
+    x2 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x10));
+    x3 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x20));
+    x4 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x30));
+    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+    x0 = _mm_load_si128(reinterpret_cast<const __m128i *>(k1k2));
+    buf += 64;
+    len -= 64;
+    while (len >= 64) {
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+        x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+        x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+        x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+        x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+        y5 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x00));
+        y6 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x10));
+        y7 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x20));
+        y8 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf + 0x30));
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
+        x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
+        x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+        buf += 64;
+        len -= 64;
+    }
+    x0 = _mm_load_si128(reinterpret_cast<const __m128i *>(k3k4));       // four lanes -> one
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+    while (len >= 16) {
+        x2 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(buf));
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+        buf += 16;
+        len -= 16;
+    }
+    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);                            // 128 -> 64 bits
+    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+    x1 = _mm_srli_si128(x1, 8);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_loadl_epi64(reinterpret_cast<const __m128i *>(k5k0));
+    x2 = _mm_srli_si128(x1, 4);
+    x1 = _mm_and_si128(x1, x3);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_load_si128(reinterpret_cast<const __m128i *>(poly));       // Barrett reduction to 32 bits
+    x2 = _mm_and_si128(x1, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+    x2 = _mm_and_si128(x2, x3);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#endif
+
+inline uint32_t crc32_fast(const uint8_t *p, size_t n)
+{
+    uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
+#if defined(__x86_64__)
+    static const bool have = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+    if (have && n >= 64) {
+        const size_t m = n & ~(size_t)15;
+        crc = ~crc32_fold_clmul(p, m, ~crc);
+        p += m;
+        n -= m;
+    }
+#endif
+    while (n) {                                           // (zlib takes a 32-bit length)
+        const uInt step = (uInt)std::min<size_t>(n, 1u << 30);
+        crc = (uint32_t)crc32(crc, p, step);
+        p += step;
+        n -= step;
+    }
+    return crc;
+}
 // Byte buffers that are NOT zero-filled on resize: a 150 MB memset (and its page faults, on one thread) cost
 // as much as the parallel inflate that overwrites every byte; the inflating threads touch the pages instead.
 template <class T>
@@ -251,7 +354,7 @@ inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::st
             zs.avail_out = k.isize;
             const int rc = inflate(&zs, Z_FINISH);
             if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                (uint32_t)crc32(crc32(0L, Z_NULL, 0), b->raw.data() + k.u0, k.isize) != k.crc)
+                crc32_fast(b->raw.data() + k.u0, k.isize) != k.crc)
                 bad = 1;
         }
         inflateEnd(&zs);

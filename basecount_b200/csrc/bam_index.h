@@ -124,7 +124,7 @@ inline bool inflate_blocks(int threads, const ByteVec &src, const std::vector<Bl
             zs.avail_out = k.isize;
             const int rc = inflate(&zs, Z_FINISH);
             if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + (k.u0 - dst_u0), k.isize) != k.crc)
+                bcbam::crc32_fast(dst + (k.u0 - dst_u0), k.isize) != k.crc)
                 bad = 1;
         }
         inflateEnd(&zs);

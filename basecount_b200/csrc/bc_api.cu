@@ -1226,6 +1226,8 @@ static thread_local std::string g_bam_err;
 
 extern "C" {
 
+uint32_t bc_bgzf_crc32(const uint8_t *data, uint64_t n) { return data || n == 0 ? bcbam::crc32_fast(data, (size_t)n) : 0u; }
+
 int bc_bam_open(const char *path, int threads, bc_bam **out)
 {
     if (!path || !out) return BC_ERR_ARG;

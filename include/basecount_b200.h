@@ -212,6 +212,9 @@ typedef struct bc_bam bc_bam;
 /* threads <= 0: one per host core (at most 32).  Errors: bc_bam_last_error() (thread-local text). */
 int bc_bam_open(const char *path, int threads, bc_bam **out);
 const char *bc_bam_last_error(void);
+/* The CRC-32 every BGZF block is checked with on the way in (RFC 1952; carry-less-multiply folding where the
+ * CPU has it, zlib's crc32 otherwise).  Exported so the decoder's check can be held to zlib's on any bytes. */
+uint32_t bc_bgzf_crc32(const uint8_t *data, uint64_t n);
 void bc_bam_close(bc_bam *b);
 uint64_t bc_bam_num_records(const bc_bam *b);
 uint32_t bc_bam_num_refs(const bc_bam *b);

@@ -291,3 +291,19 @@ def test_random_records_roundtrip_and_native_selection(tmp_path):
             nb.close()
 
     run()
+
+
+def test_block_crc_matches_zlib():
+    """bc_bgzf_crc32 (carry-less-multiply folding where the CPU has PCLMULQDQ) against zlib.crc32: every length
+    around the 16- and 64-byte steps of the fold, unaligned starts, one BGZF-sized block, a few MB."""
+    from basecount_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    assert L.bc_bgzf_crc32(None, 0) == zlib.crc32(b"")
+    big = rng.integers(0, 256, size=(3 << 20) + 77, dtype=np.uint8)
+    for n in list(range(1, 260)) + [1023, 4095, 4096, 65279, 65280, 65281, big.size - 3]:
+        for off in (0, 1, 3):
+            d = np.ascontiguousarray(big[off:off + n])
+            assert L.bc_bgzf_crc32(_lib.ptr(d), d.size) == zlib.crc32(d.tobytes()), (n, off)
+    z = np.zeros(100_000, dtype=np.uint8)
+    assert L.bc_bgzf_crc32(_lib.ptr(z), z.size) == zlib.crc32(z.tobytes())
