@@ -88,6 +88,7 @@ _SIGNATURES = {
     "bc_bam_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "bc_bam_last_error": (ctypes.c_char_p, []),
     "bc_bgzf_crc32": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_uint64]),
+    "bc_inflate_raw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64]),
     "bc_bam_pack_sizes": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint32,
                                          ctypes.c_void_p]),
     "bc_bam_pack_fill": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint32,

@@ -19,6 +19,7 @@
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
+#include "inflate_fast.h"
 #endif
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -136,6 +137,31 @@ inline uint32_t crc32_fast(const uint8_t *p, size_t n)
         n -= step;
     }
     return crc;
+}
+
+// One BGZF block: inflate `in` into dst[0, isize) and check the block's CRC-32.  The table-driven decoder of
+// inflate_fast.h goes first (1.4-1.6 x zlib on BAM payloads); zlib decides whenever it declines or the CRC differs,
+// so what counts as a valid block is exactly what zlib accepts.  `in` is followed by the block's 8-byte trailer.
+// BASECOUNT_B200_INFLATE=zlib switches the first decoder off (A/B runs).
+inline bool fast_inflate_enabled()
+{
+    static const bool on = [] {
+        const char *e = std::getenv("BASECOUNT_B200_INFLATE");
+        return !(e && std::strcmp(e, "zlib") == 0);
+    }();
+    return on;
+}
+inline bool inflate_block_checked(FastInflater *fi, z_stream *zs, const uint8_t *in, size_t in_len, uint8_t *dst,
+                                  uint32_t isize, uint32_t crc)
+{
+    if (fi && fi->inflate(in, in_len, dst, isize) && crc32_fast(dst, isize) == crc) return true;
+    inflateReset(zs);
+    zs->next_in = const_cast<Bytef *>(in);
+    zs->avail_in = (uInt)in_len;
+    zs->next_out = dst;
+    zs->avail_out = isize;
+    const int rc = inflate(zs, Z_FINISH);
+    return rc == Z_STREAM_END && zs->avail_out == 0 && crc32_fast(dst, isize) == crc;
 }
 // Byte buffers that are NOT zero-filled on resize: a 150 MB memset (and its page faults, on one thread) cost
 // as much as the parallel inflate that overwrites every byte; the inflating threads touch the pages instead.
@@ -344,18 +370,11 @@ inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::st
             bad = 1;
             return;
         }
+        std::unique_ptr<FastInflater> fi(fast_inflate_enabled() ? new FastInflater() : nullptr);
         for (uint64_t i = a; i < e; i++) {
             const Block &k = blocks[i];
             if (k.isize == 0) continue;
-            inflateReset(&zs);
-            zs.next_in = const_cast<Bytef *>(file + k.c0);
-            zs.avail_in = (uInt)(k.c1 - k.c0);
-            zs.next_out = b->raw.data() + k.u0;
-            zs.avail_out = k.isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                crc32_fast(b->raw.data() + k.u0, k.isize) != k.crc)
-                bad = 1;
+            if (!inflate_block_checked(fi.get(), &zs, file + k.c0, k.c1 - k.c0, b->raw.data() + k.u0, k.isize, k.crc)) bad = 1;
         }
         inflateEnd(&zs);
     });

@@ -114,17 +114,11 @@ inline bool inflate_blocks(int threads, const ByteVec &src, const std::vector<Bl
             bad = 1;
             return;
         }
+        std::unique_ptr<FastInflater> fi(fast_inflate_enabled() ? new FastInflater() : nullptr);
         for (uint64_t i = a + x; i < a + y; i++) {
             const Block &k = blocks[i];
             if (k.isize == 0) continue;
-            inflateReset(&zs);
-            zs.next_in = const_cast<Bytef *>(src.data() + k.c0);
-            zs.avail_in = (uInt)(k.c1 - k.c0);
-            zs.next_out = dst + (k.u0 - dst_u0);
-            zs.avail_out = k.isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
-                bcbam::crc32_fast(dst + (k.u0 - dst_u0), k.isize) != k.crc)
+            if (!inflate_block_checked(fi.get(), &zs, src.data() + k.c0, k.c1 - k.c0, dst + (k.u0 - dst_u0), k.isize, k.crc))
                 bad = 1;
         }
         inflateEnd(&zs);

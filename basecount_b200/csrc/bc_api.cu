@@ -1228,6 +1228,15 @@ extern "C" {
 
 uint32_t bc_bgzf_crc32(const uint8_t *data, uint64_t n) { return data || n == 0 ? bcbam::crc32_fast(data, (size_t)n) : 0u; }
 
+int bc_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_len)
+{
+    if ((!in && in_len) || (!out && out_len)) return 0;
+    std::vector<uint8_t> padded((size_t)in_len + 16, 0);            // the decoder may read 8 bytes past the stream
+    if (in_len) std::memcpy(padded.data(), in, (size_t)in_len);
+    std::unique_ptr<bcbam::FastInflater> fi(new bcbam::FastInflater());
+    return fi->inflate(padded.data(), (size_t)in_len, out, (size_t)out_len) ? 1 : 0;
+}
+
 int bc_bam_open(const char *path, int threads, bc_bam **out)
 {
     if (!path || !out) return BC_ERR_ARG;

@@ -215,6 +215,10 @@ const char *bc_bam_last_error(void);
 /* The CRC-32 every BGZF block is checked with on the way in (RFC 1952; carry-less-multiply folding where the
  * CPU has it, zlib's crc32 otherwise).  Exported so the decoder's check can be held to zlib's on any bytes. */
 uint32_t bc_bgzf_crc32(const uint8_t *data, uint64_t n);
+/* The block decoder that runs before zlib (csrc/inflate_fast.h), on its own: raw DEFLATE `in` -> exactly
+ * out_len bytes.  Returns 1 if it produced them, 0 if it declined (the readers then let zlib decide).
+ * Exported so it can be held to zlib on arbitrary streams, valid and damaged. */
+int bc_inflate_raw(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_len);
 void bc_bam_close(bc_bam *b);
 uint64_t bc_bam_num_records(const bc_bam *b);
 uint32_t bc_bam_num_refs(const bc_bam *b);
