@@ -8,7 +8,7 @@
 #include "../../include/basecount_b200.h"
 #include "bc_common.cuh"
 #include "k1_count.cuh"
-#include "k1_split.cuh"
+#include "k1_fast.cuh"
 #include "k2_stats.cuh"
 #include "k3_reduce.cuh"
 #include "bam_decode.h"
@@ -39,6 +39,7 @@ struct DevBuf {
 
 struct Staging {                 // device copies of one host batch
     DevBuf ref_read_off, starts, cigar_off, cigar, seq_woff, planes, okmask, exc_read, exc_pos, chunks;
+    DevBuf deferred;             // chunks k1_count_fast leaves to the general walker (device-written)
     Chunk *h_chunks = nullptr;   // pinned
     size_t h_chunks_cap = 0;
     cudaEvent_t copied = nullptr, done = nullptr, checked = nullptr;   // checked: the overflow check (side stream) is over
@@ -98,8 +99,12 @@ struct bc_handle {
     cudaEvent_t k0[kHist] = {}, k1[kHist] = {};
     uint64_t k_count = 0;
     uint64_t launches = 0;
-    int variant = 0;
-    int default_variant = 0;     // what variant 0 means: 0 = k1_count_tiled, 2 = k1_count_split (BASECOUNT_B200_K1=split)
+    int variant = 0;             // 0 = k1_count_fast + general walker for what it defers, 1 = per-base atomics, 2 = walker only
+    int default_variant = 0;     // what variant 0 means (BASECOUNT_B200_K1=walker makes it 2)
+    uint32_t *d_defer_ctrl = nullptr;     // {deferred chunks, walker warps that are done}; the walker resets both
+    int walker_ctas_per_sm = 1;           // grid of the walker behind k1_count_fast: 1 until a batch deferred a lot
+    int walker_max_ctas = 1;              // its occupancy limit
+    uint64_t reads_since_sync = 0;
 };
 
 #define CU(h, expr)                                                                              \
@@ -182,7 +187,7 @@ static void release(DevBuf &b)
 static void release_staging(Staging &s)
 {
     release(s.ref_read_off); release(s.starts); release(s.cigar_off); release(s.cigar); release(s.seq_woff);
-    release(s.planes); release(s.okmask); release(s.exc_read); release(s.exc_pos); release(s.chunks);
+    release(s.planes); release(s.okmask); release(s.exc_read); release(s.exc_pos); release(s.chunks); release(s.deferred);
     if (s.h_chunks) cudaFreeHost(s.h_chunks);
     s.h_chunks = nullptr;
     s.h_chunks_cap = 0;
@@ -239,8 +244,8 @@ int bc_create(int device, bc_handle **out)
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     h->sm_count = prop.multiProcessorCount;
     if (const char *k1 = std::getenv("BASECOUNT_B200_K1")) {       // experiments: which tiled kernel "variant 0" runs
-        if (std::strcmp(k1, "split") == 0) h->default_variant = 2;
-        else if (std::strcmp(k1, "tiled") != 0) return bail(cudaErrorInvalidValue, "BASECOUNT_B200_K1 must be tiled or split");
+        if (std::strcmp(k1, "walker") == 0) h->default_variant = 2;
+        else if (std::strcmp(k1, "fast") != 0) return bail(cudaErrorInvalidValue, "BASECOUNT_B200_K1 must be fast or walker");
         h->variant = h->default_variant;
     }
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
@@ -274,6 +279,8 @@ int bc_create(int device, bc_handle **out)
     }
     if ((e = cudaMalloc(&h->d_status, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(h->d_status, 0, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMalloc(&h->d_defer_ctrl, 2 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(h->d_defer_ctrl, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMalloc(&h->d_log2_tab, kSummaryTabDoubles * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc");
     k_fill_log2<<<(kSummaryTabDoubles + 255) / 256, 256, 0, h->compute>>>(h->d_log2_tab);
     if ((e = cudaStreamSynchronize(h->compute)) != cudaSuccess) return bail(e, "k_fill_log2");
@@ -307,6 +314,7 @@ void bc_destroy(bc_handle *h)
     if (h->d_col_base) cudaFree(h->d_col_base);
     if (h->d_ref_len) cudaFree(h->d_ref_len);
     if (h->d_status) cudaFree(h->d_status);
+    if (h->d_defer_ctrl) cudaFree(h->d_defer_ctrl);
     if (h->d_log2_tab) cudaFree(h->d_log2_tab);
     if (h->h_status) cudaFreeHost(h->h_status);
     for (cudaEvent_t ev : {h->t0, h->t1})
@@ -446,23 +454,27 @@ static int k1_prepare(size_t *smem, int *ctas_per_sm)
 }
 
 template <int G, bool OK>
-static int k1_split_prepare(size_t *smem, int *ctas_per_sm)
+static int k1_fast_prepare(size_t *smem, int *ctas_per_sm)
 {
-    *smem = (size_t)k1_split_cta_smem_bytes<G, OK>();
-    cudaError_t e = cudaFuncSetAttribute(k1_count_split<G, OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+    *smem = (size_t)k1_fast_cta_smem_bytes<G, OK>();
+    cudaError_t e = cudaFuncSetAttribute(k1_count_fast<G, OK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k1_count_split<G, OK>, kSplitThreads, *smem);
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k1_count_fast<G, OK>, kK1Threads, *smem);
 }
 
-// Warps (variant 2: warp pairs) of the chosen K1 instance that are resident on the whole GPU at once.
-static int k1_resident_warps(bc_handle *h, int G, bool ok, uint32_t *out)
+// Warps of the chosen K1 instance that are resident on the whole GPU at once (variant 0 also prepares the walker
+// that runs behind k1_count_fast and reports its occupancy in *walker_ctas).
+static int k1_resident_warps(bc_handle *h, int G, bool ok, uint32_t *out, int *walker_ctas = nullptr)
 {
     size_t smem = 0;
-    int ctas = 0, e = 0;
-    const bool split = h->variant == 2;
-#define K1_PREP(GG)                                                                                          \
-    e = split ? (ok ? k1_split_prepare<GG, true>(&smem, &ctas) : k1_split_prepare<GG, false>(&smem, &ctas)) \
-              : (ok ? k1_prepare<GG, true>(&smem, &ctas) : k1_prepare<GG, false>(&smem, &ctas))
+    int ctas = 0, wctas = 0, e = 0;
+    const bool fast = h->variant == 0;
+#define K1_PREP(GG)                                                                                             \
+    do {                                                                                                        \
+        e = ok ? k1_prepare<GG, true>(&smem, &wctas) : k1_prepare<GG, false>(&smem, &wctas);                    \
+        ctas = wctas;                                                                                           \
+        if (e == 0 && fast) e = ok ? k1_fast_prepare<GG, true>(&smem, &ctas) : k1_fast_prepare<GG, false>(&smem, &ctas); \
+    } while (0)
     if (G == 4) K1_PREP(4);
     else if (G == 8) K1_PREP(8);
     else if (G == 16) K1_PREP(16);
@@ -472,7 +484,8 @@ static int k1_resident_warps(bc_handle *h, int G, bool ok, uint32_t *out)
         h->err = std::string("k1 occupancy query: ") + cudaGetErrorString((cudaError_t)e);
         return BC_ERR_CUDA;
     }
-    *out = (uint32_t)std::max(1, ctas) * (split ? kSplitPairs : kK1WarpsPerCta) * (uint32_t)h->sm_count;
+    if (walker_ctas) *walker_ctas = std::max(1, wctas);
+    *out = (uint32_t)std::max(1, ctas) * kK1WarpsPerCta * (uint32_t)h->sm_count;
     return BC_OK;
 }
 
@@ -512,8 +525,13 @@ static int validate_batch(bc_handle *h, const bc_batch *b)
 }
 
 // Launch K1 (+ corrections, + exact overflow check) for a batch whose arrays are in HBM.
+static uint32_t fast_reads_per_block(uint32_t mean_words)
+{
+    return std::max<uint32_t>(1, std::min<uint32_t>(kFastRpbMax, (kSeqCap - 8) / std::max<uint32_t>(1, mean_words)));
+}
+
 static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks, uint32_t n_chunks, int G,
-                        uint32_t mean_words)
+                        uint32_t mean_words, Chunk *d_deferred)
 {
     if (v.n_reads == 0) return BC_OK;
     // uint32 counters cannot wrap while fewer than 2^32 reads went in since the last fold
@@ -528,6 +546,7 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
         h->reads_since_fold = 0;
     }
     h->reads_since_fold += v.n_reads;
+    h->reads_since_sync += v.n_reads;
 
     CountView cv;
     cv.counts = h->d_counts;
@@ -552,46 +571,41 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     CU(h, cudaEventRecord(h->k0[ki], h->compute));
     if (h->variant == 1) {
         k1_count_per_base<<<(v.n_reads + 127) / 128, 128, 0, h->compute>>>(v, cv);
-    } else if (h->variant == 2) {
-        const unsigned grid = (n_chunks + kSplitPairs - 1) / kSplitPairs;
-        const bool ok = v.okmask != nullptr;
-        const uint32_t words_per_read = std::max<uint32_t>(1, mean_words);
-        const uint32_t rpb = std::max<uint32_t>(1, std::min<uint32_t>(kMaxRpb, (kSeqCap - 8) / words_per_read));
-#define K1S_LAUNCH(GG)                                                                                          \
-    do {                                                                                                        \
-        if (ok) {                                                                                               \
-            const size_t smem = (size_t)k1_split_cta_smem_bytes<GG, true>();                                    \
-            k1_count_split<GG, true><<<grid, kSplitThreads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb);  \
-        } else {                                                                                                \
-            const size_t smem = (size_t)k1_split_cta_smem_bytes<GG, false>();                                   \
-            k1_count_split<GG, false><<<grid, kSplitThreads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb); \
-        }                                                                                                       \
-    } while (0)
-        if (G == 4) K1S_LAUNCH(4);
-        else if (G == 8) K1S_LAUNCH(8);
-        else if (G == 16) K1S_LAUNCH(16);
-        else K1S_LAUNCH(32);
-#undef K1S_LAUNCH
     } else {
         const unsigned grid = (n_chunks + kK1WarpsPerCta - 1) / kK1WarpsPerCta;
         const bool ok = v.okmask != nullptr;
         // reads per staging block: a block's plane words must fit one pipeline stage
         const uint32_t words_per_read = std::max<uint32_t>(1, mean_words);
         const uint32_t rpb = std::max<uint32_t>(1, std::min<uint32_t>(kMaxRpb, (kSeqCap - 8) / words_per_read));
-#define K1_LAUNCH(GG)                                                                                          \
-    do {                                                                                                       \
-        if (ok) {                                                                                              \
-            const size_t smem = (size_t)k1_cta_smem_bytes<GG, true>();                      \
-            k1_count_tiled<GG, true><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb);  \
-        } else {                                                                                               \
-            const size_t smem = (size_t)k1_cta_smem_bytes<GG, false>();                      \
-            k1_count_tiled<GG, false><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb); \
-        }                                                                                                      \
+        const uint32_t rpb_fast = fast_reads_per_block(mean_words);
+        const bool fast = h->variant == 0;
+        // variant 0: k1_count_fast takes every block of reads its straight-line decode can and defers the rest, as
+        // chunks, to a list in HBM; the general walker runs right behind it over that list (a fixed grid striding
+        // over a device-side count: with nothing deferred it is an empty launch).
+        const unsigned wgrid = (unsigned)(h->sm_count * std::max(1, h->walker_ctas_per_sm));
+#define K1_LAUNCH(GG, OKK)                                                                                              \
+    do {                                                                                                                \
+        const size_t wsmem = (size_t)k1_cta_smem_bytes<GG, OKK>();                                                      \
+        if (fast) {                                                                                                     \
+            const size_t smem = (size_t)k1_fast_cta_smem_bytes<GG, OKK>();                                              \
+            k1_count_fast<GG, OKK><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb_fast, d_deferred, \
+                                                                            h->d_defer_ctrl);                           \
+            k1_count_tiled<GG, OKK><<<wgrid, kK1Threads, wsmem, h->compute>>>(v, cv, d_deferred, 0u, rpb, h->d_defer_ctrl); \
+            h->launches++;                                                                                              \
+        } else {                                                                                                        \
+            k1_count_tiled<GG, OKK><<<grid, kK1Threads, wsmem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb, nullptr);   \
+        }                                                                                                               \
     } while (0)
-        if (G == 4) K1_LAUNCH(4);
-        else if (G == 8) K1_LAUNCH(8);
-        else if (G == 16) K1_LAUNCH(16);
-        else K1_LAUNCH(32);
+#define K1_LAUNCH_G(GG)                 \
+    do {                                \
+        if (ok) K1_LAUNCH(GG, true);    \
+        else K1_LAUNCH(GG, false);      \
+    } while (0)
+        if (G == 4) K1_LAUNCH_G(4);
+        else if (G == 8) K1_LAUNCH_G(8);
+        else if (G == 16) K1_LAUNCH_G(16);
+        else K1_LAUNCH_G(32);
+#undef K1_LAUNCH_G
 #undef K1_LAUNCH
     }
     CU(h, cudaEventRecord(h->k1[ki], h->compute));
@@ -633,7 +647,7 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
     G = 32;
     mean_words = 1;
     if (n == 0) return BC_OK;
-    if (n > 0xFFFFFFFFu - 64u) return fail(h, BC_ERR_ARG, "too many reads in one batch");
+    if (n > 0xFFFFFFFFu - 256u) return fail(h, BC_ERR_ARG, "too many reads in one batch");
     if (b->ref_read_off[0] != 0 || b->ref_read_off[b->n_refs] != n)
         return fail(h, BC_ERR_ARG, "ref_read_off must start at 0 and end at n_reads");
     for (uint32_t r = 0; r < b->n_refs; r++)
@@ -647,9 +661,11 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
 
     std::vector<Chunk> chunks;
     uint32_t target_warps = 0;
-    int rc0 = k1_resident_warps(h, G, b->okmask != nullptr, &target_warps);
+    int rc0 = k1_resident_warps(h, G, b->okmask != nullptr, &target_warps, &h->walker_max_ctas);
     if (rc0) return rc0;
     n_chunks = build_chunks(h, b->ref_read_off, n, target_warps, chunks);
+    // room for every run of blocks k1_count_fast may defer (at worst every other block of every chunk)
+    if ((rc0 = ensure(h, st.deferred, ((size_t)n / fast_reads_per_block(mean_words) + n_chunks + 16) * sizeof(Chunk)))) return rc0;
     if (n_chunks > st.h_chunks_cap) {
         if (st.h_chunks) CU(h, cudaFreeHost(st.h_chunks));
         st.h_chunks = nullptr;
@@ -699,7 +715,8 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
         if (id == 0 || id > h->resident.size() || !h->resident[id - 1] || !h->resident[id - 1]->live)
             return fail(h, BC_ERR_ARG, "on_device batch was not created by bc_batch_upload on this handle");
         Resident *r = h->resident[id - 1];
-        return launch_count(h, r->view, (const Chunk *)r->st.chunks.p, r->n_chunks, r->G, r->mean_words);
+        return launch_count(h, r->view, (const Chunk *)r->st.chunks.p, r->n_chunks, r->G, r->mean_words,
+                            (Chunk *)r->st.deferred.p);
     }
     Staging &st = h->stage[h->pushes & 1];
     h->pushes++;
@@ -714,7 +731,7 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
     if ((rc = stage_batch(h, st, b, view, n_chunks, G, mean_words))) return rc;
     CU(h, cudaEventRecord(st.copied, h->copy));
     CU(h, cudaStreamWaitEvent(h->compute, st.copied, 0));
-    rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G, mean_words);
+    rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G, mean_words, (Chunk *)st.deferred.p);
     CU(h, cudaEventRecord(st.done, h->compute));
     CU(h, cudaEventRecord(st.checked, h->side));
     st.used = true;
@@ -734,6 +751,15 @@ int bc_sync(bc_handle *h)
     CU(h, cudaMemcpyAsync(h->h_status, h->d_status, kStatWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
     deliver_summaries(h);
+    {
+        // size the walker's grid for the next batches from what this one deferred: one CTA per SM while nearly
+        // everything takes the fast kernel (an empty launch then), full occupancy once an eighth of the reads do not
+        const uint64_t deferred = h->h_status[kStatDeferredReads];
+        h->walker_ctas_per_sm = (deferred * 8u > h->reads_since_sync) ? h->walker_max_ctas : 1;
+        h->reads_since_sync = 0;
+        if (deferred && !h->h_status[kStatIndexError] && !h->h_status[kStatMaybeOverflow])
+            CU(h, cudaMemsetAsync(h->d_status, 0, kStatWords * sizeof(uint32_t), h->compute));
+    }
     if (h->h_status[kStatIndexError]) {
         CU(h, cudaMemsetAsync(h->d_status, 0, kStatWords * sizeof(uint32_t), h->compute));
         return fail(h, BC_ERR_INDEX, "alignment counted past the end of the reference (std::out_of_range in count.cpp)");

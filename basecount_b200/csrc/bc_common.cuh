@@ -18,6 +18,7 @@ constexpr uint32_t kColAlign = 128;
 enum StatusWord : int {
     kStatMaybeOverflow = 0,   // an M/=/X piece crossed ref_len: run the exact check
     kStatIndexError = 1,      // a counted event at refPos >= ref_len  (count.cpp .at())
+    kStatDeferredReads = 2,   // reads k1_count_fast left to the general walker (diagnostic; sizes the walker's grid)
     kStatWords = 4
 };
 

@@ -352,6 +352,113 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity)
         : "memory");
 }
 
+// Masked words of one ring entry (a piece) for a lane's two window words.  e.x / e.y = first / end column of the
+// piece relative to the window, e.z = bit index of window column 0 in the staged data (only its low 5 bits, the
+// funnel-shift amount, are used), e.w = shared address of the plane word that holds window column 0.
+template <bool HAS_OK>
+__device__ __forceinline__ void piece_words(const uint4 e, uint32_t (&x)[kW][kNC], int L0, uint32_t lutb,
+                                            uint32_t lane_seq_off, uint32_t seqb, uint32_t okb)
+{
+    const int a_c = __viaddmin_s32_relu((int)e.x, -L0, 64);      // clamp(first - L0, 0, 64), one VIADDMNMX
+    const int e_c = __viaddmin_s32_relu((int)e.y, -L0, 64);
+    const uint2 ga = lds64(lutb + 8u * (uint32_t)a_c), ge = lds64(lutb + 8u * (uint32_t)e_c);
+    uint32_t m[kW] = {ga.x & ~ge.x, ga.y & ~ge.y};
+    const uint32_t wa = e.w + lane_seq_off;
+    const uint2 r0 = lds64(wa), r1 = lds64(wa + 8u), r2 = lds64(wa + 16u);
+    const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, e.z), __funnelshift_r(r1.x, r2.x, e.z)};
+    const uint32_t hi[kW] = {__funnelshift_r(r0.y, r1.y, e.z), __funnelshift_r(r1.y, r2.y, e.z)};
+    if (HAS_OK) {
+        const uint32_t oa = okb + (uint32_t)((int)(wa - seqb) >> 1);
+        const uint32_t o0 = lds32(oa), o1 = lds32(oa + 4u), o2 = lds32(oa + 8u);
+        m[0] &= __funnelshift_r(o0, o1, e.z);
+        m[1] &= __funnelshift_r(o1, o2, e.z);
+    }
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+        x[w][0] = lo[w] & m[w];
+        x[w][1] = hi[w] & m[w];
+        x[w][2] = lo[w] & hi[w] & m[w];
+        x[w][3] = m[w];
+    }
+}
+
+// One trip of the vertical counters: four masked inputs per counter go through carry-save levels 0 and 1 every
+// trip, level 2 every 2nd, level 3 every 4th and level 4 (with planes 5..7 in shared memory) every 8th trip.
+// cnt = pieces per slot counted since the last flush (a multiple of 4, < kCntMax); the caller adds 4 afterwards.
+__device__ __forceinline__ void csa_trip(uint32_t (&x)[4][kW][kNC], uint32_t (&pl)[kW][kNC][kNR], uint32_t (&pa)[kW][kNC],
+                                         uint32_t (&pb)[kW][kNC], uint32_t cnt, uint32_t spb)
+{
+    uint32_t c2[kW][kNC];
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+#pragma unroll
+        for (int k = 0; k < kNC; k++) {
+            const uint32_t c1a = maj3(pl[w][k][0], x[0][w][k], x[1][w][k]);
+            const uint32_t t = pl[w][k][0] ^ x[0][w][k] ^ x[1][w][k];
+            const uint32_t c1b = maj3(t, x[2][w][k], x[3][w][k]);
+            pl[w][k][0] = t ^ x[2][w][k] ^ x[3][w][k];
+            c2[w][k] = maj3(pl[w][k][1], c1a, c1b);
+            pl[w][k][1] ^= c1a ^ c1b;
+        }
+    }
+    if (!(cnt & 4u)) {
+#pragma unroll
+        for (int w = 0; w < kW; w++)
+#pragma unroll
+            for (int k = 0; k < kNC; k++) pa[w][k] = c2[w][k];
+    } else {
+        uint32_t c3[kW][kNC];
+#pragma unroll
+        for (int w = 0; w < kW; w++) {
+#pragma unroll
+            for (int k = 0; k < kNC; k++) {
+                c3[w][k] = maj3(pl[w][k][2], pa[w][k], c2[w][k]);
+                pl[w][k][2] ^= pa[w][k] ^ c2[w][k];
+            }
+        }
+        if (!(cnt & 8u)) {
+#pragma unroll
+            for (int w = 0; w < kW; w++)
+#pragma unroll
+                for (int k = 0; k < kNC; k++) pb[w][k] = c3[w][k];
+        } else {
+            uint32_t c4[kW][kNC];
+#pragma unroll
+            for (int w = 0; w < kW; w++) {
+#pragma unroll
+                for (int k = 0; k < kNC; k++) {
+                    c4[w][k] = maj3(pl[w][k][3], pb[w][k], c3[w][k]);
+                    pl[w][k][3] ^= pb[w][k] ^ c3[w][k];
+                }
+            }
+            if (!(cnt & 16u)) {                           // every 8th trip: park the weight-16 carry
+#pragma unroll
+                for (int w = 0; w < kW; w++)
+#pragma unroll
+                    for (int k = 0; k < kNC; k++) sts32(spb + 128u * (uint32_t)((w * kNC + k) * 4), c4[w][k]);
+            } else {                                      // every 8th trip: planes 5..7 in shared memory
+                const bool have = cnt >= 32u;             // (they were never written before trip 8)
+#pragma unroll
+                for (int w = 0; w < kW; w++) {
+#pragma unroll
+                    for (int k = 0; k < kNC; k++) {
+                        const uint32_t qa = spb + 128u * (uint32_t)((w * kNC + k) * 4);
+                        const uint32_t pcv = lds32(qa);
+                        uint32_t c = maj3(pl[w][k][4], pcv, c4[w][k]);
+                        pl[w][k][4] ^= pcv ^ c4[w][k];
+#pragma unroll
+                        for (int p = 1; p < 4; p++) {     // ripple the weight-32 carry upwards
+                            const uint32_t v = have ? lds32(qa + 128u * p) : 0u;
+                            sts32(qa + 128u * p, v ^ c);
+                            c &= v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // The counting kernel.  One warp = one chunk of consecutive reads, processed in blocks of
 // `rpb` <= 31 reads, one read per lane.
 template <int G, bool HAS_OK>
@@ -360,7 +467,8 @@ __global__ void __maxnreg__(BC_K1_MAXNREG)
 #else
 __global__ void __launch_bounds__(kK1Threads, kK1MinCtas)
 #endif
-k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb)
+k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb,
+               const uint32_t *__restrict__ n_chunks_dev)
 {
     using C = K1Cfg<G, HAS_OK>;
     constexpr int S = C::S, Q = C::Q;
@@ -378,8 +486,13 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         lut[v] = make_uint2(v < 32 ? 0xFFFFFFFFu << v : 0u, v <= 32 ? 0xFFFFFFFFu : (v < 64 ? 0xFFFFFFFFu << (v - 32) : 0u));
     __syncthreads();                                // the only CTA-wide barrier: warps are independent from here on
 
+    // n_chunks_dev != nullptr: the chunk list was written by an earlier kernel (k1_count_fast defers the blocks its
+    // straight-line decode does not take) and its length lives in device memory; the grid is then a fixed number of
+    // warps that stride over the list.  Otherwise one chunk per warp.
     const uint32_t warp_id = blockIdx.x * kK1WarpsPerCta + warp_in_cta;
-    if (warp_id >= n_chunks) return;
+    if (n_chunks_dev) n_chunks = __ldcg(n_chunks_dev);
+    else if (warp_id >= n_chunks) return;
+    const uint32_t warp_stride = gridDim.x * kK1WarpsPerCta;
 
     unsigned char *wsm = k1_smem + C::lut_bytes + (size_t)warp_in_cta * C::warp_bytes;
     uint16_t *frow = reinterpret_cast<uint16_t *>(wsm + C::frow_off);          // flush only
@@ -395,20 +508,22 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     const uint32_t trip_ringb = opaque(ringb + 16u * (uint32_t)slot);          // ring entry of this slot in a trip
     const uint32_t lane_seq_off = 8u * kW * (uint32_t)wl;                      // byte offset of this lane's window words
 
-    const Chunk ch = chunks[warp_id];
-    const uint32_t ref_len = ch.ref_len;
-    const uint32_t rb = ch.read_begin, re = ch.read_end;
-    if (re <= rb) return;
-    const uint32_t nblk = (re - rb + rpb - 1) / rpb;
-    uint32_t *const plane0 = cv.counts + ch.col_base;                       // plane A, column 0 of this slot
-    uint32_t *const ds_plane = plane0 + (uint64_t)kPlaneDS * cv.stride;
-
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; s++) mbar_init_s(barb + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    uint32_t phases = 0;                            // bit s: parity to wait for on stage s (persists across chunks)
+
+    for (uint32_t chunk_id = warp_id; chunk_id < n_chunks; chunk_id += warp_stride) {
+    const Chunk ch = chunks[chunk_id];
+    const uint32_t ref_len = ch.ref_len;
+    const uint32_t rb = ch.read_begin, re = ch.read_end;
+    if (re <= rb) continue;
+    const uint32_t nblk = (re - rb + rpb - 1) / rpb;
+    uint32_t *const plane0 = cv.counts + ch.col_base;                       // plane A, column 0 of this slot
+    uint32_t *const ds_plane = plane0 + (uint64_t)kPlaneDS * cv.stride;
 
 #if BC_K1_META_SMEM
     // ---- block metadata: {cigar_off, seq_woff, start} of block b go to slot b % kStages of a small shared-memory
@@ -501,7 +616,6 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
     if (nblk > 1) issue_block(1, m1, 1);
     if (nblk > 2) issue_block(2, m2, 2);
 #endif
-    uint32_t phases = 0;                            // bit s: parity to wait for on stage s
     uint32_t st = 0;                                // stage of the current block
 
     // ---- warp-uniform state that persists across blocks
@@ -527,30 +641,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         const int z = qbit - (int)rel;
         return make_uint4(rel, rel + n, (uint32_t)z, seqb + (uint32_t)((z >> 5) * 8));
     };
-    // Masked words of one piece for this lane's two window words.
-    auto piece = [&](const uint4 e, uint32_t (&x)[kW][kNC]) {
-        const int a_c = __viaddmin_s32_relu((int)e.x, -L0, 64);      // clamp(first - L0, 0, 64), one VIADDMNMX
-        const int e_c = __viaddmin_s32_relu((int)e.y, -L0, 64);
-        const uint2 ga = lds64(lutb + 8u * (uint32_t)a_c), ge = lds64(lutb + 8u * (uint32_t)e_c);
-        uint32_t m[kW] = {ga.x & ~ge.x, ga.y & ~ge.y};
-        const uint32_t wa = e.w + lane_seq_off;
-        const uint2 r0 = lds64(wa), r1 = lds64(wa + 8u), r2 = lds64(wa + 16u);
-        const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, e.z), __funnelshift_r(r1.x, r2.x, e.z)};
-        const uint32_t hi[kW] = {__funnelshift_r(r0.y, r1.y, e.z), __funnelshift_r(r1.y, r2.y, e.z)};
-        if (HAS_OK) {
-            const uint32_t oa = okb + (uint32_t)((int)(wa - seqb) >> 1);
-            const uint32_t o0 = lds32(oa), o1 = lds32(oa + 4u), o2 = lds32(oa + 8u);
-            m[0] &= __funnelshift_r(o0, o1, e.z);
-            m[1] &= __funnelshift_r(o1, o2, e.z);
-        }
-#pragma unroll
-        for (int w = 0; w < kW; w++) {
-            x[w][0] = lo[w] & m[w];
-            x[w][1] = hi[w] & m[w];
-            x[w][2] = lo[w] & hi[w] & m[w];
-            x[w][3] = m[w];
-        }
-    };
+    auto piece = [&](const uint4 e, uint32_t (&x)[kW][kNC]) { piece_words<HAS_OK>(e, x, L0, lutb, lane_seq_off, seqb, okb); };
 
     // j == nblk is a virtual empty block: it drains the ring and does the final flush in the
     // same (single) trip / flush code as everything else.
@@ -801,75 +892,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
                 uint32_t x[4][kW][kNC];
 #pragma unroll
                 for (int q = 0; q < 4; q++) piece(e[q], x[q]);
-                uint32_t c2[kW][kNC];
-#pragma unroll
-                for (int w = 0; w < kW; w++) {
-#pragma unroll
-                    for (int k = 0; k < kNC; k++) {
-                        const uint32_t c1a = maj3(pl[w][k][0], x[0][w][k], x[1][w][k]);
-                        const uint32_t t = pl[w][k][0] ^ x[0][w][k] ^ x[1][w][k];
-                        const uint32_t c1b = maj3(t, x[2][w][k], x[3][w][k]);
-                        pl[w][k][0] = t ^ x[2][w][k] ^ x[3][w][k];
-                        c2[w][k] = maj3(pl[w][k][1], c1a, c1b);
-                        pl[w][k][1] ^= c1a ^ c1b;
-                    }
-                }
-                if (!(cnt & 4u)) {
-#pragma unroll
-                    for (int w = 0; w < kW; w++)
-#pragma unroll
-                        for (int k = 0; k < kNC; k++) pa[w][k] = c2[w][k];
-                } else {
-                    uint32_t c3[kW][kNC];
-#pragma unroll
-                    for (int w = 0; w < kW; w++) {
-#pragma unroll
-                        for (int k = 0; k < kNC; k++) {
-                            c3[w][k] = maj3(pl[w][k][2], pa[w][k], c2[w][k]);
-                            pl[w][k][2] ^= pa[w][k] ^ c2[w][k];
-                        }
-                    }
-                    if (!(cnt & 8u)) {
-#pragma unroll
-                        for (int w = 0; w < kW; w++)
-#pragma unroll
-                            for (int k = 0; k < kNC; k++) pb[w][k] = c3[w][k];
-                    } else {
-                        uint32_t c4[kW][kNC];
-#pragma unroll
-                        for (int w = 0; w < kW; w++) {
-#pragma unroll
-                            for (int k = 0; k < kNC; k++) {
-                                c4[w][k] = maj3(pl[w][k][3], pb[w][k], c3[w][k]);
-                                pl[w][k][3] ^= pb[w][k] ^ c3[w][k];
-                            }
-                        }
-                        if (!(cnt & 16u)) {                           // every 8th trip: park the weight-16 carry
-#pragma unroll
-                            for (int w = 0; w < kW; w++)
-#pragma unroll
-                                for (int k = 0; k < kNC; k++) sts32(spb + 128u * (uint32_t)((w * kNC + k) * 4), c4[w][k]);
-                        } else {                                      // every 8th trip: planes 5..7 in shared memory
-                            const bool have = cnt >= 32u;             // (they were never written before trip 8)
-#pragma unroll
-                            for (int w = 0; w < kW; w++) {
-#pragma unroll
-                                for (int k = 0; k < kNC; k++) {
-                                    const uint32_t qa = spb + 128u * (uint32_t)((w * kNC + k) * 4);
-                                    const uint32_t pcv = lds32(qa);
-                                    uint32_t c = maj3(pl[w][k][4], pcv, c4[w][k]);
-                                    pl[w][k][4] ^= pcv ^ c4[w][k];
-#pragma unroll
-                                    for (int p = 1; p < 4; p++) {     // ripple the weight-32 carry upwards
-                                        const uint32_t v = have ? lds32(qa + 128u * p) : 0u;
-                                        sts32(qa + 128u * p, v ^ c);
-                                        c &= v;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
+                csa_trip(x, pl, pa, pb, cnt, spb);
                 cnt += 4u;
             }
             if (issue_pending && (int)(ring_head - mark) >= 0) {     // block j-1's pieces are all counted
@@ -937,6 +960,17 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         m2 = m3;
         m3 = m4;
 #endif
+    }
+    __syncwarp();
+    }   // chunk loop
+    if (n_chunks_dev && lane == 0) {
+        // the last warp to get here empties the list for the next launch (everything is stream-ordered)
+        uint32_t *ctrl = const_cast<uint32_t *>(n_chunks_dev);
+        __threadfence();
+        if (atomicAdd(ctrl + 1, 1u) == warp_stride - 1u) {
+            ctrl[0] = 0u;
+            ctrl[1] = 0u;
+        }
     }
 }
 

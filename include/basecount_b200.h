@@ -194,9 +194,10 @@ int bc_last_count_kernel_ms(bc_handle *h, float *ms);
  * Returns how many were written, or -1. */
 int bc_count_kernel_ms_history(bc_handle *h, float *ms, int n);
 uint64_t bc_kernel_launches(bc_handle *h);
-/* Debug / cross-check: 0 = tiled bit-sliced kernel (default), 1 = one-thread-per-read
- * per-base atomics, 2 = the tiled kernel with the CIGAR walk and the counting in different
- * warps (csrc/k1_split.cuh, experimental; BASECOUNT_B200_K1=split makes it what 0 selects).
+/* Debug / cross-check: 0 = the lean bit-sliced kernel (csrc/k1_fast.cuh; straight-line decode of reads with
+ * at most three CIGAR ops) followed by the general walker (csrc/k1_count.cuh) over the blocks it deferred
+ * (default), 1 = one-thread-per-read per-base atomics, 2 = the general walker alone
+ * (BASECOUNT_B200_K1=walker makes it what 0 selects).
  * All are CUDA; there is no host path.  Set it before bc_batch_upload: a resident batch keeps
  * the chunking of the variant it was uploaded under. */
 int bc_set_count_variant(bc_handle *h, int variant);

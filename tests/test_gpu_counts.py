@@ -44,7 +44,7 @@ def test_reference_kats_through_bcount():
             assert bcount(*args) == case["counts"]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])      # tiled (default), per-base atomics, walk / count in different warps
+@pytest.mark.parametrize("variant", [0, 1, 2])      # fast kernel + walker (default), per-base atomics, walker alone
 @pytest.mark.parametrize("mbq", [0, 20, 40])
 def test_fuzz_vs_oracle(eng, mbq, variant):
     for seed in range(40, 52):
@@ -64,8 +64,9 @@ def test_group_widths_vs_oracle(eng, read_len, n_reads, mbq):
 
 
 @pytest.mark.parametrize("read_len,n_reads", [(150, 6000), (400, 4000), (1000, 1500), (5000, 300)])
-def test_split_kernel_vs_oracle(eng, read_len, n_reads):
-    """Count variant 2 (csrc/k1_split.cuh): every group width, quality masks on and off, the sample-batch shape."""
+def test_walker_alone_vs_oracle(eng, read_len, n_reads):
+    """Count variant 2 (the general walker of csrc/k1_count.cuh without the fast kernel in front): every group width,
+    quality masks on and off, the sample-batch shape."""
     rec = synth.uniform_short_read_sample(seed=read_len + 1, ref_len=20000, n_reads=n_reads, read_len=read_len, ref_name="x")
     b = select_reads(rec, 0, 0)
     for mbq in (0, 20):
