@@ -105,6 +105,7 @@ struct bc_handle {
     int walker_ctas_per_sm = 1;           // grid of the walker behind k1_count_fast: 1 until a batch deferred a lot
     int walker_max_ctas = 1;              // its occupancy limit
     uint64_t reads_since_sync = 0;
+    int dbg_skip = 0;                     // BASECOUNT_B200_DEBUG_SKIP (timing experiments only): 1 = no walker launch, 2 = no corrections
 };
 
 #define CU(h, expr)                                                                              \
@@ -248,6 +249,7 @@ int bc_create(int device, bc_handle **out)
         else if (std::strcmp(k1, "fast") != 0) return bail(cudaErrorInvalidValue, "BASECOUNT_B200_K1 must be fast or walker");
         h->variant = h->default_variant;
     }
+    if (const char *d = std::getenv("BASECOUNT_B200_DEBUG_SKIP")) h->dbg_skip = std::atoi(d);
     if ((e = cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "stream");
     {
         // K1 is one resident wave whose three CTAs per SM hold 96 % of the register file: whatever shares
@@ -590,6 +592,7 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
             const size_t smem = (size_t)k1_fast_cta_smem_bytes<GG, OKK>();                                              \
             k1_count_fast<GG, OKK><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb_fast, d_deferred, \
                                                                             h->d_defer_ctrl);                           \
+            if (!(h->dbg_skip & 1))                                                                                     \
             k1_count_tiled<GG, OKK><<<wgrid, kK1Threads, wsmem, h->compute>>>(v, cv, d_deferred, 0u, rpb, h->d_defer_ctrl); \
             h->launches++;                                                                                              \
         } else {                                                                                                        \
@@ -611,7 +614,7 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     CU(h, cudaEventRecord(h->k1[ki], h->compute));
     h->k_count++;
     h->launches++;
-    if (v.n_exc) {
+    if (v.n_exc && !(h->dbg_skip & 2)) {
         int rce = launch_exceptions();
         if (rce) return rce;
     }
@@ -620,7 +623,7 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     k1_check_overflow<<<std::min<unsigned>((v.n_reads + 255) / 256, (unsigned)h->sm_count * 2), 256, 0, h->side>>>(v, cv);
     CU(h, cudaEventRecord(h->checked, h->side));
     h->launches++;
-    if (v.n_exc) CU(h, cudaStreamWaitEvent(h->compute, h->join, 0));
+    if (v.n_exc && !(h->dbg_skip & 2)) CU(h, cudaStreamWaitEvent(h->compute, h->join, 0));
     CU(h, cudaGetLastError());
     return BC_OK;
 }

@@ -41,26 +41,37 @@ constexpr uint32_t kNoWindow = 0x80000000u;    // a window position no piece fit
 template <int G, bool HAS_OK>
 struct K1FastCfg {
     static constexpr int S = 32 / G;
-    static constexpr int Q = 4 * S;
+    static constexpr int Q = 4 * S;                         // ring entries per half trip (four pieces per read slot)
+    static constexpr int Q2 = 2 * Q;                        // per trip
+    // Counted quantities per window word.  Without a quality mask the number of pieces covering a column is an
+    // interval count: it comes from a difference array in shared memory (+1 at a piece's first column, -1 behind
+    // its last, two shared-memory atomics per piece when it is pushed, one prefix sum per flush) instead of a
+    // fourth bit-sliced counter.  With a mask, "valid" is per base and stays bit-sliced.
+    static constexpr int NC = HAS_OK ? 4 : 3;
+    static constexpr int NB = HAS_OK ? 7 : 8;               // bit planes per counter, all in registers
+    static constexpr uint32_t kCntMax = (1u << NB) - 8u;    // pieces per slot between flushes (a multiple of 8)
     static constexpr uint32_t kWin = 32u * kW * G;
     static constexpr uint32_t kMaxFit = kWin - 31u;
     static constexpr uint32_t kCols = kFlushStride * kW * G;
     static constexpr uint32_t lut_bytes = 528;
-    // per warp: ring | sequence stages | quality-mask stages | flush rows (= spill words) | mbarriers.  A piece's
+    // per warp: ring | sequence stages | quality-mask stages | flush rows | difference array | mbarriers.  A piece's
     // unclamped word index reaches up to 64*G columns before or after its data: the ring in front and the flush
     // rows behind keep those (masked-away) reads inside the CTA's shared memory.
     static constexpr uint32_t ring_off = 0;
     static constexpr uint32_t seq_off = ring_off + kFastRing * 16u;
     static constexpr uint32_t ok_off = seq_off + kFastStages * kSeqCap * 8u;
     static constexpr uint32_t frow_off = ok_off + (HAS_OK ? kFastStages * kSeqCap * 4u : 0u);
-    static constexpr uint32_t frow_bytes = kNC * kCols * 2u > kSpillWords * 128u ? kNC * kCols * 2u : kSpillWords * 128u;
-    static constexpr uint32_t bar_off = frow_off + frow_bytes;
+    static constexpr uint32_t frow_bytes = (uint32_t)NC * kCols * 2u;
+    static constexpr uint32_t cov_off = frow_off + frow_bytes;
+    static constexpr uint32_t cov_bytes = HAS_OK ? 0u : (kWin + 4u) * 4u;
+    static constexpr uint32_t bar_off = cov_off + cov_bytes;
     static constexpr uint32_t warp_bytes = bar_off + 32u;
     static constexpr uint32_t cta_bytes = lut_bytes + kK1WarpsPerCta * warp_bytes;
-    static_assert(seq_off % 16 == 0 && ok_off % 16 == 0 && frow_off % 16 == 0 && bar_off % 16 == 0 && warp_bytes % 16 == 0,
+    static_assert(seq_off % 16 == 0 && ok_off % 16 == 0 && frow_off % 16 == 0 && cov_off % 16 == 0 && bar_off % 16 == 0 &&
+                      warp_bytes % 16 == 0,
                   "TMA destinations are 16-byte aligned");
     static_assert(seq_off >= (kWin / 32 + 4) * 8 && frow_bytes >= (kWin / 32 + 4) * 8, "guard bands around the stages");
-    static_assert(kFastRing % Q == 0 && kFastRing >= 64 + Q, "a block's pieces and a partial trip fit the ring");
+    static_assert(kFastRing % Q2 == 0 && kFastRing >= 64 + Q2, "a block's pieces and a partial trip fit the ring");
     static_assert(kFastStages >= 2 && kFastStages <= 3, "stages");
 };
 template <int G, bool HAS_OK>
@@ -76,6 +87,272 @@ __device__ __forceinline__ uint32_t ldg_if(const uint32_t *p, bool on)
     asm volatile("{\n.reg .pred P1;\nsetp.ne.u32 P1, %2, 0;\n@P1 ld.global.nc.u32 %0, [%1];\n}" : "+r"(v) : "l"(p), "r"((uint32_t)on));
     return v;
 }
+__device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// Masked words of one ring entry (a piece) for a lane's two window words: lo, hi, lo & hi (and the mask itself when
+// "valid" is counted bit-sliced).  Entry layout as in k1_count.cuh.
+template <bool HAS_OK, int NC>
+__device__ __forceinline__ void fast_piece(const uint4 e, uint32_t (&x)[kW][NC], int L0, uint32_t lutb, uint32_t lane_seq_off,
+                                           uint32_t seqb, uint32_t okb)
+{
+    const int a_c = __viaddmin_s32_relu((int)e.x, -L0, 64);      // clamp(first - L0, 0, 64)
+    const int e_c = __viaddmin_s32_relu((int)e.y, -L0, 64);
+    const uint2 ga = lds64(lutb + 8u * (uint32_t)a_c), ge = lds64(lutb + 8u * (uint32_t)e_c);
+    uint32_t m[kW] = {ga.x & ~ge.x, ga.y & ~ge.y};
+    const uint32_t wa = e.w + lane_seq_off;
+    const uint2 r0 = lds64(wa), r1 = lds64(wa + 8u), r2 = lds64(wa + 16u);
+    const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, e.z), __funnelshift_r(r1.x, r2.x, e.z)};
+    const uint32_t hi[kW] = {__funnelshift_r(r0.y, r1.y, e.z), __funnelshift_r(r1.y, r2.y, e.z)};
+    if (HAS_OK) {
+        const uint32_t oa = okb + (uint32_t)((int)(wa - seqb) >> 1);
+        const uint32_t o0 = lds32(oa), o1 = lds32(oa + 4u), o2 = lds32(oa + 8u);
+        m[0] &= __funnelshift_r(o0, o1, e.z);
+        m[1] &= __funnelshift_r(o1, o2, e.z);
+    }
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+        x[w][0] = lo[w] & m[w];
+        x[w][1] = hi[w] & m[w];
+        x[w][2] = lo[w] & hi[w] & m[w];
+        if (NC > 3) x[w][3] = m[w];
+    }
+}
+
+// Four pieces per read slot into carry-save levels 0 and 1; the weight-4 carry comes back in c2.
+template <int NC, int NB>
+__device__ __forceinline__ void csa_half(const uint32_t (&x)[4][kW][NC], uint32_t (&pl)[kW][NC][NB], uint32_t (&c2)[kW][NC])
+{
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            const uint32_t c1a = maj3(pl[w][k][0], x[0][w][k], x[1][w][k]);
+            const uint32_t t = pl[w][k][0] ^ x[0][w][k] ^ x[1][w][k];
+            const uint32_t c1b = maj3(t, x[2][w][k], x[3][w][k]);
+            pl[w][k][0] = t ^ x[2][w][k] ^ x[3][w][k];
+            c2[w][k] = maj3(pl[w][k][1], c1a, c1b);
+            pl[w][k][1] ^= c1a ^ c1b;
+        }
+    }
+}
+
+// The upper levels of one trip (eight pieces per read slot): the two weight-4 carries of its halves meet in plane 2
+// with no pending register; the weight-8 carry is parked every other trip (pb), the weight-16 carry every fourth
+// (pc), and the weight-32 carry ripples through planes 5.. every eighth.  cnt = pieces per slot counted before
+// this trip (a multiple of 8).
+template <int NC, int NB>
+__device__ __forceinline__ void csa_upper(const uint32_t (&c2a)[kW][NC], const uint32_t (&c2b)[kW][NC], uint32_t (&pl)[kW][NC][NB],
+                                          uint32_t (&pb)[kW][NC], uint32_t (&pc)[kW][NC], uint32_t cnt)
+{
+    uint32_t c3[kW][NC];
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            c3[w][k] = maj3(pl[w][k][2], c2a[w][k], c2b[w][k]);
+            pl[w][k][2] ^= c2a[w][k] ^ c2b[w][k];
+        }
+    }
+    if (!(cnt & 8u)) {
+#pragma unroll
+        for (int w = 0; w < kW; w++)
+#pragma unroll
+            for (int k = 0; k < NC; k++) pb[w][k] = c3[w][k];
+    } else {
+        uint32_t c4[kW][NC];
+#pragma unroll
+        for (int w = 0; w < kW; w++) {
+#pragma unroll
+            for (int k = 0; k < NC; k++) {
+                c4[w][k] = maj3(pl[w][k][3], pb[w][k], c3[w][k]);
+                pl[w][k][3] ^= pb[w][k] ^ c3[w][k];
+            }
+        }
+        if (!(cnt & 16u)) {
+#pragma unroll
+            for (int w = 0; w < kW; w++)
+#pragma unroll
+                for (int k = 0; k < NC; k++) pc[w][k] = c4[w][k];
+        } else {
+#pragma unroll
+            for (int w = 0; w < kW; w++) {
+#pragma unroll
+                for (int k = 0; k < NC; k++) {
+                    uint32_t c = maj3(pl[w][k][4], pc[w][k], c4[w][k]);
+                    pl[w][k][4] ^= pc[w][k] ^ c4[w][k];
+#pragma unroll
+                    for (int p = 5; p < NB; p++) {        // ripple the weight-32 carry upwards
+                        const uint32_t t = pl[w][k][p] & c;
+                        pl[w][k][p] ^= c;
+                        c = t;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Convert the warp's vertical counters to integers and add them to the HBM planes (the flush of k1_count.cuh with
+// every plane in registers, the pending carries of csa_upper, and -- without a quality mask -- the coverage taken
+// from the difference array at shared address covb: an in-place prefix sum, read, then zeroed for the next window).
+//   frow: NC rows x (kW*G window words x kFlushStride) uint16
+template <int G, int NC, int NB>
+__device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t (&pb)[kW][NC], uint32_t (&pc)[kW][NC],
+                                           uint32_t cnt, uint16_t *frow, uint32_t covb, uint32_t *__restrict__ counts,
+                                           uint64_t stride, int lane)
+{
+    constexpr int S = 32 / G;
+    constexpr int R = S == 8 ? 3 : (S == 4 ? 2 : (S == 2 ? 1 : 0));      // combine rounds
+    constexpr int kCols = (int)kFlushStride * kW * G;
+    constexpr int kQ = 4;                                                 // counter slots per window word (NC real ones)
+    constexpr int kN = kW * kQ;                                           // counter slots per lane (8)
+    const int slot = lane / G, wl = lane % G;
+    uint32_t A[kN][NB + 3];
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+#pragma unroll
+        for (int k = 0; k < kQ; k++) {
+            const int i = w * kQ + k;
+            if (k < NC) {
+#pragma unroll
+                for (int p = 0; p < NB; p++) A[i][p] = pl[w][k][p];
+                // pending carries of weight 8 / 16 are live iff that bit of cnt is set
+                uint32_t c = (cnt & 8u) ? pb[w][k] : 0u;
+                {
+                    const uint32_t t = A[i][3] & c;
+                    A[i][3] ^= c;
+                    c = t;
+                }
+                {
+                    const uint32_t d = (cnt & 16u) ? pc[w][k] : 0u;      // two carries into plane 4: full adder
+                    const uint32_t t = maj3(A[i][4], c, d);
+                    A[i][4] ^= c ^ d;
+                    c = t;
+                }
+#pragma unroll
+                for (int p = 5; p < NB; p++) {
+                    const uint32_t t = A[i][p] & c;
+                    A[i][p] ^= c;
+                    c = t;
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < NB; p++) A[i][p] = 0u;
+            }
+#pragma unroll
+            for (int p = NB; p < NB + 3; p++) A[i][p] = 0u;
+        }
+    }
+    // ---- coverage from the difference array: lane l owns entries [l * 2G, (l + 1) * 2G)
+    if (NC == 3) {
+        constexpr int kPer = 2 * G;                   // entries per lane (a multiple of 4)
+        const uint32_t mine = covb + 4u * (uint32_t)(lane * kPer);
+        uint32_t tot = 0u;
+#pragma unroll 1
+        for (int i = 0; i < kPer; i += 4) {
+            const uint4 v = lds128(mine + 4u * (uint32_t)i);
+            tot += v.x + v.y + v.z + v.w;
+        }
+        uint32_t run = tot;                           // inclusive scan of the lane totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(kFull, run, d);
+            if (lane >= d) run += o;
+        }
+        run -= tot;                                   // exclusive: what lies before this lane's entries
+#pragma unroll 1
+        for (int i = 0; i < kPer; i += 4) {
+            uint4 v = lds128(mine + 4u * (uint32_t)i);
+            v.x += run;
+            v.y += v.x;
+            v.z += v.y;
+            v.w += v.z;
+            run = v.w;
+            sts128(mine + 4u * (uint32_t)i, v);
+        }
+    }
+    // ---- bit-sliced sum over the read slots
+    int first = 0;                                    // counter index (w * kQ + k) of A[0] after the rounds
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int d = G << r;
+        const int h = kN >> (r + 1);
+        const bool up = (slot >> r) & 1;
+        if (up) first += h;
+#pragma unroll
+        for (int i = 0; i < h; i++) {
+            uint32_t carry = 0u;
+#pragma unroll
+            for (int p = 0; p < NB + r; p++) {
+                const uint32_t mine = up ? A[h + i][p] : A[i][p];
+                const uint32_t give = up ? A[i][p] : A[h + i][p];
+                const uint32_t got = __shfl_xor_sync(kFull, give, d);
+                A[i][p] = mine ^ got ^ carry;
+                carry = maj3(mine, got, carry);
+            }
+            A[i][NB + r] = carry;
+        }
+    }
+    constexpr int kLeft = kN >> R;                    // counters this lane extracts
+    const bool high = cnt * (uint32_t)S >= 16u;       // planes 4.. can only be set once 16 inputs went in
+#pragma unroll 1
+    for (int jj = 0; jj < 8; jj++) {
+#pragma unroll
+        for (int i = 0; i < kLeft; i++) {
+            uint32_t acc = 0u, acc2 = 0u;             // byte t = count of column jj + 8t: low 8 bits / bits 8..
+#pragma unroll
+            for (int p = 0; p < 4; p++) acc += ((A[i][p] >> jj) & 0x01010101u) << p;
+            if (high) {
+#pragma unroll
+                for (int p = 4; p < 8 && p < NB + R; p++) acc += ((A[i][p] >> jj) & 0x01010101u) << p;
+#pragma unroll
+                for (int p = 8; p < NB + R; p++) acc2 += ((A[i][p] >> jj) & 0x01010101u) << (p - 8);
+            }
+            const uint32_t ev = (acc & 0x00FF00FFu) + ((acc2 & 0x00FF00FFu) << 8);               // columns jj, jj+16
+            const uint32_t od = ((acc >> 8) & 0x00FF00FFu) + (((acc2 >> 8) & 0x00FF00FFu) << 8);  // columns jj+8, jj+24
+            const int ci = first + i, w = ci / kQ, k = ci % kQ;
+            if (k < NC) {                             // (slot 3 of a window word is empty without a quality mask)
+                uint16_t *dst = frow + k * kCols + (kW * wl + w) * (int)kFlushStride + jj;
+                dst[0] = (uint16_t)ev;
+                dst[16] = (uint16_t)(ev >> 16);
+                dst[8] = (uint16_t)od;
+                dst[24] = (uint16_t)(od >> 16);
+            }
+        }
+    }
+    __syncwarp();
+    uint32_t *const pA = counts + lane, *const pC = pA + stride, *const pG = pC + stride, *const pT = pG + stride;
+#pragma unroll
+    for (int w = 0; w < kW * G; w++) {
+        const int at = (int)kFlushStride * w + lane;
+        const uint32_t nlo = frow[at], nhi = frow[kCols + at], nb = frow[2 * kCols + at];
+        const uint32_t nv = NC == 3 ? lds32(covb + 4u * (uint32_t)(32 * w + lane)) : (uint32_t)frow[3 * kCols + at];
+        red_add(pA + 32 * w, nv + nb - nlo - nhi);           // RED.ADD, 128 B per warp instruction
+        red_add(pC + 32 * w, nlo - nb);
+        red_add(pG + 32 * w, nhi - nb);
+        red_add(pT + 32 * w, nb);
+    }
+    __syncwarp();
+    if (NC == 3) {                                    // a fresh difference array for the next window / next pieces
+#pragma unroll
+        for (int w = 0; w < kW * G; w++) sts32(covb + 4u * (uint32_t)(32 * w + lane), 0u);
+        if (lane < 4) sts32(covb + 4u * (uint32_t)(32 * kW * G + lane), 0u);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < kW; w++) {
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+#pragma unroll
+            for (int p = 0; p < NB; p++) pl[w][k][p] = 0u;
+            pb[w][k] = 0u;
+            pc[w][k] = 0u;
+        }
+    }
+}
 
 template <int G, bool HAS_OK>
 __global__ void __launch_bounds__(kK1Threads, BC_K1F_MINCTAS)
@@ -83,7 +360,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
               Chunk *__restrict__ deferred, uint32_t *__restrict__ n_deferred)
 {
     using C = K1FastCfg<G, HAS_OK>;
-    constexpr int S = C::S, Q = C::Q;
+    constexpr int S = C::S, Q = C::Q, Q2 = C::Q2, NC = C::NC, NB = C::NB;
     constexpr uint32_t kWin = C::kWin;
     extern __shared__ __align__(128) unsigned char k1_smem[];
 
@@ -105,12 +382,12 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
     uint16_t *frow = reinterpret_cast<uint16_t *>(wsm + C::frow_off);          // flush only
     const uint32_t lutb = opaque(smem_u32(k1_smem));
     const uint32_t wb = opaque(smem_u32(wsm));                                 // the warp's region
-    const uint32_t ringb = wb + C::ring_off, seqb = wb + C::seq_off, okb = wb + C::ok_off, barb = wb + C::bar_off;
+    const uint32_t ringb = wb + C::ring_off, seqb = wb + C::seq_off, okb = wb + C::ok_off, barb = wb + C::bar_off,
+                   covb = wb + C::cov_off;
 
     const int slot = lane / G, wl = lane % G;
     const int L0 = 32 * kW * wl;                    // window column of this lane's bit 0
     const uint32_t lt_mask = opaque((1u << lane) - 1u);
-    const uint32_t spb = opaque(wb + C::frow_off + 4u * (uint32_t)lane);       // this lane's spill words, 128 B apart
     const uint32_t trip_ringb = opaque(ringb + 16u * (uint32_t)slot);          // ring entry of this slot in a trip
     const uint32_t lane_seq_off = 8u * kW * (uint32_t)wl;                      // byte offset of this lane's window words
 
@@ -127,13 +404,16 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
         for (int s = 0; s < kFastStages; s++) mbar_init_s(barb + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (NC == 3) {
+        for (uint32_t i = (uint32_t)lane; i < kWin + 4u; i += 32u) sts32(covb + 4u * i, 0u);
+    }
     __syncwarp();
 
     // ---- block metadata.  Lane l holds read (block begin + l); indices are clamped to the block's end, so a lane
     //      without a read holds an empty read (no CIGAR words, no sequence words) and lane 31's ends are the block's.
     struct Meta { uint32_t start, cb, ce, wb, we; };
     auto load_meta = [&](uint32_t blk) {
-        const uint32_t b0 = rb + blk * rpb;                                  // (the host keeps n_reads < 2^32 - 128)
+        const uint32_t b0 = rb + blk * rpb;                                  // (the host keeps n_reads < 2^32 - 256)
         const uint32_t bend = min(b0 + rpb, re);
         const uint32_t i0 = min(b0 + (uint32_t)lane, bend);
         const uint32_t i1 = min(i0 + 1u, bend);
@@ -180,15 +460,15 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
     uint32_t ring_head = 0, ring_tail = 0, mark = 0;      // mark: entries before it come from earlier blocks
     uint32_t win_lo = kNoWindow, cnt = 0;
     uint32_t def_begin = 0xFFFFFFFFu, def_end = 0xFFFFFFFFu;   // open run of deferred blocks (reads [begin, end))
-    uint32_t pl[kW][kNC][kNR], pa[kW][kNC], pb[kW][kNC];
+    uint32_t pl[kW][NC][NB], pb[kW][NC], pc[kW][NC];
 #pragma unroll
     for (int w = 0; w < kW; w++) {
 #pragma unroll
-        for (int k = 0; k < kNC; k++) {
+        for (int k = 0; k < NC; k++) {
 #pragma unroll
-            for (int p = 0; p < kNR; p++) pl[w][k][p] = 0u;
-            pa[w][k] = 0u;
+            for (int p = 0; p < NB; p++) pl[w][k][p] = 0u;
             pb[w][k] = 0u;
+            pc[w][k] = 0u;
         }
     }
     auto emit_deferred = [&]() {
@@ -204,10 +484,15 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
         }
     };
     // A ring entry: x / y = first / end column of the piece relative to the window, z = bit index of window
-    // column 0 in the staged data, w = shared address of the plane word that holds window column 0.
+    // column 0 in the staged data, w = shared address of the plane word that holds window column 0.  Without a
+    // quality mask the piece also enters the coverage difference array here.
     auto push_entry = [&](uint32_t at, uint32_t rel, uint32_t n, int qbit) {
         const int z = qbit - (int)rel;
         sts128(ringb + 16u * (at & (kFastRing - 1u)), make_uint4(rel, rel + n, (uint32_t)z, seqb + (uint32_t)((z >> 5) * 8)));
+        if (NC == 3) {
+            red_shared_add(covb + 4u * rel, 1u);
+            red_shared_add(covb + 4u * (rel + n), 0xFFFFFFFFu);
+        }
     };
 
     // j == nblk is a virtual empty block: it drains the ring and does the final flush in the one trip / flush site.
@@ -306,34 +591,47 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
             // ---- the one trip site and the one flush site
             for (;;) {
                 const uint32_t avail = ring_tail - ring_head;
-                if (avail < (uint32_t)Q || cnt == kCntMax) {                 // rare: everything but a plain trip
-                    if (avail < (uint32_t)Q) {
+                if (avail < (uint32_t)Q2 || cnt == C::kCntMax) {             // rare: everything but a plain trip
+                    if (avail < (uint32_t)Q2) {
                         const bool drain = left || last || (want_issue && (int)(ring_head - mark) < 0);
                         if (avail != 0u && drain) {                          // pad the ring with empty pieces to a full trip
-                            if ((uint32_t)lane < (uint32_t)Q - avail)
-                                sts128(ringb + 16u * ((ring_tail + lane) & (kFastRing - 1u)), make_uint4(0u, 0u, 0u, seqb));
-                            ring_tail += (uint32_t)Q - avail;
+                            for (uint32_t i = (uint32_t)lane; i < (uint32_t)Q2 - avail; i += 32u)
+                                sts128(ringb + 16u * ((ring_tail + i) & (kFastRing - 1u)), make_uint4(0u, 0u, 0u, seqb));
+                            ring_tail += (uint32_t)Q2 - avail;
                             __syncwarp();
                             continue;
                         }
                         if (!(cnt != 0u && (left || last))) break;
                     }
-                    flush_counters<G>(pl, pa, pb, cnt, frow, plane0 + win_lo, cv.stride, lane);
+                    flush_fast<G, NC, NB>(pl, pb, pc, cnt, frow, covb, plane0 + win_lo, cv.stride, lane);
                     cnt = 0u;
                     continue;
                 }
-                // -- trip: four pieces per read slot, straight-line.  ring_head is a multiple of Q and Q divides
-                //    the ring, so the Q entries of a trip never wrap.
+                // -- trip: eight pieces per read slot in two halves, straight-line.  ring_head is a multiple of Q2 and
+                //    Q2 divides the ring, so the entries of a trip never wrap.
                 const uint32_t ea = trip_ringb + 16u * (ring_head & (kFastRing - 1u));
-                uint4 e[4];
+                ring_head += (uint32_t)Q2;
+                uint32_t c2a[kW][NC], c2b[kW][NC];
+                {
+                    uint4 e[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) e[q] = lds128(ea + 16u * (uint32_t)(q * S));
-                ring_head += (uint32_t)Q;
-                uint32_t x[4][kW][kNC];
+                    for (int q = 0; q < 4; q++) e[q] = lds128(ea + 16u * (uint32_t)(q * S));
+                    uint32_t x[4][kW][NC];
 #pragma unroll
-                for (int q = 0; q < 4; q++) piece_words<HAS_OK>(e[q], x[q], L0, lutb, lane_seq_off, seqb, okb);
-                csa_trip(x, pl, pa, pb, cnt, spb);
-                cnt += 4u;
+                    for (int q = 0; q < 4; q++) fast_piece<HAS_OK, NC>(e[q], x[q], L0, lutb, lane_seq_off, seqb, okb);
+                    csa_half<NC, NB>(x, pl, c2a);
+                }
+                {
+                    uint4 e[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) e[q] = lds128(ea + 16u * (uint32_t)(Q + q * S));
+                    uint32_t x[4][kW][NC];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) fast_piece<HAS_OK, NC>(e[q], x[q], L0, lutb, lane_seq_off, seqb, okb);
+                    csa_half<NC, NB>(x, pl, c2b);
+                }
+                csa_upper<NC, NB>(c2a, c2b, pl, pb, pc, cnt);
+                cnt += 8u;
             }
             if (!left) break;
             // move the window to the lowest pending piece (the counters were flushed above)
@@ -342,10 +640,10 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
         if (want_issue) issue_block(kFastStages > 2 ? M2 : M1, st == 0u ? (uint32_t)(kFastStages - 1) : st - 1u);
 
         // ---- rotate the pipelines
-        mark = ring_tail;
-        st = (st == (uint32_t)kFastStages - 1u) ? 0u : st + 1u;
         // (the values loaded at the top of this block are first touched HERE, by instructions the compiler cannot
         //  hoist: left to itself it copies them right behind the loads and every block waits out the HBM latency)
+        mark = ring_tail;
+        st = (st == (uint32_t)kFastStages - 1u) ? 0u : st + 1u;
         M0 = M1;
         M1.start = opaque(M2.start);
         M1.cb = opaque(M2.cb);
