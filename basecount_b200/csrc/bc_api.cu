@@ -40,6 +40,7 @@ struct DevBuf {
 struct Staging {                 // device copies of one host batch
     DevBuf ref_read_off, starts, cigar_off, cigar, seq_woff, planes, okmask, exc_read, exc_pos, chunks;
     DevBuf deferred;             // chunks k1_count_fast leaves to the general walker (device-written)
+    DevBuf ctrl;                 // {deferred chunks, walker warps done, chunks of the last walker launch, -}: see k1_count_tiled
     Chunk *h_chunks = nullptr;   // pinned
     size_t h_chunks_cap = 0;
     cudaEvent_t copied = nullptr, done = nullptr, checked = nullptr;   // checked: the overflow check (side stream) is over
@@ -53,6 +54,10 @@ struct Resident {                // a batch kept in HBM by bc_batch_upload
     int G = 32;
     uint32_t mean_words = 1;
     bool live = false;
+    // What k1_count_fast defers is a function of the batch alone, so a resident batch that deferred nothing the first
+    // time never will: its later launches leave out the (then empty) walker launch behind the fast kernel.
+    int walker = 0;              // 0 = not known yet, 1 = needed, 2 = not needed
+    bool launched = false;       // launched since the last bc_sync while walker == 0 or 2
 };
 
 }  // namespace
@@ -67,7 +72,13 @@ struct bc_handle {
     uint32_t n_refs = 0;
     std::vector<uint32_t> ref_len, col_base, slot_cap;      // slot_cap: a slot's length at bc_begin (bc_truncate may not exceed it)
     uint64_t stride = 0;
-    uint32_t *d_counts = nullptr;
+    // Two sets of accumulators: bc_reset switches to the other one, which is zeroed on the side stream while the
+    // kernels that still read the first (the summary of the step before) run, so neither the memset nor the sparse
+    // corrections of the next batch (they need zeroed planes) sit between one step's summary and the next one's K1.
+    uint32_t *d_counts = nullptr;            // = d_counts_set[cur_set]
+    uint32_t *d_counts_set[2] = {nullptr, nullptr};
+    int cur_set = 0;
+    cudaEvent_t set_free[2] = {nullptr, nullptr}, set_zeroed[2] = {nullptr, nullptr};
     unsigned long long *d_counts64 = nullptr;
     uint32_t *d_col_base = nullptr, *d_ref_len = nullptr;
     uint32_t *d_status = nullptr;
@@ -101,10 +112,10 @@ struct bc_handle {
     uint64_t launches = 0;
     int variant = 0;             // 0 = k1_count_fast + general walker for what it defers, 1 = per-base atomics, 2 = walker only
     int default_variant = 0;     // what variant 0 means (BASECOUNT_B200_K1=walker makes it 2)
-    uint32_t *d_defer_ctrl = nullptr;     // {deferred chunks, walker warps that are done}; the walker resets both
     int walker_ctas_per_sm = 1;           // grid of the walker behind k1_count_fast: 1 until a batch deferred a lot
     int walker_max_ctas = 1;              // its occupancy limit
     uint64_t reads_since_sync = 0;
+    bool side_needs_compute = true;       // the next corrections kernel must wait for everything queued on the compute stream
     int dbg_skip = 0;                     // BASECOUNT_B200_DEBUG_SKIP (timing experiments only): 1 = no walker launch, 2 = no corrections
 };
 
@@ -188,7 +199,7 @@ static void release(DevBuf &b)
 static void release_staging(Staging &s)
 {
     release(s.ref_read_off); release(s.starts); release(s.cigar_off); release(s.cigar); release(s.seq_woff);
-    release(s.planes); release(s.okmask); release(s.exc_read); release(s.exc_pos); release(s.chunks); release(s.deferred);
+    release(s.planes); release(s.okmask); release(s.exc_read); release(s.exc_pos); release(s.chunks); release(s.deferred); release(s.ctrl);
     if (s.h_chunks) cudaFreeHost(s.h_chunks);
     s.h_chunks = nullptr;
     s.h_chunks_cap = 0;
@@ -268,6 +279,10 @@ int bc_create(int device, bc_handle **out)
     if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->counted, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->checked, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    for (int i = 0; i < 2; i++) {
+        if ((e = cudaEventCreateWithFlags(&h->set_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+        if ((e = cudaEventCreateWithFlags(&h->set_zeroed[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    }
     for (cudaEvent_t *ev : {&h->t0, &h->t1})
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail(e, "event");
     for (int i = 0; i < bc_handle::kHist; i++) {
@@ -281,8 +296,6 @@ int bc_create(int device, bc_handle **out)
     }
     if ((e = cudaMalloc(&h->d_status, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(h->d_status, 0, kStatWords * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
-    if ((e = cudaMalloc(&h->d_defer_ctrl, 2 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemset(h->d_defer_ctrl, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMemset");
     if ((e = cudaMalloc(&h->d_log2_tab, kSummaryTabDoubles * sizeof(double))) != cudaSuccess) return bail(e, "cudaMalloc");
     k_fill_log2<<<(kSummaryTabDoubles + 255) / 256, 256, 0, h->compute>>>(h->d_log2_tab);
     if ((e = cudaStreamSynchronize(h->compute)) != cudaSuccess) return bail(e, "k_fill_log2");
@@ -311,12 +324,15 @@ void bc_destroy(bc_handle *h)
     if (h->d_part_off) cudaFree(h->d_part_off);
     if (h->d_results) cudaFree(h->d_results);
     if (h->h_results) cudaFreeHost(h->h_results);
-    if (h->d_counts) cudaFree(h->d_counts);
+    for (int i = 0; i < 2; i++) {
+        if (h->d_counts_set[i]) cudaFree(h->d_counts_set[i]);
+        if (h->set_free[i]) cudaEventDestroy(h->set_free[i]);
+        if (h->set_zeroed[i]) cudaEventDestroy(h->set_zeroed[i]);
+    }
     if (h->d_counts64) cudaFree(h->d_counts64);
     if (h->d_col_base) cudaFree(h->d_col_base);
     if (h->d_ref_len) cudaFree(h->d_ref_len);
     if (h->d_status) cudaFree(h->d_status);
-    if (h->d_defer_ctrl) cudaFree(h->d_defer_ctrl);
     if (h->d_log2_tab) cudaFree(h->d_log2_tab);
     if (h->h_status) cudaFreeHost(h->h_status);
     for (cudaEvent_t ev : {h->t0, h->t1})
@@ -366,14 +382,17 @@ int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens)
     total += 32u * kW * 32u + 64u;   // slack: a full window (64 * G columns, G <= 32) may overhang the last slot
     if (total > 0xFFFFFFFFull) return fail(h, BC_ERR_ARG, "bc_begin: more than 2^32 columns in one handle");
     if (total != h->stride || n_refs != h->n_refs) {
-        if (h->d_counts) CU(h, cudaFree(h->d_counts));
+        for (int i = 0; i < 2; i++) {
+            if (h->d_counts_set[i]) CU(h, cudaFree(h->d_counts_set[i]));
+            h->d_counts_set[i] = nullptr;
+        }
         if (h->d_counts64) CU(h, cudaFree(h->d_counts64));
         if (h->d_col_base) CU(h, cudaFree(h->d_col_base));
         if (h->d_ref_len) CU(h, cudaFree(h->d_ref_len));
         h->d_counts = nullptr;
         h->d_counts64 = nullptr;
         h->d_col_base = h->d_ref_len = nullptr;
-        CU(h, cudaMalloc(&h->d_counts, (size_t)total * kPlanes * sizeof(uint32_t)));
+        for (int i = 0; i < 2; i++) CU(h, cudaMalloc(&h->d_counts_set[i], (size_t)total * kPlanes * sizeof(uint32_t)));
         CU(h, cudaMalloc(&h->d_col_base, n_refs * sizeof(uint32_t)));
         CU(h, cudaMalloc(&h->d_ref_len, n_refs * sizeof(uint32_t)));
     } else if (h->d_counts64) {
@@ -387,7 +406,11 @@ int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens)
     h->slot_cap = rl;
     h->col_base = cb;
     h->reads_since_fold = 0;
-    CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)total * kPlanes * sizeof(uint32_t), h->compute));
+    h->cur_set = 0;
+    h->side_needs_compute = true;
+    h->d_counts = h->d_counts_set[0];
+    for (int i = 0; i < 2; i++)
+        CU(h, cudaMemsetAsync(h->d_counts_set[i], 0, (size_t)total * kPlanes * sizeof(uint32_t), h->compute));
     CU(h, cudaMemsetAsync(h->d_status, 0, kStatWords * sizeof(uint32_t), h->compute));
     CU(h, cudaMemcpyAsync(h->d_col_base, cb.data(), n_refs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
     CU(h, cudaMemcpyAsync(h->d_ref_len, rl.data(), n_refs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
@@ -400,7 +423,16 @@ int bc_reset(bc_handle *h)
     if (!h) return BC_ERR_ARG;
     if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->stride * kPlanes * sizeof(uint32_t), h->compute));
+    // everything queued so far may still read the current set; the other one is free once what was queued before
+    // the previous switch is done.  It is zeroed on the side stream, behind the overflow check of the last batch
+    // (i.e. not beside its K1), and the compute stream only waits for that memset.
+    CU(h, cudaEventRecord(h->set_free[h->cur_set], h->compute));
+    h->cur_set ^= 1;
+    h->d_counts = h->d_counts_set[h->cur_set];
+    CU(h, cudaStreamWaitEvent(h->side, h->set_free[h->cur_set], 0));
+    CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->stride * kPlanes * sizeof(uint32_t), h->side));
+    CU(h, cudaEventRecord(h->set_zeroed[h->cur_set], h->side));
+    CU(h, cudaStreamWaitEvent(h->compute, h->set_zeroed[h->cur_set], 0));
     if (h->d_counts64)
         CU(h, cudaMemsetAsync(h->d_counts64, 0, (size_t)h->stride * kPlanes * sizeof(unsigned long long), h->compute));
     h->reads_since_fold = 0;
@@ -532,8 +564,15 @@ static uint32_t fast_reads_per_block(uint32_t mean_words)
     return std::max<uint32_t>(1, std::min<uint32_t>(kFastRpbMax, (kSeqCap - 8) / std::max<uint32_t>(1, mean_words)));
 }
 
+// Stages of k1_count_fast's sequence buffer: four short ones when a block of reads fits a quarter of it.
+static uint32_t fast_stages(uint32_t mean_words)
+{
+    const uint32_t block_words = fast_reads_per_block(mean_words) * (std::max<uint32_t>(1, mean_words) + 1) + 8;
+    return block_words <= kFastStageShort ? 4u : 3u;
+}
+
 static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks, uint32_t n_chunks, int G,
-                        uint32_t mean_words, Chunk *d_deferred)
+                        uint32_t mean_words, Chunk *d_deferred, uint32_t *d_ctrl, Resident *res, cudaEvent_t copied)
 {
     if (v.n_reads == 0) return BC_OK;
     // uint32 counters cannot wrap while fewer than 2^32 reads went in since the last fold
@@ -546,6 +585,7 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
         k_fold_counts<<<(unsigned)((n + 255) / 256), 256, 0, h->compute>>>(h->d_counts, h->d_counts64, n);
         h->launches++;
         h->reads_since_fold = 0;
+        h->side_needs_compute = true;
     }
     h->reads_since_fold += v.n_reads;
     h->reads_since_sync += v.n_reads;
@@ -557,18 +597,26 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     cv.ref_len = h->d_ref_len;
     cv.status = h->d_status;
 
-    // The sparse corrections only add to planes A and N with atomics, so they commute with K1:
-    // run them on the forked (lowest-priority) stream, beside the counting kernel.  The exact overflow
-    // check follows them there once K1 is done: it only writes status words (read in bc_sync),
-    // so the statistics kernels on the compute stream need not wait for it.
-    auto launch_exceptions = [&]() -> int {
-        CU(h, cudaStreamWaitEvent(h->side, h->fork, 0));
+    // The sparse corrections only add to planes A and N with atomics, so they commute with K1 and need nothing from
+    // the compute stream but zeroed planes (bc_reset zeroes on the side stream, i.e. in front of them) and the batch
+    // itself.  They go to the side (lowest-priority) stream and wait there for the K1 of the batch BEFORE this one,
+    // so in a pipeline of steps they run beside that step's summary kernel, not beside a counting kernel (beside K1
+    // they cost it ~5 us).  After an operation that does not commute (truncate, halo add, fold, begin) they wait
+    // for the whole compute stream once.  The exact overflow check follows on the same stream once this K1 is done:
+    // it only writes status words (read in bc_sync), so the statistics kernels need not wait for it.
+    if (v.n_exc && !(h->dbg_skip & 2)) {
+        if (h->side_needs_compute) {
+            CU(h, cudaEventRecord(h->fork, h->compute));
+            CU(h, cudaStreamWaitEvent(h->side, h->fork, 0));
+            h->side_needs_compute = false;
+        } else {
+            if (copied) CU(h, cudaStreamWaitEvent(h->side, copied, 0));
+            CU(h, cudaStreamWaitEvent(h->side, h->counted, 0));          // the previous K1 (no-op if there was none)
+        }
         k1_exceptions<<<(v.n_exc + 127) / 128, 128, 0, h->side>>>(v, cv);
         CU(h, cudaEventRecord(h->join, h->side));
         h->launches++;
-        return BC_OK;
-    };
-    if (v.n_exc) CU(h, cudaEventRecord(h->fork, h->compute));
+    }
     const int ki = (int)(h->k_count % bc_handle::kHist);
     CU(h, cudaEventRecord(h->k0[ki], h->compute));
     if (h->variant == 1) {
@@ -585,16 +633,20 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
         // chunks, to a list in HBM; the general walker runs right behind it over that list (a fixed grid striding
         // over a device-side count: with nothing deferred it is an empty launch).
         const unsigned wgrid = (unsigned)(h->sm_count * std::max(1, h->walker_ctas_per_sm));
+        const bool walk = !(res && res->walker == 2) && !(h->dbg_skip & 1);
+        if (res && res->walker != 1) res->launched = true;
 #define K1_LAUNCH(GG, OKK)                                                                                              \
     do {                                                                                                                \
         const size_t wsmem = (size_t)k1_cta_smem_bytes<GG, OKK>();                                                      \
         if (fast) {                                                                                                     \
             const size_t smem = (size_t)k1_fast_cta_smem_bytes<GG, OKK>();                                              \
-            k1_count_fast<GG, OKK><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb_fast, d_deferred, \
-                                                                            h->d_defer_ctrl);                           \
-            if (!(h->dbg_skip & 1))                                                                                     \
-            k1_count_tiled<GG, OKK><<<wgrid, kK1Threads, wsmem, h->compute>>>(v, cv, d_deferred, 0u, rpb, h->d_defer_ctrl); \
-            h->launches++;                                                                                              \
+            k1_count_fast<GG, OKK><<<grid, kK1Threads, smem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb_fast,         \
+                                                                            fast_stages(mean_words), d_deferred,       \
+                                                                            d_ctrl);                                    \
+            if (walk) {                                                                                                 \
+                k1_count_tiled<GG, OKK><<<wgrid, kK1Threads, wsmem, h->compute>>>(v, cv, d_deferred, 0u, rpb, d_ctrl);   \
+                h->launches++;                                                                                          \
+            }                                                                                                           \
         } else {                                                                                                        \
             k1_count_tiled<GG, OKK><<<grid, kK1Threads, wsmem, h->compute>>>(v, cv, d_chunks, n_chunks, rpb, nullptr);   \
         }                                                                                                               \
@@ -614,10 +666,6 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     CU(h, cudaEventRecord(h->k1[ki], h->compute));
     h->k_count++;
     h->launches++;
-    if (v.n_exc && !(h->dbg_skip & 2)) {
-        int rce = launch_exceptions();
-        if (rce) return rce;
-    }
     CU(h, cudaEventRecord(h->counted, h->compute));
     CU(h, cudaStreamWaitEvent(h->side, h->counted, 0));
     k1_check_overflow<<<std::min<unsigned>((v.n_reads + 255) / 256, (unsigned)h->sm_count * 2), 256, 0, h->side>>>(v, cv);
@@ -669,6 +717,10 @@ static int stage_batch(bc_handle *h, Staging &st, const bc_batch *b, BatchView &
     n_chunks = build_chunks(h, b->ref_read_off, n, target_warps, chunks);
     // room for every run of blocks k1_count_fast may defer (at worst every other block of every chunk)
     if ((rc0 = ensure(h, st.deferred, ((size_t)n / fast_reads_per_block(mean_words) + n_chunks + 16) * sizeof(Chunk)))) return rc0;
+    if (!st.ctrl.p) {
+        if ((rc0 = ensure(h, st.ctrl, 4 * sizeof(uint32_t)))) return rc0;
+        CU(h, cudaMemsetAsync(st.ctrl.p, 0, 4 * sizeof(uint32_t), h->copy));
+    }
     if (n_chunks > st.h_chunks_cap) {
         if (st.h_chunks) CU(h, cudaFreeHost(st.h_chunks));
         st.h_chunks = nullptr;
@@ -719,7 +771,7 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
             return fail(h, BC_ERR_ARG, "on_device batch was not created by bc_batch_upload on this handle");
         Resident *r = h->resident[id - 1];
         return launch_count(h, r->view, (const Chunk *)r->st.chunks.p, r->n_chunks, r->G, r->mean_words,
-                            (Chunk *)r->st.deferred.p);
+                            (Chunk *)r->st.deferred.p, (uint32_t *)r->st.ctrl.p, r, nullptr);
     }
     Staging &st = h->stage[h->pushes & 1];
     h->pushes++;
@@ -734,7 +786,8 @@ int bc_push_batch(bc_handle *h, const bc_batch *b)
     if ((rc = stage_batch(h, st, b, view, n_chunks, G, mean_words))) return rc;
     CU(h, cudaEventRecord(st.copied, h->copy));
     CU(h, cudaStreamWaitEvent(h->compute, st.copied, 0));
-    rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G, mean_words, (Chunk *)st.deferred.p);
+    rc = launch_count(h, view, (const Chunk *)st.chunks.p, n_chunks, G, mean_words, (Chunk *)st.deferred.p,
+                      (uint32_t *)st.ctrl.p, nullptr, st.copied);
     CU(h, cudaEventRecord(st.done, h->compute));
     CU(h, cudaEventRecord(st.checked, h->side));
     st.used = true;
@@ -754,6 +807,15 @@ int bc_sync(bc_handle *h)
     CU(h, cudaMemcpyAsync(h->h_status, h->d_status, kStatWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
     deliver_summaries(h);
+    for (Resident *r : h->resident) {
+        if (!r || !r->live || !r->launched) continue;
+        uint32_t c[4] = {0, 0, 0, 0};
+        CU(h, cudaMemcpy(c, r->st.ctrl.p, sizeof(c), cudaMemcpyDeviceToHost));
+        r->launched = false;
+        if (r->walker == 0) r->walker = c[2] ? 1 : 2;
+        else if (r->walker == 2 && c[0])
+            return fail(h, BC_ERR_STATE, "internal: a resident batch deferred reads after its walker launch was dropped");
+    }
     {
         // size the walker's grid for the next batches from what this one deferred: one CTA per SM while nearly
         // everything takes the fast kernel (an empty launch then), full occupancy once an eighth of the reads do not
@@ -1043,6 +1105,7 @@ int bc_halo_export(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols,
     if (ref >= h->n_refs || (uint64_t)col_lo + n_cols > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "halo out of range");
     if (n_cols == 0) return BC_OK;
     CU(h, cudaSetDevice(h->device));
+    h->side_needs_compute = true;
     k_halo_export<<<(n_cols * kPlanes + 255) / 256, 256, 0, h->compute>>>(h->d_counts, h->stride,
                                                                          (uint64_t)h->col_base[ref] + col_lo, n_cols, dev_buf);
     h->launches++;
@@ -1056,6 +1119,7 @@ int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, co
     if (ref >= h->n_refs || (uint64_t)col_lo + n_cols > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "halo out of range");
     if (n_cols == 0) return BC_OK;
     CU(h, cudaSetDevice(h->device));
+    h->side_needs_compute = true;
     k_halo_add<<<(n_cols * kPlanes + 255) / 256, 256, 0, h->compute>>>(h->d_counts, h->stride,
                                                                       (uint64_t)h->col_base[ref] + col_lo, n_cols, dev_buf);
     h->launches++;
@@ -1070,6 +1134,7 @@ int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len)
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->side));               // an overflow check may still read the old length
     h->ref_len[ref] = new_len;
+    h->side_needs_compute = true;
     h->part_off_refs = 0;
     CU(h, cudaMemcpyAsync(h->d_ref_len + ref, &h->ref_len[ref], sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
@@ -1118,6 +1183,8 @@ int bc_set_count_variant(bc_handle *h, int variant)
 {
     if (!h || variant < 0 || variant > 2) return BC_ERR_ARG;
     h->variant = variant == 0 ? h->default_variant : variant;
+    for (Resident *r : h->resident)
+        if (r) r->walker = 0;
     return BC_OK;
 }
 

@@ -968,6 +968,7 @@ k1_count_tiled(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uin
         uint32_t *ctrl = const_cast<uint32_t *>(n_chunks_dev);
         __threadfence();
         if (atomicAdd(ctrl + 1, 1u) == warp_stride - 1u) {
+            ctrl[2] = n_chunks;                     // what this launch processed: the host learns whether a batch needs the walker
             ctrl[0] = 0u;
             ctrl[1] = 0u;
         }

@@ -25,13 +25,12 @@
 
 namespace bc {
 
-#ifndef BC_K1F_STAGES
-#define BC_K1F_STAGES 3
-#endif
 #ifndef BC_K1F_MINCTAS
 #define BC_K1F_MINCTAS 3
 #endif
-constexpr int kFastStages = BC_K1F_STAGES;
+constexpr uint32_t kFastSeqBuf = 3u * kSeqCap;   // staged 64-bit plane words per warp: 3 stages of kSeqCap words, or 4 of 3/4 kSeqCap
+constexpr uint32_t kFastStageShort = kFastSeqBuf / 4u;
+constexpr int kFastMaxStages = 4;
 constexpr uint32_t kFastRing = 128;            // ring entries: <= 64 pieces of a block + a partial trip (< 32)
 constexpr uint32_t kFastRpbMax = 32;
 constexpr uint32_t kAdvCode = 0x3C05Bu;        // 2 bits per CIGAR op: bit 0 = consumes reference, bit 1 = consumes query
@@ -59,8 +58,8 @@ struct K1FastCfg {
     // rows behind keep those (masked-away) reads inside the CTA's shared memory.
     static constexpr uint32_t ring_off = 0;
     static constexpr uint32_t seq_off = ring_off + kFastRing * 16u;
-    static constexpr uint32_t ok_off = seq_off + kFastStages * kSeqCap * 8u;
-    static constexpr uint32_t frow_off = ok_off + (HAS_OK ? kFastStages * kSeqCap * 4u : 0u);
+    static constexpr uint32_t ok_off = seq_off + kFastSeqBuf * 8u;
+    static constexpr uint32_t frow_off = ok_off + (HAS_OK ? kFastSeqBuf * 4u : 0u);
     static constexpr uint32_t frow_bytes = (uint32_t)NC * kCols * 2u;
     static constexpr uint32_t cov_off = frow_off + frow_bytes;
     static constexpr uint32_t cov_bytes = HAS_OK ? 0u : (kWin + 4u) * 4u;
@@ -72,7 +71,7 @@ struct K1FastCfg {
                   "TMA destinations are 16-byte aligned");
     static_assert(seq_off >= (kWin / 32 + 4) * 8 && frow_bytes >= (kWin / 32 + 4) * 8, "guard bands around the stages");
     static_assert(kFastRing % Q2 == 0 && kFastRing >= 64 + Q2, "a block's pieces and a partial trip fit the ring");
-    static_assert(kFastStages >= 2 && kFastStages <= 3, "stages");
+    static_assert(kFastStageShort % 4 == 0, "stages start on 32-byte boundaries");
 };
 template <int G, bool HAS_OK>
 __host__ __device__ constexpr uint32_t k1_fast_cta_smem_bytes()
@@ -356,7 +355,7 @@ __device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t 
 
 template <int G, bool HAS_OK>
 __global__ void __launch_bounds__(kK1Threads, BC_K1F_MINCTAS)
-k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb,
+k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb, uint32_t nst,
               Chunk *__restrict__ deferred, uint32_t *__restrict__ n_deferred)
 {
     using C = K1FastCfg<G, HAS_OK>;
@@ -399,9 +398,14 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
     uint32_t *const plane0 = cv.counts + ch.col_base;                       // plane A, column 0 of this slot
     uint32_t *const ds_plane = plane0 + (uint64_t)kPlaneDS * cv.stride;
 
+    // nst = 3 stages of kSeqCap words, or 4 of kFastStageShort when a block of reads is that short: block j + 2 is
+    // staged during block j into the stage block j + 2 - nst has left, and with four stages that tenant's pieces are
+    // always counted by then (with three, a trip that takes more entries than a block pushes -- 64 at G = 4 -- had
+    // to be padded every other block to free the stage).
+    const uint32_t stage_words = nst == 3u ? kSeqCap : kFastStageShort;
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kFastStages; s++) mbar_init_s(barb + 8u * s, 1);
+        for (int s = 0; s < kFastMaxStages; s++) mbar_init_s(barb + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (NC == 3) {
@@ -439,25 +443,26 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
     auto issue_block = [&](const Meta &m, uint32_t stg) {
         const uint32_t s0 = __shfl_sync(kFull, m.wb, 0), s1 = __shfl_sync(kFull, m.we, 31);
         if (lane == 0) {
-            const uint32_t s_lo = s0 & ~3u, s_n = min(((s1 + 3u) & ~3u) - s_lo, kSeqCap);     // 32 B / 16 B aligned sources
+            const uint32_t s_lo = s0 & ~3u, s_n = min(((s1 + 3u) & ~3u) - s_lo, stage_words);  // 32 B / 16 B aligned sources
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this stage
             const uint32_t bar = barb + 8u * stg;
             mbar_expect_tx_s(bar, s_n * 8u + (HAS_OK ? s_n * 4u : 0u));
             if (s_n) {
-                bulk_g2s_s(seqb + stg * (kSeqCap * 8u), bv.planes + s_lo, s_n * 8u, bar);
-                if (HAS_OK) bulk_g2s_s(okb + stg * (kSeqCap * 4u), bv.okmask + s_lo, s_n * 4u, bar);
+                bulk_g2s_s(seqb + stg * (stage_words * 8u), bv.planes + s_lo, s_n * 8u, bar);
+                if (HAS_OK) bulk_g2s_s(okb + stg * (stage_words * 4u), bv.okmask + s_lo, s_n * 4u, bar);
             }
         }
     };
 
     Meta M0 = load_meta(0), M1 = load_meta(1);
     issue_block(M0, 0);
-    if (nblk > 1 && kFastStages > 2) issue_block(M1, 1);
+    if (nblk > 1) issue_block(M1, 1);
     Cig C0 = load_cig(M0);
 
     uint32_t phases = 0;                            // bit s: parity to wait for on stage s
     uint32_t st = 0;                                // stage of the current block
-    uint32_t ring_head = 0, ring_tail = 0, mark = 0;      // mark: entries before it come from earlier blocks
+    uint32_t ring_head = 0, ring_tail = 0;
+    uint32_t mark1 = 0, mark2 = 0;                  // ring entries before mark1 / mark2 come from blocks before j / j - 1
     uint32_t win_lo = kNoWindow, cnt = 0;
     uint32_t def_begin = 0xFFFFFFFFu, def_end = 0xFFFFFFFFu;   // open run of deferred blocks (reads [begin, end))
     uint32_t pl[kW][NC][NB], pb[kW][NC], pc[kW][NC];
@@ -496,8 +501,8 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
     };
 
     // j == nblk is a virtual empty block: it drains the ring and does the final flush in the one trip / flush site.
-    // Stage schedule: block j lives in stage j % kFastStages; block j + kFastStages - 1 is staged during block j, as
-    // soon as the pieces of block j - 1 (the previous tenant of that stage) have all been counted.
+    // Stage schedule: block j lives in stage j % nst; block j + 2 is staged during block j, as soon as the pieces of
+    // block j + 2 - nst (the previous tenant of that stage) have all been counted.
     for (uint32_t j = 0; j <= nblk; j++) {
         const bool last = (j == nblk);
         const Meta M2 = load_meta(j + 2u);                                   // in flight during this block
@@ -510,7 +515,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
         // ---- straight-line decode of at most three ops (count.cpp:35-96): runs of M/=/X merge into pieces; run A
         //      starts at the read start, run B right after the first non-empty I/D/N.
         const uint32_t s_lo = __shfl_sync(kFull, M0.wb, 0) & ~3u;
-        const int qb = (int)(st * (kSeqCap * 32u) + (M0.wb - s_lo) * 32u);   // bit index of the read's first base
+        const int qb = (int)(st * (stage_words * 32u) + (M0.wb - s_lo) * 32u);   // bit index of the read's first base
         uint32_t nA, nB, ppB, sk_n, sk_pos;
         int pqB;
         bool bad;
@@ -539,7 +544,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
             sk_n = dl[0] + dl[1] + dl[2];
             sk_pos = dl[0] ? r[0] : (dl[1] ? r[1] : r[2]);
             const uint32_t qend = (uint32_t)qb + (M0.we - M0.wb) * 32u;      // end of the staged data of this read
-            bad = (M0.ce - M0.cb) > 3u || (M0.we - s_lo) > kSeqCap              // more ops; not (fully) staged
+            bad = (M0.ce - M0.cb) > 3u || (M0.we - s_lo) > stage_words          // more ops; not (fully) staged
                   || r[3] > ref_len || q[3] > qend                            // reference end; CIGAR overruns the read
                   || (bk[0] && bk[1] && ml[2] != 0u)                          // a third match run
                   || sk_n != max(dl[0], max(dl[1], dl[2])) || sk_n > kLaneSkipMax   // two D/N runs; a long one
@@ -565,7 +570,8 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
             for (uint32_t t = 3u; t < sk_n; t++) red_add(dp + t, 1u);
         }
         const uint32_t rpA = M0.start;
-        const bool want_issue = j + (uint32_t)(kFastStages - 1) < nblk;
+        const bool want_issue = j + 2u < nblk;
+        const uint32_t mark = nst == 3u ? mark1 : mark2;                     // the stage's last tenant ends here
 
         for (;;) {
             // ---- push the pending pieces that fit the window: rel + n <= kWin with rel = pos - win_lo as unsigned
@@ -637,13 +643,14 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
             // move the window to the lowest pending piece (the counters were flushed above)
             win_lo = __reduce_min_sync(kFull, min(nA ? rpA : 0xFFFFFFFFu, nB ? ppB : 0xFFFFFFFFu)) & ~31u;
         }
-        if (want_issue) issue_block(kFastStages > 2 ? M2 : M1, st == 0u ? (uint32_t)(kFastStages - 1) : st - 1u);
+        if (want_issue) issue_block(M2, st + 2u >= nst ? st + 2u - nst : st + 2u);
 
         // ---- rotate the pipelines
         // (the values loaded at the top of this block are first touched HERE, by instructions the compiler cannot
         //  hoist: left to itself it copies them right behind the loads and every block waits out the HBM latency)
-        mark = ring_tail;
-        st = (st == (uint32_t)kFastStages - 1u) ? 0u : st + 1u;
+        mark2 = mark1;
+        mark1 = ring_tail;
+        st = (st + 1u == nst) ? 0u : st + 1u;
         M0 = M1;
         M1.start = opaque(M2.start);
         M1.cb = opaque(M2.cb);
