@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libbasecount_b200.so")
 SOURCES = ["bc_api.cu"]
-HEADERS = ["bc_common.cuh", "k1_count.cuh", "k1_fast.cuh", "k2_stats.cuh", "k3_reduce.cuh", "bam_decode.h", "bam_index.h", "inflate_fast.h", "tsv_format.h", 
+HEADERS = ["bc_common.cuh", "k1_count.cuh", "k1_fast.cuh", "k2_stats.cuh", "k3_reduce.cuh", "bam_decode.h", "cigar_canon.h", "bam_index.h", "inflate_fast.h", "tsv_format.h", 
            os.path.join("..", "..", "include", "basecount_b200.h")]
 
 NVCC_FLAGS = [

@@ -11,6 +11,7 @@
 //
 // Host-only code (zlib + std::thread); compiled into the same C-ABI library as the kernels.
 #pragma once
+#include "cigar_canon.h"
 #include <stdint.h>
 #include <zlib.h>
 
@@ -616,7 +617,7 @@ inline void bc_bam_pack_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec
             if (!keep(v, ref_id, min_mapq)) continue;
             const Trim t = trimmed(v);
             p.r++;
-            p.c += v.n_cigar;
+            p.c += bccanon::canon_cigar(v.n_cigar, [&](uint32_t k) { return rd32(v.cig + 4 * k); }, nullptr);
             p.s += t.s1 - t.s0;
             p.w += (t.s1 - t.s0 + 31) / 32;
             for (uint32_t k = 0; k < v.n_cigar; k++) {
@@ -669,7 +670,7 @@ inline int bc_bam_pack_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b
             if (!keep(v, ref_id, min_mapq)) continue;
             const Trim t = trimmed(v);
             r++;
-            c += v.n_cigar;
+            c += bccanon::canon_cigar(v.n_cigar, [&](uint32_t k) { return rd32(v.cig + 4 * k); }, nullptr);
             w += (t.s1 - t.s0 + 31) / 32;
         }
         const uint64_t k = a / grain;
@@ -699,9 +700,9 @@ inline int bc_bam_pack_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b
             const uint64_t len = t.s1 - t.s0;
             starts[r] = (uint32_t)v.pos;
             uint64_t rp = 0;                                             // count.cpp:56,58 index the read unchecked
+            const uint32_t n_canon = bccanon::canon_cigar(v.n_cigar, [&](uint32_t k) { return rd32(v.cig + 4 * k); }, cigar + c);
             for (uint32_t q = 0; q < v.n_cigar; q++) {
                 const uint32_t word = rd32(v.cig + 4 * q), op = word & 15u, l = word >> 4;
-                cigar[c + q] = word;
                 if (op == 0u || op == 7u || op == 8u) {
                     if (l && rp + l > len) overrun = 1;
                     rp += l;
@@ -766,7 +767,7 @@ inline int bc_bam_pack_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b
                 if (okmask) okmask[w] = ok & ~odd;
             }
             r++;
-            c += v.n_cigar;
+            c += n_canon;
             cigar_off[r] = (uint32_t)c;
             seq_woff[r] = (uint32_t)w;
         }

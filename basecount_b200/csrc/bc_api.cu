@@ -1189,6 +1189,22 @@ int bc_set_count_variant(bc_handle *h, int variant)
 }
 
 // ------------------------------------------------------------------ host packer
+// The packers' CIGAR normal form (csrc/cigar_canon.h) for n reads: out_off[n + 1] and, when `out` is not NULL, the words.
+// Returns the number of words of the normal form.
+uint64_t bc_canonical_cigars(uint32_t n_reads, const uint32_t *cigar, const uint64_t *cigar_off, uint32_t *out, uint32_t *out_off)
+{
+    if (!cigar_off || !out_off || (n_reads && cigar_off[n_reads] && !cigar)) return ~0ull;
+    uint64_t m = 0;
+    out_off[0] = 0;
+    for (uint32_t i = 0; i < n_reads; i++) {
+        const uint32_t *src = cigar + cigar_off[i];
+        m += bccanon::canon_cigar((uint32_t)(cigar_off[i + 1] - cigar_off[i]), [&](uint32_t k) { return src[k]; }, out ? out + m : nullptr);
+        if (m > 0xFFFFFFFFull) return ~0ull;
+        out_off[i + 1] = (uint32_t)m;
+    }
+    return m;
+}
+
 uint64_t bc_pack_words(uint32_t n_reads, const uint64_t *seq_off)
 {
     uint64_t w = 0;

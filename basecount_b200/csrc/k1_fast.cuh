@@ -1,6 +1,6 @@
 // k1_fast.cuh -- K1, the lean counting kernel: CIGAR walk + per-position base counting on sm_100a for the
-// reads a straight-line decode can take (at most three CIGAR ops: M, M-I-M, M-D-M, clipped and =/X
-// spellings -- practically every short read).  Replaces the loop nest of the reference operator
+// reads a straight-line decode can take (M, M-I-M, M-D-M once clips are dropped and =/X are spelled M, which the
+// packers do -- practically every short read).  Replaces the loop nest of the reference operator
 // (basecount/count.cpp:22-97) together with k1_count_tiled (k1_count.cuh), which stays as the general walker:
 // a block of reads this kernel does not take (more ops, a run longer than a window, clipping at the
 // reference end, reads longer than a pipeline stage) is appended, untouched, to a list of deferred chunks
@@ -17,7 +17,7 @@
 //     staging, no staged-range bookkeeping;
 //   * sequence words are staged by one 1-D TMA bulk copy per block (two with a quality mask) into a ring of
 //     stages; the range a stage holds is recomputed from the metadata instead of being parked in shared memory;
-//   * the decode is multiply-add arithmetic on a 2-bit "consumes reference / consumes query" code per op;
+//   * the decode knows two shapes only, "M" and "M, I or D, M", in the packers' CIGAR normal form (cigar_canon.h);
 //   * the ring holds a whole block's pieces plus a partial trip, so pushes never wait for ring space, and an
 //     invalid window is a window position no read can fit (no validity flag).
 #pragma once
@@ -33,8 +33,6 @@ constexpr uint32_t kFastStageShort = kFastSeqBuf / 4u;
 constexpr int kFastMaxStages = 4;
 constexpr uint32_t kFastRing = 128;            // ring entries: <= 64 pieces of a block + a partial trip (< 32)
 constexpr uint32_t kFastRpbMax = 32;
-constexpr uint32_t kAdvCode = 0x3C05Bu;        // 2 bits per CIGAR op: bit 0 = consumes reference, bit 1 = consumes query
-                                               // (M,=,X: 3; I: 2; D,N: 1; S,H,P,B: 0 -- soft clips are trimmed already)
 constexpr uint32_t kNoWindow = 0x80000000u;    // a window position no piece fits (reference positions are < 2^31)
 
 template <int G, bool HAS_OK>
@@ -512,43 +510,29 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
             phases ^= 1u << st;
         }
 
-        // ---- straight-line decode of at most three ops (count.cpp:35-96): runs of M/=/X merge into pieces; run A
-        //      starts at the read start, run B right after the first non-empty I/D/N.
+        // ---- straight-line decode (count.cpp:35-96) of the two shapes a short read has in the packers' normal
+        //      form (csrc/cigar_canon.h): "M" and "M, I or D, M".  Piece A is the first match run, piece B the
+        //      second; a missing op reads as a zero word.  Any other CIGAR sends the block to the general walker.
         const uint32_t s_lo = __shfl_sync(kFull, M0.wb, 0) & ~3u;
         const int qb = (int)(st * (stage_words * 32u) + (M0.wb - s_lo) * 32u);   // bit index of the read's first base
         uint32_t nA, nB, ppB, sk_n, sk_pos;
         int pqB;
         bool bad;
         {
-            const uint32_t cw[3] = {C0.c0, C0.c1, C0.c2};
-            uint32_t r[4], q[4], ml[3], dl[3];
-            bool bk[3];
-            r[0] = M0.start;
-            q[0] = (uint32_t)qb;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const uint32_t len = cw[k] >> 4;
-                const uint32_t code = kAdvCode >> ((cw[k] & 15u) * 2u);
-                const uint32_t fr = code & 1u, fq = (code >> 1) & 1u;
-                const uint32_t ra = len * fr, qa = len * fq;                 // count.cpp:67-68, 75, 87
-                r[k + 1] = r[k] + ra;
-                q[k + 1] = q[k] + qa;
-                ml[k] = ra & (0u - fq);                                      // M/=/X
-                dl[k] = ra - ml[k];                                          // D/N
-                bk[k] = ra != qa;                                            // a non-empty I/D/N ends the match run
-            }
-            nA = ml[0] + (bk[0] ? 0u : ml[1]) + ((bk[0] || bk[1]) ? 0u : ml[2]);
-            nB = (bk[0] ? ml[1] : 0u) + ((bk[0] != bk[1]) ? ml[2] : 0u);
-            ppB = bk[0] ? r[1] : r[2];
-            pqB = (int)(bk[0] ? q[1] : q[2]);
-            sk_n = dl[0] + dl[1] + dl[2];
-            sk_pos = dl[0] ? r[0] : (dl[1] ? r[1] : r[2]);
+            const uint32_t ncig = M0.ce - M0.cb;
+            const uint32_t len1 = C0.c1 >> 4, op1 = C0.c1 & 15u;
+            nA = C0.c0 >> 4;
+            nB = C0.c2 >> 4;
+            const bool ins = op1 == 1u;                                       // count.cpp:74; otherwise D (count.cpp:80-87)
+            sk_n = ins ? 0u : len1;
+            sk_pos = M0.start + nA;
+            ppB = sk_pos + sk_n;
+            pqB = qb + (int)(nA + (ins ? len1 : 0u));
             const uint32_t qend = (uint32_t)qb + (M0.we - M0.wb) * 32u;      // end of the staged data of this read
-            bad = (M0.ce - M0.cb) > 3u || (M0.we - s_lo) > stage_words          // more ops; not (fully) staged
-                  || r[3] > ref_len || q[3] > qend                            // reference end; CIGAR overruns the read
-                  || (bk[0] && bk[1] && ml[2] != 0u)                          // a third match run
-                  || sk_n != max(dl[0], max(dl[1], dl[2])) || sk_n > kLaneSkipMax   // two D/N runs; a long one
-                  || nA > C::kMaxFit || nB > C::kMaxFit;
+            bad = ncig == 2u || ncig > 3u || ((C0.c0 | C0.c2) & 15u) != 0u || (ncig == 3u && (op1 - 1u) > 1u)   // shape
+                  || (M0.we - s_lo) > stage_words                             // not (fully) staged
+                  || ppB + nB > ref_len || (uint32_t)pqB + nB > qend           // reference end; CIGAR overruns the read
+                  || sk_n > kLaneSkipMax || nA > C::kMaxFit || nB > C::kMaxFit;
         }
         if (__any_sync(kFull, bad)) {                                        // the whole block goes to the general walker
             nA = 0u;

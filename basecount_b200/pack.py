@@ -80,8 +80,12 @@ def _alloc(n, dtype, pinned):
     return _lib.pinned_empty(n, dtype) if pinned else np.empty(int(n), dtype=dtype)
 
 
-def pack_batches(batches, min_base_quality: int = 0, pinned: bool = False) -> PackedBatch:
-    """Pack one ReadBatch per reference slot (in slot order) into a single device batch."""
+def pack_batches(batches, min_base_quality: int = 0, pinned: bool = False, canonical: bool = True) -> PackedBatch:
+    """Pack one ReadBatch per reference slot (in slot order) into a single device batch.
+
+    canonical: hand the device the CIGARs' normal form (csrc/cigar_canon.h: =/X spelled M, N spelled D, ignored
+    and empty operations dropped, equal neighbours merged -- the same counts by count.cpp:51,74,80,92).  False
+    keeps the BAM-native words as they are (tests: the general kernel takes those reads)."""
     L = _lib.lib()
     if isinstance(batches, ReadBatch):
         batches = [batches]
@@ -125,9 +129,18 @@ def pack_batches(batches, min_base_quality: int = 0, pinned: bool = False) -> Pa
     starts = _alloc(n, np.uint32, pinned)
     starts[:] = starts_src
     cigar_off = _alloc(n + 1, np.uint32, pinned)
-    cigar_off[:] = cigar_off64
-    cigar = _alloc(cigar_src.shape[0], np.uint32, pinned)
-    cigar[:] = cigar_src
+    if canonical:
+        cigar_src = np.ascontiguousarray(cigar_src, dtype=np.uint32)
+        cigar_off64 = np.ascontiguousarray(cigar_off64, dtype=np.uint64)
+        m = int(L.bc_canonical_cigars(n, _lib.ptr(cigar_src), _lib.ptr(cigar_off64), None, _lib.ptr(cigar_off)))
+        if m >= 2 ** 32:
+            raise TypeError("bc_canonical_cigars failed")
+        cigar = _alloc(m, np.uint32, pinned)
+        L.bc_canonical_cigars(n, _lib.ptr(cigar_src), _lib.ptr(cigar_off64), _lib.ptr(cigar), _lib.ptr(cigar_off))
+    else:
+        cigar_off[:] = cigar_off64
+        cigar = _alloc(cigar_src.shape[0], np.uint32, pinned)
+        cigar[:] = cigar_src
 
     n_words = int(L.bc_pack_words(n, _lib.ptr(seq_off)))
     if n_words >= 2 ** 32:

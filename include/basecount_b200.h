@@ -47,7 +47,12 @@ typedef struct bc_handle bc_handle;
  *
  *   starts[i]      reference_start of read i, relative to ITS reference  (count.cpp:35)
  *   cigar[...]     BAM-native words  len << 4 | op ; read i owns
- *                  cigar[cigar_off[i] .. cigar_off[i+1])                  (count.cpp:40-46)
+ *                  cigar[cigar_off[i] .. cigar_off[i+1])                  (count.cpp:40-46).
+ *                  Any CIGAR is counted correctly.  The packers of this library hand over a normal form
+ *                  with the same meaning (bc_canonical_cigars: =/X spelled M, N spelled D, S/H/P and
+ *                  zero-length operations dropped, equal neighbours merged -- count.cpp:51,74,80,92 treats
+ *                  them alike); reads whose CIGAR is "M" or "M, I or D, M" in that form take the fast
+ *                  counting kernel, everything else the general one.
  *   planes[...]    the query_alignment_sequence, 2 bits per base, bit-planar:
  *                  base j of read i is bit (j & 31) of word
  *                  planes[seq_woff[i] + (j >> 5)]; the low 32 bits of the 64-bit
@@ -201,6 +206,11 @@ uint64_t bc_kernel_launches(bc_handle *h);
  * All are CUDA; there is no host path.  Set it before bc_batch_upload: a resident batch keeps
  * the chunking of the variant it was uploaded under. */
 int bc_set_count_variant(bc_handle *h, int variant);
+
+/* The packers' CIGAR normal form (see bc_batch.cigar) of n_reads reads: out_off[n_reads + 1] and, when out is not
+ * NULL, the words (at most as many as went in).  Returns the number of words, or ~0 on bad arguments. */
+uint64_t bc_canonical_cigars(uint32_t n_reads, const uint32_t *cigar, const uint64_t *cigar_off, uint32_t *out,
+                             uint32_t *out_off);
 
 /* ---- native BAM decode (host code) -------------------------------------------
  * Replaces what the reference does per read through pysam: open (basecount/main.py:97-99),

@@ -17,11 +17,11 @@ def eng():
     e.close()
 
 
-def gpu_counts(eng, batches, ref_lens, mbq=0, variant=0):
+def gpu_counts(eng, batches, ref_lens, mbq=0, variant=0, canonical=True):
     from basecount_b200.pack import pack_batches
     eng.set_count_variant(variant)
     eng.begin(ref_lens)
-    eng.push(pack_batches(batches, mbq))
+    eng.push(pack_batches(batches, mbq, canonical=canonical))
     eng.sync()
     return [eng.counts(r) for r in range(len(ref_lens))]
 
@@ -51,6 +51,19 @@ def test_fuzz_vs_oracle(eng, mbq, variant):
         b = synth.fuzz_batch(seed, n_reads=300, ref_len=700, sorted_by_pos=(seed % 2 == 0))
         got = gpu_counts(eng, b, [700], mbq, variant)[0]
         assert np.array_equal(got, oracle_counts(b, 700, mbq)), seed
+
+
+@pytest.mark.parametrize("mbq", [0, 20])
+def test_bam_native_cigars_vs_oracle(eng, mbq):
+    """CIGARs handed over as the BAM holds them (no normal form: S/H/P, =/X, N, empty ops): the fast kernel takes
+    the reads that happen to be in its two shapes and defers every other block to the general walker."""
+    for seed in range(60, 66):
+        b = synth.fuzz_batch(seed, n_reads=300, ref_len=700, sorted_by_pos=(seed % 2 == 0))
+        got = gpu_counts(eng, b, [700], mbq, 0, canonical=False)[0]
+        assert np.array_equal(got, oracle_counts(b, 700, mbq)), seed
+    amp = select_reads(synth.amplicon_sample(seed=77, n_reads=20000, ref_len=6000, ref_name="x"), 0, 0)
+    got = gpu_counts(eng, amp, [6000], mbq, 0, canonical=False)[0]       # deferred and fast blocks interleave
+    assert np.array_equal(got, oracle_counts(amp, 6000, mbq))
 
 
 @pytest.mark.parametrize("read_len,n_reads", [(150, 6000), (400, 4000), (700, 2500), (1000, 1500), (5000, 300)])

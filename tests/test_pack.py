@@ -1,5 +1,7 @@
 """Host packer (native, runs without a GPU): planes / okmask / exception list."""
 import numpy as np
+
+from basecount_b200 import _lib
 import pytest
 
 from basecount_b200 import synth
@@ -55,12 +57,66 @@ def test_pack_multi_ref_and_empty():
     a = synth.fuzz_batch(1, n_reads=30)
     e = ReadBatch.from_lists([], [], [], [])
     c = synth.fuzz_batch(2, n_reads=50)
-    p = pack_batches([a, e, c], 0)
+    p = pack_batches([a, e, c], 0, canonical=False)
     assert p.ref_read_off.tolist() == [0, 30, 30, 80]
     assert p.n_reads == 80 and p.cigar_off[-1] == a.cigar.shape[0] + c.cigar.shape[0]
     assert p.aligned_bases == a.aligned_bases() + c.aligned_bases()
+    pc = pack_batches([a, e, c], 0)                 # the packers' normal form: never longer, same reads
+    assert pc.n_reads == 80 and pc.cigar_off[-1] <= p.cigar_off[-1] and pc.cigar_off[-1] == pc.cigar.shape[0]
+    assert np.array_equal(pc.planes, p.planes) and np.array_equal(pc.starts, p.starts)
     p0 = pack_batches(e, 0)
     assert p0.n_reads == 0 and p0.planes.shape[0] == 0
+
+
+def _walk(ops, start=0):
+    """What count.cpp:40-96 does with a CIGAR: (reference column, read position) of every counted base, and the
+    deletion / skip columns."""
+    r, q, bases, dels = start, 0, [], []
+    for op, ln in ops:
+        if op in (0, 7, 8):
+            bases += [(r + k, q + k) for k in range(ln)]
+            r += ln
+            q += ln
+        elif op == 1:
+            q += ln
+        elif op in (2, 3):
+            dels += list(range(r, r + ln))
+            r += ln
+    return bases, dels
+
+
+def test_canonical_cigars_mean_the_same():
+    """The packers' normal form (csrc/cigar_canon.h) against a plain restatement of the reference's walk, on random
+    CIGARs over all ten op codes with empty operations and long runs of equal neighbours."""
+    rng = np.random.default_rng(5)
+    L = _lib.lib()
+    cig, off = [], [0]
+    reads = []
+    for _ in range(400):
+        n = int(rng.integers(0, 9))
+        ops = [(int(rng.integers(0, 10)), int(rng.integers(0, 6))) for _ in range(n)]
+        reads.append(ops)
+        cig += [(ln << 4) | op for op, ln in ops]
+        off.append(len(cig))
+    reads.append([(0, (1 << 28) - 1), (7, 5)])                  # a merge that would not fit 28 bits stays two ops
+    cig += [(((1 << 28) - 1) << 4) | 0, (5 << 4) | 7]
+    off.append(len(cig))
+    cig = np.array(cig, dtype=np.uint32)
+    off = np.array(off, dtype=np.uint64)
+    n = len(reads)
+    out_off = np.zeros(n + 1, dtype=np.uint32)
+    m = int(L.bc_canonical_cigars(n, _lib.ptr(cig), _lib.ptr(off), None, _lib.ptr(out_off)))
+    out = np.zeros(m, dtype=np.uint32)
+    assert int(L.bc_canonical_cigars(n, _lib.ptr(cig), _lib.ptr(off), _lib.ptr(out), _lib.ptr(out_off))) == m
+    assert m <= cig.shape[0] and out_off[-1] == m
+    for i, ops in enumerate(reads):
+        canon = [(int(w & 15), int(w >> 4)) for w in out[out_off[i]:out_off[i + 1]]]
+        assert all(op in (0, 1, 2) and ln > 0 for op, ln in canon)
+        if i < n - 1:
+            assert all(a[0] != b[0] for a, b in zip(canon, canon[1:]))       # equal neighbours are merged
+            assert _walk(canon, 7) == _walk(ops, 7)
+        else:
+            assert canon == [(0, (1 << 28) - 1), (0, 5)]
 
 
 def test_pack_rejects_read_overrun():
