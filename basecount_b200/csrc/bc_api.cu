@@ -451,6 +451,10 @@ int bc_reset(bc_handle *h)
 // reads; shallow whole-genome coverage (30x) at the next one up.
 static int pick_group_width(const bc_handle *h, const bc_batch *b, uint64_t total_words)
 {
+    if (const char *g = std::getenv("BASECOUNT_B200_G")) {         // experiments: force the lane-group width
+        const int v = std::atoi(g);
+        if (v == 4 || v == 8 || v == 16 || v == 32) return v;
+    }
     uint64_t mean = b->mean_read_len;
     if (mean == 0 && b->n_reads) mean = total_words * 32u / b->n_reads;
     if (mean == 0) mean = 1;

@@ -196,18 +196,22 @@ __device__ __forceinline__ void csa_upper(const uint32_t (&c2a)[kW][NC], const u
 // every plane in registers, the pending carries of csa_upper, and -- without a quality mask -- the coverage taken
 // from the difference array at shared address covb: an in-place prefix sum, read, then zeroed for the next window).
 //   frow: NC rows x (kW*G window words x kFlushStride) uint16
-template <int G, int NC, int NB>
-__device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t (&pb)[kW][NC], uint32_t (&pc)[kW][NC],
-                                           uint32_t cnt, uint16_t *frow, uint32_t covb, uint32_t *__restrict__ counts,
-                                           uint64_t stride, int lane)
+// PIN = planes that can be non-zero in a lane's counters (cnt < 2^PIN pieces went in): the slot combine and the
+// extraction only touch those (and the R carry planes the combine adds), which is most of a flush after a short
+// window -- whole-genome coverage flushes every ~70 reads.
+template <int G, int NC, int NB, int PIN>
+__device__ __forceinline__ void flush_fast_body(uint32_t (&pl)[kW][NC][NB], uint32_t (&pb)[kW][NC], uint32_t (&pc)[kW][NC],
+                                                uint32_t cnt, uint16_t *frow, uint32_t covb, uint32_t *__restrict__ counts,
+                                                uint64_t stride, int lane)
 {
     constexpr int S = 32 / G;
     constexpr int R = S == 8 ? 3 : (S == 4 ? 2 : (S == 2 ? 1 : 0));      // combine rounds
     constexpr int kCols = (int)kFlushStride * kW * G;
     constexpr int kQ = 4;                                                 // counter slots per window word (NC real ones)
     constexpr int kN = kW * kQ;                                           // counter slots per lane (8)
+    constexpr int P = PIN + R;                                            // planes after the combine
     const int slot = lane / G, wl = lane % G;
-    uint32_t A[kN][NB + 3];
+    uint32_t A[kN][P];
 #pragma unroll
     for (int w = 0; w < kW; w++) {
 #pragma unroll
@@ -215,32 +219,34 @@ __device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t 
             const int i = w * kQ + k;
             if (k < NC) {
 #pragma unroll
-                for (int p = 0; p < NB; p++) A[i][p] = pl[w][k][p];
+                for (int p = 0; p < PIN; p++) A[i][p] = pl[w][k][p];
                 // pending carries of weight 8 / 16 are live iff that bit of cnt is set
-                uint32_t c = (cnt & 8u) ? pb[w][k] : 0u;
-                {
-                    const uint32_t t = A[i][3] & c;
-                    A[i][3] ^= c;
-                    c = t;
-                }
-                {
-                    const uint32_t d = (cnt & 16u) ? pc[w][k] : 0u;      // two carries into plane 4: full adder
-                    const uint32_t t = maj3(A[i][4], c, d);
-                    A[i][4] ^= c ^ d;
-                    c = t;
-                }
+                if (PIN > 3) {
+                    uint32_t c = (cnt & 8u) ? pb[w][k] : 0u;
+                    {
+                        const uint32_t t = A[i][3] & c;
+                        A[i][3] ^= c;
+                        c = t;
+                    }
+                    if (PIN > 4) {
+                        const uint32_t d = (cnt & 16u) ? pc[w][k] : 0u;  // two carries into plane 4: full adder
+                        const uint32_t t = maj3(A[i][4], c, d);
+                        A[i][4] ^= c ^ d;
+                        c = t;
+                    }
 #pragma unroll
-                for (int p = 5; p < NB; p++) {
-                    const uint32_t t = A[i][p] & c;
-                    A[i][p] ^= c;
-                    c = t;
+                    for (int p = 5; p < PIN; p++) {
+                        const uint32_t t = A[i][p] & c;
+                        A[i][p] ^= c;
+                        c = t;
+                    }
                 }
             } else {
 #pragma unroll
-                for (int p = 0; p < NB; p++) A[i][p] = 0u;
+                for (int p = 0; p < PIN; p++) A[i][p] = 0u;
             }
 #pragma unroll
-            for (int p = NB; p < NB + 3; p++) A[i][p] = 0u;
+            for (int p = PIN; p < P; p++) A[i][p] = 0u;
         }
     }
     // ---- coverage from the difference array: lane l owns entries [l * 2G, (l + 1) * 2G)
@@ -271,7 +277,8 @@ __device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t 
             sts128(mine + 4u * (uint32_t)i, v);
         }
     }
-    // ---- bit-sliced sum over the read slots
+    // ---- bit-sliced sum over the read slots: each round a lane keeps half of its counter slots and adds the
+    //      partner's copies of them (ripple-carry over the planes, one more plane per round)
     int first = 0;                                    // counter index (w * kQ + k) of A[0] after the rounds
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -281,42 +288,46 @@ __device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t 
         if (up) first += h;
 #pragma unroll
         for (int i = 0; i < h; i++) {
+            if (NC == 3 && r == 0 && i == kQ - 1) continue;           // slot 3 of either window word is empty
             uint32_t carry = 0u;
 #pragma unroll
-            for (int p = 0; p < NB + r; p++) {
+            for (int p = 0; p < PIN + r; p++) {
                 const uint32_t mine = up ? A[h + i][p] : A[i][p];
                 const uint32_t give = up ? A[i][p] : A[h + i][p];
                 const uint32_t got = __shfl_xor_sync(kFull, give, d);
                 A[i][p] = mine ^ got ^ carry;
                 carry = maj3(mine, got, carry);
             }
-            A[i][NB + r] = carry;
+            A[i][PIN + r] = carry;
         }
     }
-    constexpr int kLeft = kN >> R;                    // counters this lane extracts
-    const bool high = cnt * (uint32_t)S >= 16u;       // planes 4.. can only be set once 16 inputs went in
-#pragma unroll 1
-    for (int jj = 0; jj < 8; jj++) {
+    // ---- extraction: byte t of acc = count of column jj + 8t (its low 8 bits; acc2 holds bits 8..), one shift and
+    //      one (x & mask) | acc per plane with every shift amount an immediate
+    constexpr int kLeft = kN >> R;                    // counter slots this lane extracts
 #pragma unroll
-        for (int i = 0; i < kLeft; i++) {
-            uint32_t acc = 0u, acc2 = 0u;             // byte t = count of column jj + 8t: low 8 bits / bits 8..
+    for (int i = 0; i < kLeft; i++) {
+        const int ci = first + i, w = ci / kQ, k = ci % kQ;
+        uint16_t *const dst = frow + k * kCols + (kW * wl + w) * (int)kFlushStride;
 #pragma unroll
-            for (int p = 0; p < 4; p++) acc += ((A[i][p] >> jj) & 0x01010101u) << p;
-            if (high) {
+        for (int jj = 0; jj < 8; jj++) {
+            uint32_t acc = 0u, acc2 = 0u;
 #pragma unroll
-                for (int p = 4; p < 8 && p < NB + R; p++) acc += ((A[i][p] >> jj) & 0x01010101u) << p;
-#pragma unroll
-                for (int p = 8; p < NB + R; p++) acc2 += ((A[i][p] >> jj) & 0x01010101u) << (p - 8);
+            for (int p = 0; p < P && p < 8; p++) {
+                const uint32_t t = p <= jj ? A[i][p] >> (jj - p) : A[i][p] << (p - jj);
+                acc |= t & (0x01010101u << p);
             }
-            const uint32_t ev = (acc & 0x00FF00FFu) + ((acc2 & 0x00FF00FFu) << 8);               // columns jj, jj+16
-            const uint32_t od = ((acc >> 8) & 0x00FF00FFu) + (((acc2 >> 8) & 0x00FF00FFu) << 8);  // columns jj+8, jj+24
-            const int ci = first + i, w = ci / kQ, k = ci % kQ;
+#pragma unroll
+            for (int p = 8; p < P; p++) {
+                const uint32_t t = (p - 8) <= jj ? A[i][p] >> (jj - (p - 8)) : A[i][p] << ((p - 8) - jj);
+                acc2 |= t & (0x01010101u << (p - 8));
+            }
+            const uint32_t ev = P > 8 ? __byte_perm(acc, acc2, 0x6240) : (acc & 0x00FF00FFu);             // columns jj, jj+16
+            const uint32_t od = P > 8 ? __byte_perm(acc, acc2, 0x7351) : ((acc >> 8) & 0x00FF00FFu);      // columns jj+8, jj+24
             if (k < NC) {                             // (slot 3 of a window word is empty without a quality mask)
-                uint16_t *dst = frow + k * kCols + (kW * wl + w) * (int)kFlushStride + jj;
-                dst[0] = (uint16_t)ev;
-                dst[16] = (uint16_t)(ev >> 16);
-                dst[8] = (uint16_t)od;
-                dst[24] = (uint16_t)(od >> 16);
+                dst[jj] = (uint16_t)ev;
+                dst[jj + 16] = (uint16_t)(ev >> 16);
+                dst[jj + 8] = (uint16_t)od;
+                dst[jj + 24] = (uint16_t)(od >> 16);
             }
         }
     }
@@ -339,6 +350,16 @@ __device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t 
         if (lane < 4) sts32(covb + 4u * (uint32_t)(32 * kW * G + lane), 0u);
     }
     __syncwarp();
+}
+
+template <int G, int NC, int NB>
+__device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t (&pb)[kW][NC], uint32_t (&pc)[kW][NC],
+                                           uint32_t cnt, uint16_t *frow, uint32_t covb, uint32_t *__restrict__ counts,
+                                           uint64_t stride, int lane)
+{
+    if (cnt < 32u) flush_fast_body<G, NC, NB, 5>(pl, pb, pc, cnt, frow, covb, counts, stride, lane);
+    else if (NB > 7 && cnt < 128u) flush_fast_body<G, NC, NB, 7>(pl, pb, pc, cnt, frow, covb, counts, stride, lane);
+    else flush_fast_body<G, NC, NB, NB>(pl, pb, pc, cnt, frow, covb, counts, stride, lane);
 #pragma unroll
     for (int w = 0; w < kW; w++) {
 #pragma unroll
