@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BASECOUNT_B200_LIB: another build of the same library (kernel A/B experiments); still no fallback
 LIB_PATH = os.environ.get("BASECOUNT_B200_LIB") or os.path.join(_HERE, "csrc", "libbasecount_b200.so")
 
-BC_OK, BC_ERR_ARG, BC_ERR_INDEX, BC_ERR_CUDA, BC_ERR_STATE, BC_ERR_READ_OVERRUN = range(6)
+BC_OK, BC_ERR_ARG, BC_ERR_INDEX, BC_ERR_CUDA, BC_ERR_STATE, BC_ERR_READ_OVERRUN, BC_ERR_MISSING_QUAL = range(7)
 
 _u32p = ctypes.POINTER(ctypes.c_uint32)
 _u64p = ctypes.POINTER(ctypes.c_uint64)

@@ -112,6 +112,37 @@ def _record_offsets(buf: bytes, p: int) -> np.ndarray:
     return np.frombuffer(offs, dtype=np.int64) if len(offs) else np.zeros(0, np.int64)
 
 
+_AUX_SIZE = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4}
+
+
+def _find_cg_tag(buf: bytes, a: int, end: int):
+    """(offset of the first word, number of words) of a CG:B,I tag among the optional fields buf[a:end], or None."""
+    while a + 3 <= end:
+        tag, ty = buf[a:a + 2], buf[a + 2:a + 3]
+        a += 3
+        if ty in _AUX_SIZE:
+            a += _AUX_SIZE[ty]
+        elif ty in (b"Z", b"H"):
+            z = buf.find(b"\0", a, end)
+            if z < 0:
+                raise ValueError("truncated BAM record")
+            a = z + 1
+        elif ty == b"B":
+            if a + 5 > end:
+                raise ValueError("truncated BAM record")
+            sub, cnt = buf[a:a + 1], struct.unpack_from("<I", buf, a + 1)[0]
+            if sub not in _AUX_SIZE:
+                raise ValueError("malformed BAM optional field")
+            if tag == b"CG" and sub == b"I":
+                if a + 5 + 4 * cnt > end:
+                    raise ValueError("truncated BAM record")
+                return a + 5, cnt
+            a += 5 + _AUX_SIZE[sub] * cnt
+        else:
+            raise ValueError("malformed BAM optional field")
+    return None
+
+
 def _ragged_gather(u8: np.ndarray, starts: np.ndarray, lens: np.ndarray):
     """Concatenate u8[starts[i] : starts[i]+lens[i]] for all i; returns (bytes, offsets)."""
     off = np.zeros(lens.size + 1, dtype=np.int64)
@@ -148,7 +179,19 @@ def decode_bam_bytes(buf: bytes) -> Records:
     s_start = c_start + 4 * n_cigar
     q_start = s_start + (l_seq + 1) // 2
 
-    cig_bytes, cb_off = _ragged_gather(u8, c_start, 4 * n_cigar)
+    # A CIGAR of more than 65535 operations is stored as the placeholder "<l_seq>S<span>N" with the real CIGAR in
+    # the CG:B,I tag (SAM spec 4.2.2); htslib / pysam's cigartuples (basecount/main.py:173) hand out the real one.
+    cg_start, cg_n = c_start, n_cigar
+    for i in np.flatnonzero(n_cigar == 2):
+        w0, w1 = struct.unpack_from("<II", buf, int(c_start[i]))
+        if (w0 & 15) == 4 and (w0 >> 4) == int(l_seq[i]) and (w1 & 15) == 3:
+            end = int(offs[i + 1]) if i + 1 < n else len(buf)
+            hit = _find_cg_tag(buf, int(q_start[i] + l_seq[i]), end)
+            if hit is not None:
+                if cg_start is c_start:
+                    cg_start, cg_n = c_start.copy(), n_cigar.copy()
+                cg_start[i], cg_n[i] = hit
+    cig_bytes, cb_off = _ragged_gather(u8, cg_start, 4 * cg_n)
     cigar = np.ascontiguousarray(cig_bytes).view("<u4").astype(np.uint32)
     cigar_off = cb_off // 4
 
@@ -230,9 +273,14 @@ class NativeBam:
         from . import _lib
         from .records import ReadBatch
         rec_b = self.n if rec_b is None else rec_b
+        min_mapping_quality = max(int(min_mapping_quality), 0)      # MAPQ is unsigned: a negative threshold keeps everything
         nr, nc, nb = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
-        self._L.bc_bam_select_sizes(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), ctypes.byref(nr),
-                                    ctypes.byref(nc), ctypes.byref(nb))
+        rc = self._L.bc_bam_select_sizes(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), ctypes.byref(nr),
+                                         ctypes.byref(nc), ctypes.byref(nb))
+        if rc == _lib.BC_ERR_MISSING_QUAL:
+            raise TypeError("a read has no base qualities (QUAL '*'): the reference's bcount raises TypeError on None")
+        if rc != _lib.BC_OK:
+            raise TypeError(f"bc_bam_select_sizes failed with status {rc}")
         n = nr.value
         starts = np.empty(n, np.uint32)
         cigar = np.empty(nc.value, np.uint32)
@@ -256,8 +304,12 @@ def _native_pack(self, ref_id: int, min_mapping_quality: int = 0, min_base_quali
     if min_base_quality < 0:
         raise TypeError("min_base_quality must be unsigned")
     rec_b = self.n if rec_b is None else rec_b
+    min_mapping_quality = max(int(min_mapping_quality), 0)          # MAPQ is unsigned: a negative threshold keeps everything
     z = np.zeros(6, np.uint64)
-    if self._L.bc_bam_pack_sizes(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), _lib.ptr(z)) != 0:
+    rc = self._L.bc_bam_pack_sizes(self._h, rec_a, rec_b, int(ref_id), int(min_mapping_quality), _lib.ptr(z))
+    if rc == _lib.BC_ERR_MISSING_QUAL:
+        raise TypeError("a read has no base qualities (QUAL '*'): the reference's bcount raises TypeError on None")
+    if rc != 0:
         raise TypeError("bc_bam_pack_sizes failed")
     n, n_cigar, n_words, n_bases, aligned, is_sorted = (int(x) for x in z)
     if n >= 2 ** 32 or n_cigar >= 2 ** 32 or n_words >= 2 ** 32:

@@ -314,6 +314,46 @@ inline bool view(const bc_bam *b, uint64_t i, RecView &v)
     v.cig = p + 36 + v.l_read_name;
     v.seq = v.cig + 4ull * v.n_cigar;
     v.qual = v.seq + (v.l_seq + 1ull) / 2;
+    // A CIGAR of more than 65535 operations does not fit n_cigar_op: BAM stores the placeholder
+    // "<l_seq>S<reference span>N" and the real CIGAR in the CG:B,I tag (SAM spec 4.2.2); htslib -- and so pysam's
+    // cigartuples, basecount/main.py:173 -- hands out the real one.  A placeholder without the tag is malformed.
+    if (v.n_cigar == 2 && (rd32(v.cig) & 15u) == 4u && (rd32(v.cig) >> 4) == v.l_seq && (rd32(v.cig + 4) & 15u) == 3u) {
+        const uint8_t *a = v.qual + v.l_seq, *end = p + (e - o);
+        bool found = false;
+        while (a + 3 <= end) {
+            const uint8_t t0 = a[0], t1 = a[1], ty = a[2];
+            a += 3;
+            uint64_t sz = 0;
+            if (ty == 'A' || ty == 'c' || ty == 'C') sz = 1;
+            else if (ty == 's' || ty == 'S') sz = 2;
+            else if (ty == 'i' || ty == 'I' || ty == 'f') sz = 4;
+            else if (ty == 'Z' || ty == 'H') {
+                const uint8_t *z = a;
+                while (z < end && *z) z++;
+                if (z >= end) return false;
+                sz = (uint64_t)(z - a) + 1;
+            } else if (ty == 'B') {
+                if (a + 5 > end) return false;
+                const uint8_t sub = a[0];
+                const uint64_t cnt = rd32(a + 1);
+                const uint64_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0;
+                if (es == 0) return false;
+                if (t0 == 'C' && t1 == 'G' && sub == 'I') {
+                    if (a + 5 + 4 * cnt > end || cnt > 0xFFFFFFFFull) return false;
+                    v.cig = a + 5;
+                    v.n_cigar = (uint32_t)cnt;
+                    found = true;
+                    break;
+                }
+                sz = 5 + es * cnt;
+            } else {
+                return false;
+            }
+            if (sz > (uint64_t)(end - a)) return false;
+            a += sz;
+        }
+        (void)found;                       // (without the tag the record keeps its two operations, as in htslib)
+    }
     return true;
 }
 
@@ -321,6 +361,10 @@ inline bool keep(const RecView &v, int32_t ref_id, uint32_t min_mapq)
 {
     return !(v.flag & 4u) && v.mapq >= min_mapq && v.ref_id == ref_id;      // basecount/main.py:165-166
 }
+
+// QUAL '*' is stored as 0xFF bytes: pysam then returns None for query_alignment_qualities and the reference's
+// bcount raises TypeError for the whole chunk (the pybind11 cast at count.cpp:11), whatever min_base_quality is.
+inline bool missing_qual(const RecView &v) { return v.l_seq > 0 && v.qual[0] == 0xFF; }
 
 }  // namespace bcbam
 
@@ -467,17 +511,20 @@ inline void bc_bam_core_impl(const bc_bam *b, int32_t *ref_id, int32_t *pos, uin
 }
 
 // Sizes of the selection: kept reads, their CIGAR ops and their soft-clip-trimmed bases.
-inline void bc_bam_select_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
+// Returns false if a kept read has no QUAL (the reference raises TypeError there).
+inline bool bc_bam_select_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
                                      uint64_t *n_reads, uint64_t *n_cigar, uint64_t *n_bases)
 {
     using namespace bcbam;
     std::atomic<uint64_t> nr(0), nc(0), nb(0);
+    std::atomic<int> noqual(0);
     parallel_for(b->threads, rec_b - rec_a, 1 << 13, [&](uint64_t a, uint64_t e) {
         uint64_t r = 0, c = 0, s = 0;
         RecView v;
         for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
             view(b, i, v);
             if (!keep(v, ref_id, min_mapq)) continue;
+            if (missing_qual(v)) noqual = 1;
             uint32_t lead, trail;
             clips(v.cig, v.n_cigar, lead, trail);
             const uint64_t s0 = std::min<uint64_t>(lead, v.l_seq);
@@ -493,6 +540,7 @@ inline void bc_bam_select_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t r
     *n_reads = nr;
     *n_cigar = nc;
     *n_bases = nb;
+    return noqual == 0;
 }
 
 // Fill a ReadBatch for the selection.  Arrays sized by bc_bam_select_sizes (offset arrays n+1).
@@ -578,6 +626,7 @@ inline void bc_bam_select_fill_impl(const bc_bam *b, uint64_t rec_a, uint64_t re
 struct bc_pack_sizes {
     uint64_t n_reads, n_cigar, n_words, n_bases, aligned_bases;
     uint32_t sorted;                         // starts are non-decreasing
+    uint32_t missing_qual;                   // a kept read has no QUAL (the reference raises TypeError there)
 };
 
 namespace bcbam {
@@ -607,14 +656,15 @@ inline void bc_bam_pack_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec
 {
     using namespace bcbam;
     const uint64_t n = rec_b - rec_a, grain = 1 << 13, chunks = (n + grain - 1) / grain;
-    struct Part { uint64_t r, c, w, s, al; int32_t first, last; bool sorted, any; };
+    struct Part { uint64_t r, c, w, s, al; int32_t first, last; bool sorted, any, noqual; };
     std::vector<Part> parts(chunks ? chunks : 1);
     parallel_for(b->threads, n, grain, [&](uint64_t a, uint64_t e) {
-        Part p = {0, 0, 0, 0, 0, 0, 0, true, false};
+        Part p = {0, 0, 0, 0, 0, 0, 0, true, false, false};
         RecView v;
         for (uint64_t i = rec_a + a; i < rec_a + e; i++) {
             view(b, i, v);
             if (!keep(v, ref_id, min_mapq)) continue;
+            if (missing_qual(v)) p.noqual = true;
             const Trim t = trimmed(v);
             p.r++;
             p.c += bccanon::canon_cigar(v.n_cigar, [&](uint32_t k) { return rd32(v.cig + 4 * k); }, nullptr);
@@ -631,7 +681,7 @@ inline void bc_bam_pack_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec
         }
         parts[a / grain] = p;
     });
-    bc_pack_sizes z = {0, 0, 0, 0, 0, 1};
+    bc_pack_sizes z = {0, 0, 0, 0, 0, 1, 0};
     bool any = false;
     int32_t last = 0;
     for (uint64_t k = 0; k < chunks; k++) {
@@ -641,6 +691,7 @@ inline void bc_bam_pack_sizes_impl(const bc_bam *b, uint64_t rec_a, uint64_t rec
         z.n_words += p.w;
         z.n_bases += p.s;
         z.aligned_bases += p.al;
+        if (p.noqual) z.missing_qual = 1;
         if (!p.any) continue;
         if (!p.sorted || (any && p.first < last)) z.sorted = 0;
         last = p.last;

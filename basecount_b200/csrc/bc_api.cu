@@ -1401,8 +1401,7 @@ int bc_bam_select_sizes(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t
                         uint64_t *n_reads, uint64_t *n_cigar, uint64_t *n_bases)
 {
     if (!b || !n_reads || !n_cigar || !n_bases || rec_a > rec_b || rec_b > b->rec_off.size() - 1) return BC_ERR_ARG;
-    bc_bam_select_sizes_impl(b, rec_a, rec_b, ref_id, min_mapq, n_reads, n_cigar, n_bases);
-    return BC_OK;
+    return bc_bam_select_sizes_impl(b, rec_a, rec_b, ref_id, min_mapq, n_reads, n_cigar, n_bases) ? BC_OK : BC_ERR_MISSING_QUAL;
 }
 
 int bc_bam_select_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,
@@ -1425,7 +1424,7 @@ int bc_bam_pack_sizes(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t r
     out6[3] = z.n_bases;
     out6[4] = z.aligned_bases;
     out6[5] = z.sorted;
-    return BC_OK;
+    return z.missing_qual ? BC_ERR_MISSING_QUAL : BC_OK;
 }
 
 int bc_bam_pack_fill(const bc_bam *b, uint64_t rec_a, uint64_t rec_b, int32_t ref_id, uint32_t min_mapq,

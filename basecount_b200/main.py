@@ -26,15 +26,6 @@ from .version import __version__
 
 BASES = ("A", "C", "G", "T", "DS", "N")          # column order of the count matrix (count.cpp:16-17, main.py:16)
 
-_ENGINE = None
-
-
-def _engine() -> Engine:
-    global _ENGINE
-    if _ENGINE is None:
-        _ENGINE = Engine(0)
-    return _ENGINE
-
 
 # ----------------------------------------------------------------------------- alignment input
 def _records_via_pysam(bam):
@@ -144,16 +135,33 @@ def get_references(all_references, references=None):
 
 # ----------------------------------------------------------------------------- counting
 class Pileup:
-    """Counts of one BAM held on the device, plus lazily fetched statistics."""
+    """Counts of one BAM held on the device, plus lazily fetched statistics.
 
-    def __init__(self, engine, references, lengths, num_reads, show_n_bases):
+    A Pileup made without an explicit engine owns its own (a handle of the C-ABI library with its accumulators):
+    the reference computes a BaseCount's data eagerly (main.py:266-278), so two live objects never see each
+    other; here the numbers stay on the device until they are asked for, and must not be overwritten by the next
+    BAM that is counted."""
+
+    def __init__(self, engine, references, lengths, num_reads, show_n_bases, owns_engine=False):
         self.engine = engine
         self.references = references
         self.lengths = lengths
         self.num_reads = num_reads
         self.show_n_bases = show_n_bases
+        self.owns_engine = owns_engine
         self._stats = {}
         self._counts = {}
+
+    def close(self):
+        if self.owns_engine and self.engine is not None:
+            self.engine.close()
+        self.engine = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def counts(self, i):
         if i not in self._counts:
@@ -170,12 +178,26 @@ def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quali
                      show_n_bases=False, engine=None) -> Pileup:
     """BAM -> device count matrices (the numeric part of get_basecounts, main.py:119-189)."""
     rec = _RecordSource(bam)
-    refs = get_references(rec.ref_names, references)
-    ids = [rec.ref_names.index(r) for r in refs]
-    lengths = [int(rec.ref_lengths[i]) for i in ids]
-    eng = engine or _engine()
-    num_reads = [0] * len(refs)
-    if refs:
+    owns = engine is None
+    eng = None
+    try:
+        refs = get_references(rec.ref_names, references)
+        ids = [rec.ref_names.index(r) for r in refs]
+        lengths = [int(rec.ref_lengths[i]) for i in ids]
+        eng = engine if engine is not None else Engine(0)
+        num_reads = [0] * len(refs)
+        _count_into(eng, rec, ids, lengths, num_reads, min_base_quality, min_mapping_quality, chunk_size)
+    except BaseException:
+        if owns and eng is not None:
+            eng.close()
+        raise
+    finally:
+        rec.close()
+    return Pileup(eng, refs, lengths, num_reads, show_n_bases, owns_engine=owns)
+
+
+def _count_into(eng, rec, ids, lengths, num_reads, min_base_quality, min_mapping_quality, chunk_size):
+    if ids:
         eng.begin(lengths)
         # The reference flushes every `chunk_size` kept reads (main.py:142); the counts do not
         # depend on where the chunks fall, so chunking here only bounds the packed buffers.
@@ -201,8 +223,6 @@ def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quali
                 packed = pack_batches(batches, min_base_quality)
             eng.push(packed)
             eng.sync()
-    rec.close()
-    return Pileup(eng, refs, lengths, num_reads, show_n_bases)
 
 
 def build_rows(ref, counts, st, show_n_bases=False, long_format=False):
@@ -265,11 +285,14 @@ def get_basecounts(bam, references=None, min_base_quality=0, min_mapping_quality
                    show_n_bases=False, long_format=False):
     """Same contract as the reference: {ref: {"rows": [...], "num_reads": int}} (main.py:192-205)."""
     pile = count_alignments(bam, references, min_base_quality, min_mapping_quality, chunk_size, show_n_bases)
-    out = {}
-    for i, ref in enumerate(pile.references):
-        out[ref] = {"rows": build_rows(ref, pile.counts(i), pile.stats(i), show_n_bases, long_format),
-                    "num_reads": pile.num_reads[i]}
-    return out
+    try:
+        out = {}
+        for i, ref in enumerate(pile.references):
+            out[ref] = {"rows": build_rows(ref, pile.counts(i), pile.stats(i), show_n_bases, long_format),
+                        "num_reads": pile.num_reads[i]}
+        return out
+    finally:
+        pile.close()
 
 
 def column_names(show_n_bases=False, long_format=False):
@@ -297,8 +320,21 @@ class BaseCount:
         self._show_n, self._long = show_n_bases, long_format
         self._pile = count_alignments(bam, references, min_base_quality, min_mapping_quality, chunk_size, show_n_bases)
         self.references = list(self._pile.references)
-        self.reference_lengths = dict(zip(self.references, self._pile.lengths))
+        # the reference's reference_lengths is len(rows) (main.py:276-278): the reference length in wide format,
+        # K times it in long format, where every position is K rows
+        rep = (6 if show_n_bases else 5) if long_format else 1
+        self.reference_lengths = {r: n * rep for r, n in zip(self.references, self._pile.lengths)}
         self._data = None
+
+    def close(self):
+        """Release the device state behind this object (rows already materialised stay available)."""
+        self._pile.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     @property
     def data(self):
@@ -386,7 +422,7 @@ class BaseCount:
         if not hasattr(self, "_summary"):
             self._summary = self._pile.engine.summary(self._show_n)
         nz, cs, es = self._summary
-        L = self.reference_lengths[reference]
+        L = self._pile.lengths[i]
         return 100 * (int(nz[i]) / L), np.float64(int(cs[i])) / L, np.float64(es[i]) / L
 
     def amplicon_vectors(self, reference, scheme):

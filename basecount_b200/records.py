@@ -144,6 +144,12 @@ def select_reads(rec: Records, ref_id: int, min_mapping_quality: int = 0) -> Rea
     """
     keep = ((rec.flag & FLAG_UNMAPPED) == 0) & (rec.mapq >= min_mapping_quality) & (rec.ref_id == ref_id)
     idx = np.flatnonzero(keep)
+    # QUAL '*' is stored as 0xFF bytes: pysam returns None for query_alignment_qualities and the reference's bcount
+    # raises TypeError (pybind11 cannot cast None at count.cpp:11), whatever min_base_quality is
+    first = rec.seq_off[:-1][idx]
+    has = rec.seq_off[1:][idx] > first
+    if has.any() and bool((rec.qual[first[has]] == 0xFF).any()):
+        raise TypeError("a read has no base qualities (QUAL '*'): the reference's bcount raises TypeError on None")
     lead, trail = _leading_trailing_clips(rec)
     s0 = rec.seq_off[:-1][idx] + lead[idx]
     s1 = rec.seq_off[1:][idx] - trail[idx]

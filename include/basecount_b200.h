@@ -36,7 +36,8 @@ typedef enum bc_status {
     BC_ERR_INDEX = 2,      /* a counted event fell at refPos >= refLen -> IndexError */
     BC_ERR_CUDA = 3,       /* CUDA runtime failure (message in bc_last_error)        */
     BC_ERR_STATE = 4,      /* call out of order (no bc_begin, ...)                   */
-    BC_ERR_READ_OVERRUN = 5 /* CIGAR consumes more bases than the read holds (UB in the reference) */
+    BC_ERR_READ_OVERRUN = 5, /* CIGAR consumes more bases than the read holds (UB in the reference) */
+    BC_ERR_MISSING_QUAL = 6 /* a kept read has QUAL '*': pysam hands the reference None     -> TypeError  */
 } bc_status;
 
 typedef struct bc_handle bc_handle;

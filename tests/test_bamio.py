@@ -93,8 +93,9 @@ def _same_batch(a, b):
 
 def _clip_torture_records():
     """Records that exercise the soft-clip trimming rule (pysam query_alignment_*): H outside S on
-    either side, a CIGAR that is a single S, no CIGAR at all, missing SEQ, missing QUAL (0xFF),
-    odd lengths, IUPAC letters, unmapped records with a reference id, two references."""
+    either side, a CIGAR that is a single S, no CIGAR at all, missing SEQ, odd lengths, IUPAC letters,
+    unmapped records with a reference id, two references.  (Missing QUAL makes the reference raise:
+    test_missing_qualities_raise_type_error.)"""
     from basecount_b200.records import Records
     rng = np.random.default_rng(17)
     cigs = [
@@ -118,7 +119,7 @@ def _clip_torture_records():
             cigar += [(l << 4) | o for o, l in ct]
             coff.append(len(cigar))
             seq.append(letters[rng.integers(0, letters.size, size=qn)])
-            qual.append(np.full(qn, 0xFF, np.uint8) if k == 6 and rep % 2 else rng.integers(0, 61, size=qn).astype(np.uint8))
+            qual.append(rng.integers(0, 61, size=qn).astype(np.uint8))
             soff.append(soff[-1] + qn)
     return Records(["r0", "r1"], [1000, 700], np.asarray(ref_id, np.int32), np.asarray(pos, np.int32),
                    np.asarray(mapq, np.uint8), np.asarray(flag, np.uint16), np.asarray(cigar, np.uint32),
@@ -286,7 +287,15 @@ def test_random_records_roundtrip_and_native_selection(tmp_path):
             assert nb.n == rec.n
             for rid in (0, 1):
                 for mmq in (0, 30):
-                    _same_batch(nb.select(rid, mmq), select_reads(back, rid, mmq))
+                    try:
+                        want = select_reads(back, rid, mmq)
+                    except TypeError:                    # a kept read without QUAL: both paths refuse, as the reference
+                        with pytest.raises(TypeError):
+                            nb.select(rid, mmq)
+                        with pytest.raises(TypeError):
+                            nb.pack(rid, mmq, 0)
+                        continue
+                    _same_batch(nb.select(rid, mmq), want)
         finally:
             nb.close()
 
@@ -409,3 +418,79 @@ def test_native_decoder_on_randomly_damaged_files(tmp_path):
         finally:
             nb.close()
     assert raised >= 50
+
+
+def _raw_record(ref_id, pos, mapq, flag, cigar_words, seq_ascii, qual, aux=b"", name=b"q1\0"):
+    """One BAM alignment record (SAM spec 4.2) with optional fields, block_size included."""
+    code = {c: i for i, c in enumerate(b"=ACMGRSVTWYHKDBN")}
+    l_seq = len(seq_ascii)
+    packed = bytearray((l_seq + 1) // 2)
+    for j, ch in enumerate(seq_ascii):
+        packed[j >> 1] |= code[ch] << (4 if j % 2 == 0 else 0)
+    body = struct.pack("<iiBBHHHIiii", ref_id, pos, len(name), mapq, 4680, len(cigar_words), flag, l_seq, -1, -1, 0)
+    body += name + b"".join(struct.pack("<I", w) for w in cigar_words) + bytes(packed) + bytes(qual) + aux
+    return struct.pack("<i", len(body)) + body
+
+
+def _bam_with(records_bytes, ref_name="chrT", ref_len=5000):
+    rec0 = synth.take_records(synth.amplicon_sample(seed=5, n_reads=5, ref_len=ref_len, ref_name=ref_name),
+                              np.zeros(0, dtype=np.int64))
+    return bamio.bgzf_compress(bamio.encode_bam_bytes(rec0) + b"".join(records_bytes), 1)
+
+
+def test_long_cigar_is_taken_from_the_cg_tag(tmp_path):
+    """More than 65535 CIGAR operations: the record holds the placeholder <l_seq>S<span>N and the real CIGAR sits
+    in CG:B,I (SAM spec 4.2.2); htslib / pysam hand out the real one, and so must both decoders -- with other
+    optional fields of every type in front of the tag."""
+    real = [(3 << 4) | 0, (1 << 4) | 2, (5 << 4) | 0]                      # 3M1D5M over "ACGTACGT"
+    seq, qual = b"ACGTACGT", [30] * 8
+    aux = (b"NMC\x01" + b"XAA!" + b"XSs" + struct.pack("<h", -2) + b"XIi" + struct.pack("<i", 7) + b"XFf" + struct.pack("<f", 1.5) +
+           b"RGZgroup\0" + b"XHH1AE3\0" + b"XBBc" + struct.pack("<I", 3) + b"\x01\x02\x03" +
+           b"CGBI" + struct.pack("<I", len(real)) + b"".join(struct.pack("<I", w) for w in real) + b"ZZC\x05")
+    placeholder = [(len(seq) << 4) | 4, (9 << 4) | 3]
+    plain = _raw_record(0, 100, 60, 0, real, seq, qual, name=b"q0\0")
+    tagged = _raw_record(0, 200, 60, 0, placeholder, seq, qual, aux)
+    untagged = _raw_record(0, 300, 60, 0, placeholder, seq, qual, b"NMC\x01")     # no CG tag: stays S + N, as in htslib
+    p = str(tmp_path / "cg.bam")
+    open(p, "wb").write(_bam_with([plain, tagged, untagged]))
+    py = bamio.read_bam(p)
+    assert py.n == 3
+    assert py.cigar[py.cigar_off[0]:py.cigar_off[1]].tolist() == real
+    assert py.cigar[py.cigar_off[1]:py.cigar_off[2]].tolist() == real
+    assert py.cigar[py.cigar_off[2]:py.cigar_off[3]].tolist() == placeholder
+    nb = bamio.NativeBam(p, 2)
+    _same_batch(nb.select(0, 0), select_reads(py, 0, 0))
+    b = nb.select(0, 0)
+    assert b.cigar[b.cigar_off[1]:b.cigar_off[2]].tolist() == real and b.seq_off.tolist() == [0, 8, 16, 16]
+    packed = nb.pack(0, 0, 0)
+    assert packed.n_reads == 3 and packed.aligned_bases == 2 * 9 + 9
+    nb.close()
+
+
+def test_missing_qualities_raise_type_error(tmp_path):
+    """QUAL '*' (0xFF bytes): pysam gives the reference None and bcount raises TypeError (count.cpp:11), at any
+    min_base_quality -- but only for reads the filter keeps (main.py:165)."""
+    good = _raw_record(0, 100, 60, 0, [(8 << 4) | 0], b"ACGTACGT", [30] * 8, name=b"q0\0")
+    noqual = _raw_record(0, 200, 20, 0, [(8 << 4) | 0], b"ACGTACGT", [0xFF] * 8)
+    p = str(tmp_path / "nq.bam")
+    open(p, "wb").write(_bam_with([good, noqual]))
+    py = bamio.read_bam(p)
+    nb = bamio.NativeBam(p, 2)
+    for fn in (lambda mmq: nb.select(0, mmq), lambda mmq: nb.pack(0, mmq, 0), lambda mmq: select_reads(py, 0, mmq)):
+        with pytest.raises(TypeError):
+            fn(0)
+        fn(30)                                      # the read without qualities is filtered out: no error
+    nb.close()
+
+
+def test_negative_mapping_quality_keeps_every_mapped_read(tmp_path):
+    rec = synth.amplicon_sample(seed=6, n_reads=400, ref_len=3000, ref_name="chrT")
+    p = str(tmp_path / "m.bam")
+    bamio.write_bam(p, rec)
+    py = bamio.read_bam(p)
+    nb = bamio.NativeBam(p, 2)
+    want = select_reads(py, 0, -1)
+    assert want.n == select_reads(py, 0, 0).n > 0
+    _same_batch(nb.select(0, -1), want)
+    assert nb.pack(0, -1, 0).n_reads == want.n
+    nb.close()
