@@ -78,6 +78,14 @@ _SIGNATURES = {
     "bc_count_kernel_ms_history": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
     "bc_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
     "bc_set_count_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bc_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "bc_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "bc_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "bc_comm_allgather_u32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p]),
+    "bc_halo_merge": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]),
+    "bc_summary_allreduce_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "bc_set_length": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32]),
     "bc_canonical_cigars": (ctypes.c_uint64, [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     # exact native TSV rows (host code)
     "bc_format_tsv": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libbasecount_b200.so")
 SOURCES = ["bc_api.cu"]
-HEADERS = ["bc_common.cuh", "k1_count.cuh", "k1_fast.cuh", "k2_stats.cuh", "k3_reduce.cuh", "bam_decode.h", "cigar_canon.h", "bam_index.h", "inflate_fast.h", "tsv_format.h", 
+HEADERS = ["bc_common.cuh", "k1_count.cuh", "k1_fast.cuh", "k2_stats.cuh", "k3_reduce.cuh", "bam_decode.h", "cigar_canon.h", "nccl_dyn.h", "bam_index.h", "inflate_fast.h", "tsv_format.h", 
            os.path.join("..", "..", "include", "basecount_b200.h")]
 
 NVCC_FLAGS = [
@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()
     if out == OUT and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES + ["-lz"]
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES + ["-lz", "-ldl"]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

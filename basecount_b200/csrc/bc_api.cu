@@ -14,6 +14,7 @@
 #include "bam_decode.h"
 #include "bam_index.h"
 #include "tsv_format.h"
+#include "nccl_dyn.h"
 
 #include <algorithm>
 #include <atomic>
@@ -115,6 +116,11 @@ struct bc_handle {
     int walker_ctas_per_sm = 1;           // grid of the walker behind k1_count_fast: 1 until a batch deferred a lot
     int walker_max_ctas = 1;              // its occupancy limit
     uint64_t reads_since_sync = 0;
+    // region sharding across GPUs: an NCCL communicator owned by the handle (bc_comm_init); halo columns and the
+    // summarise scalars travel on the compute stream, no host synchronisation in between
+    ncclComm_t comm = nullptr;
+    int comm_world = 1, comm_rank = 0;
+    DevBuf halo_recv, comm_scratch;
     bool side_needs_compute = true;       // the next corrections kernel must wait for everything queued on the compute stream
     int dbg_skip = 0;                     // BASECOUNT_B200_DEBUG_SKIP (timing experiments only): 1 = no walker launch, 2 = no corrections
 };
@@ -332,6 +338,9 @@ void bc_destroy(bc_handle *h)
     if (h->d_counts64) cudaFree(h->d_counts64);
     if (h->d_col_base) cudaFree(h->d_col_base);
     if (h->d_ref_len) cudaFree(h->d_ref_len);
+    if (h->comm) bcnccl::api().CommDestroy(h->comm);
+    release(h->halo_recv);
+    release(h->comm_scratch);
     if (h->d_status) cudaFree(h->d_status);
     if (h->d_log2_tab) cudaFree(h->d_log2_tab);
     if (h->h_status) cudaFreeHost(h->h_status);
@@ -945,7 +954,7 @@ int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, 
 }
 
 static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
-                        double *entropy_sum, bool sync, long long min_cov = -1);
+                        double *entropy_sum, bool sync, long long min_cov = -1, bool allreduce = false);
 
 int bc_summary(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
                double *entropy_sum)
@@ -966,8 +975,16 @@ int bc_summary_min_coverage(bc_handle *h, int show_n, double norm, int64_t min_c
                         min_coverage < 0 ? 0 : (long long)min_coverage);
 }
 
+int bc_summary_allreduce_async(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
+                               double *entropy_sum)
+{
+    if (!h) return BC_ERR_ARG;
+    if (!h->comm) return fail(h, BC_ERR_STATE, "bc_summary_allreduce_async: bc_comm_init has not been called");
+    return summary_impl(h, show_n, norm, norm2, nonzero, cov_sum, entropy_sum, false, -1, true);
+}
+
 static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int64_t *nonzero, int64_t *cov_sum,
-                        double *entropy_sum, bool sync, long long min_cov)
+                        double *entropy_sum, bool sync, long long min_cov, bool allreduce)
 {
     if (!h || !nonzero || !cov_sum || !entropy_sum) return BC_ERR_ARG;
     if (h->n_refs == 0) return fail(h, BC_ERR_STATE, "bc_begin has not been called");
@@ -980,7 +997,7 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
         uint32_t maxb = 1;
         for (uint32_t r = 0; r < R; r++) {
             off[r] = (uint32_t)need;
-            const uint32_t nb = summary_blocks(h->ref_len[r]);
+            const uint32_t nb = summary_blocks(h->slot_cap[r]);    // (room for the slot at its longest: bc_set_length)
             need += nb;
             maxb = std::max(maxb, nb);
         }
@@ -1019,6 +1036,14 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
             h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off,
             h->d_partials, h->d_part_off + R, d_nz, d_cs, d_es);
     h->launches += 1;
+    if (allreduce && h->comm_world > 1) {
+        // every rank holds the sums over the columns it owns: the reference's numbers are the sums over ranks
+        // (main.py:479-485).  nonzero and cov_sum are adjacent int64 arrays; entropy sums are float64.
+        bcnccl::Api &nc = bcnccl::api();
+        ncclResult_t r1 = nc.AllReduce(d_nz, d_nz, (size_t)R * 2, ncclInt64, ncclSum, h->comm, h->compute);
+        ncclResult_t r2 = r1 == ncclSuccess ? nc.AllReduce(d_es, d_es, (size_t)R, ncclFloat64, ncclSum, h->comm, h->compute) : r1;
+        if (r2 != ncclSuccess) return fail(h, BC_ERR_CUDA, nc.GetErrorString(r2));
+    }
     h->pending.push_back({off, (size_t)R * 8, nonzero});
     h->pending.push_back({off + (size_t)R * 8, (size_t)R * 8, cov_sum});
     h->pending.push_back({off + (size_t)R * 16, (size_t)R * 8, entropy_sum});
@@ -1143,6 +1168,159 @@ int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len)
     CU(h, cudaMemcpyAsync(h->d_ref_len + ref, &h->ref_len[ref], sizeof(uint32_t), cudaMemcpyHostToDevice, h->compute));
     CU(h, cudaStreamSynchronize(h->compute));
     return BC_OK;
+}
+
+__global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+
+int bc_set_length(bc_handle *h, uint32_t ref, uint32_t new_len)
+{
+    if (!h) return BC_ERR_ARG;
+    if (ref >= h->n_refs || new_len > h->slot_cap[ref]) return fail(h, BC_ERR_ARG, "bc_set_length: out of range");
+    CU(h, cudaSetDevice(h->device));
+    // the overflow check of the last batch (side stream) may still read the old length: order the write behind it
+    CU(h, cudaStreamWaitEvent(h->compute, h->checked, 0));
+    h->ref_len[ref] = new_len;
+    h->side_needs_compute = true;
+    k_set_u32<<<1, 1, 0, h->compute>>>(h->d_ref_len + ref, new_len);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return BC_OK;
+}
+
+// ---- the communicator ---------------------------------------------------------------------------------------
+static int nccl_fail(bc_handle *h, ncclResult_t r, const char *what)
+{
+    bcnccl::Api &nc = bcnccl::api();
+    h->err = std::string(what) + ": " + (nc.GetErrorString ? nc.GetErrorString(r) : "NCCL error");
+    return BC_ERR_CUDA;
+}
+
+int bc_comm_unique_id(void *id128)
+{
+    if (!id128) return BC_ERR_ARG;
+    bcnccl::Api &nc = bcnccl::api();
+    if (!nc.ok()) {
+        g_create_error = nc.err;
+        return BC_ERR_CUDA;
+    }
+    ncclUniqueId id;
+    if (nc.GetUniqueId(&id) != ncclSuccess) {
+        g_create_error = "ncclGetUniqueId failed";
+        return BC_ERR_CUDA;
+    }
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(id128, &id, sizeof(id));
+    return BC_OK;
+}
+
+int bc_comm_init(bc_handle *h, int world, int rank, const void *id128)
+{
+    if (!h || !id128 || world < 1 || rank < 0 || rank >= world) return BC_ERR_ARG;
+    bcnccl::Api &nc = bcnccl::api();
+    if (!nc.ok()) return fail(h, BC_ERR_CUDA, nc.err.c_str());
+    if (h->comm) return fail(h, BC_ERR_STATE, "bc_comm_init: the handle already has a communicator");
+    CU(h, cudaSetDevice(h->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    ncclResult_t r = nc.CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        h->comm = nullptr;
+        return nccl_fail(h, r, "ncclCommInitRank");
+    }
+    h->comm_world = world;
+    h->comm_rank = rank;
+    return BC_OK;
+}
+
+int bc_comm_destroy(bc_handle *h)
+{
+    if (!h) return BC_ERR_ARG;
+    if (h->comm) {
+        cudaSetDevice(h->device);
+        cudaStreamSynchronize(h->compute);
+        bcnccl::api().CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    h->comm_world = 1;
+    h->comm_rank = 0;
+    return BC_OK;
+}
+
+int bc_comm_allgather_u32(bc_handle *h, uint32_t mine, uint32_t *out)
+{
+    if (!h || !out) return BC_ERR_ARG;
+    if (!h->comm) return fail(h, BC_ERR_STATE, "bc_comm_allgather_u32: bc_comm_init has not been called");
+    CU(h, cudaSetDevice(h->device));
+    const int W = h->comm_world;
+    int rc = ensure(h, h->comm_scratch, (size_t)(W + 1) * sizeof(uint32_t));
+    if (rc) return rc;
+    uint32_t *d = (uint32_t *)h->comm_scratch.p;
+    k_set_u32<<<1, 1, 0, h->compute>>>(d + W, mine);
+    ncclResult_t r = bcnccl::api().AllGather(d + W, d, 1, ncclUint32, h->comm, h->compute);
+    if (r != ncclSuccess) return nccl_fail(h, r, "ncclAllGather");
+    CU(h, cudaMemcpyAsync(out, d, (size_t)W * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+int bc_halo_merge(bc_handle *h, uint32_t ref, const uint32_t *bounds, const uint32_t *halos)
+{
+    if (!h || !bounds || !halos) return BC_ERR_ARG;
+    if (!h->comm) return fail(h, BC_ERR_STATE, "bc_halo_merge: bc_comm_init has not been called");
+    if (ref >= h->n_refs) return fail(h, BC_ERR_ARG, "bc_halo_merge: slot out of range");
+    const int W = h->comm_world, me = h->comm_rank;
+    for (int r = 0; r < W; r++)
+        if (bounds[r] > bounds[r + 1]) return fail(h, BC_ERR_ARG, "bc_halo_merge: boundaries must not decrease");
+    const uint64_t lo = bounds[me], hi = bounds[me + 1], own = hi - lo;
+    if (own + halos[me] != h->ref_len[ref] || own + halos[me] > h->slot_cap[ref])
+        return fail(h, BC_ERR_ARG, "bc_halo_merge: the slot must hold the owned columns plus this rank's halo");
+    if (h->d_counts64) return fail(h, BC_ERR_STATE, "bc_halo_merge: accumulators were folded to int64");
+    CU(h, cudaSetDevice(h->device));
+    struct Seg { int peer; uint64_t col; uint64_t n; };
+    std::vector<Seg> sends, recvs;
+    // what this rank sends: its halo covers global columns [hi, hi + halos[me])
+    for (int s = me + 1; s < W; s++) {
+        const uint64_t a = std::max<uint64_t>(bounds[s], hi), b = std::min<uint64_t>(bounds[s + 1], hi + halos[me]);
+        if (a < b) sends.push_back({s, a - lo, b - a});
+    }
+    // what it receives: halos of ranks to the left that reach into [lo, hi)
+    uint64_t recv_cols = 0;
+    for (int q = 0; q < me; q++) {
+        const uint64_t hq = bounds[q + 1];
+        const uint64_t a = std::max<uint64_t>(lo, hq), b = std::min<uint64_t>(hi, hq + halos[q]);
+        if (a < b) {
+            recvs.push_back({q, a - lo, b - a});
+            recv_cols += b - a;
+        }
+    }
+    int rc = ensure(h, h->halo_recv, (size_t)std::max<uint64_t>(recv_cols, 1) * kPlanes * sizeof(uint32_t));
+    if (rc) return rc;
+    bcnccl::Api &nc = bcnccl::api();
+    const uint64_t base = h->col_base[ref];
+    if (!sends.empty() || !recvs.empty()) {
+        // plane segments leave straight from the accumulators (K1 and its corrections are ahead on this stream)
+        ncclResult_t r = nc.GroupStart();
+        if (r != ncclSuccess) return nccl_fail(h, r, "ncclGroupStart");
+        for (const Seg &sg : sends)
+            for (int p = 0; p < kPlanes && r == ncclSuccess; p++)
+                r = nc.Send(h->d_counts + (uint64_t)p * h->stride + base + sg.col, sg.n, ncclUint32, sg.peer, h->comm, h->compute);
+        uint64_t at = 0;
+        for (const Seg &sg : recvs) {
+            for (int p = 0; p < kPlanes && r == ncclSuccess; p++)
+                r = nc.Recv((uint32_t *)h->halo_recv.p + at + (uint64_t)p * sg.n, sg.n, ncclUint32, sg.peer, h->comm, h->compute);
+            at += sg.n * kPlanes;
+        }
+        ncclResult_t re = nc.GroupEnd();
+        if (r != ncclSuccess || re != ncclSuccess) return nccl_fail(h, r != ncclSuccess ? r : re, "halo send/recv");
+        at = 0;
+        for (const Seg &sg : recvs) {
+            k_halo_add<<<(unsigned)((sg.n * kPlanes + 255) / 256), 256, 0, h->compute>>>(h->d_counts, h->stride, base + sg.col,
+                                                                                      (uint32_t)sg.n, (const uint32_t *)h->halo_recv.p + at);
+            h->launches++;
+            at += sg.n * kPlanes;
+        }
+    }
+    return bc_set_length(h, ref, (uint32_t)own);
 }
 
 // ------------------------------------------------------------------ instrumentation

@@ -1,4 +1,4 @@
-"""Multi-GPU partitioning of the counting path: one process per GPU, torch.distributed plumbing.
+"""Multi-GPU partitioning of the counting path: one process per GPU.
 
 Two ways the path shards:
 
@@ -11,8 +11,12 @@ Two ways the path shards:
     device buffers) and added there before the statistics, and the three --summarise scalars
     are all-reduced.  The count matrix itself is never reduced across GPUs.
 
-The functions take a *backend* (GpuBackend below; tests plug in a CPU stand-in over gloo) so
-the exchange logic is testable without GPUs.
+On GPUs the exchange lives in the C-ABI library (bc_comm_init / bc_halo_merge / bc_summary_allreduce_async: NCCL
+send/recv and all-reduce enqueued on the engine's compute stream, no host synchronisation between a batch and its
+summary).  The host only has to carry the 128-byte communicator id to every rank once -- `engine_comm` does it
+over whatever process group is around -- so torch is plumbing here, not part of the data path.  The same logic
+with the host moving the halo (exchange_halos over torch.distributed send/recv) is kept for a *backend* without
+the library's communicator; tests plug in a CPU stand-in over gloo.
 """
 from __future__ import annotations
 
@@ -58,14 +62,28 @@ def halo_columns(local: ReadBatch, region_len: int, cols_right: int) -> int:
     return int(min(max(over, 0), cols_right))
 
 
-class GpuBackend:
-    """Engine + torch CUDA buffers for the halo exchange."""
+_FAILED = 0xFFFFFFFF          # a rank's halo width when its count raised
 
-    def __init__(self, engine, device):
+
+def engine_comm(engine, dist, rank: int, world: int):
+    """Join `engine` to a communicator of its own over the ranks of the process group `dist` (any backend: the
+    group only broadcasts the 128-byte id).  Collective."""
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    engine.comm_init(world, rank, box[0])
+
+
+class GpuBackend:
+    """Engine (+ torch CUDA buffers when the host moves the halo itself).  native_comm: the engine holds the
+    library's own communicator (engine_comm) and the exchange is bc_halo_merge."""
+
+    def __init__(self, engine, device, native_comm=False):
         import torch
         self.torch = torch
         self.engine = engine
         self.device = device
+        self.native_comm = native_comm
 
     def begin(self, lens):
         self.engine.begin(lens)
@@ -140,13 +158,31 @@ def count_region_sharded(backend, dist, rank, world, batch: ReadBatch, ref_len: 
     local = local_reads if local_reads is not None else select_region(batch, lo, hi)
     h = halo_columns(local, hi - lo, ref_len - hi)
     backend.begin([hi - lo + h])
-    backend.count(local, min_base_quality)
+    # An alignment past the reference end raises IndexError on the rank that holds it (count.cpp .at()); the
+    # other ranks must not be left waiting in the collective that follows: the failure travels with the halo
+    # widths and every rank raises.
+    failed = None
+    try:
+        backend.count(local, min_base_quality)
+    except IndexError as e:
+        failed = e
+    mine_h = _FAILED if failed is not None else h
+    if getattr(backend, "native_comm", False):
+        halos = backend.engine.allgather_u32(mine_h)
+        if _FAILED in halos:
+            raise failed if failed is not None else IndexError("another rank counted past the end of the reference")
+        backend.engine.halo_merge(0, bounds, halos)          # asynchronous; the slot now holds the owned columns
+        return bounds
     if world > 1:
-        mine = backend.scalar_tensor([h], torch.int64)
+        mine = backend.scalar_tensor([mine_h], torch.int64)
         gathered = [backend.scalar_tensor([0], torch.int64) for _ in range(world)]
         dist.all_gather(gathered, mine)
         halos = [int(t.item()) for t in gathered]
+        if _FAILED in halos:
+            raise failed if failed is not None else IndexError("another rank counted past the end of the reference")
         exchange_halos(backend, dist, rank, world, bounds, halos)
+    elif failed is not None:
+        raise failed
     backend.truncate(0, hi - lo)
     return bounds
 
@@ -181,6 +217,12 @@ def summary_region_sharded(backend, dist, world, ref_len: int, show_n_bases: boo
     """(pc_reference_coverage, avg_depth, avg_entropy) of the whole reference (main.py:479-485)
     from per-rank K3 partials: all-reduce of {nonzero, coverage sum} (int64) and entropy sum (f64)."""
     import torch
+    if getattr(backend, "native_comm", False):
+        from . import _lib
+        out = (_lib.pinned_empty(1, np.int64), _lib.pinned_empty(1, np.int64), _lib.pinned_empty(1, np.float64))
+        backend.engine.summary_allreduce_async(out, show_n_bases)
+        backend.engine.sync()
+        return 100 * (int(out[0][0]) / ref_len), np.float64(int(out[1][0])) / ref_len, np.float64(out[2][0]) / ref_len
     nz, cs, es = backend.summary(show_n_bases)
     # one collective: the two integers ride as float64 (sums below 2^53 are exact)
     assert int(cs[0]) < 2 ** 53 // max(world, 1)

@@ -44,6 +44,7 @@ class Engine:
         self.device = device
         self.ref_lens = []
         self._keepalive = []
+        self.comm_world, self.comm_rank = 1, 0
 
     # -- lifecycle
     def close(self):
@@ -174,6 +175,50 @@ class Engine:
     def truncate(self, ref: int, new_len: int):
         _lib.check(self._h, self._L.bc_truncate(self._h, ref, new_len))
         self.ref_lens[ref] = int(new_len)
+
+    def set_length(self, ref: int, new_len: int):
+        """Asynchronous bc_truncate: a device-side write on the compute stream."""
+        _lib.check(self._h, self._L.bc_set_length(self._h, ref, new_len))
+        self.ref_lens[ref] = int(new_len)
+
+    # -- the library's own NCCL communicator (region sharding without torch on the data path)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        rc = _lib.lib().bc_comm_unique_id(buf)
+        if rc != _lib.BC_OK:
+            msg = _lib.lib().bc_last_error(None)
+            raise RuntimeError(f"bc_comm_unique_id failed: {msg.decode() if msg else rc}")
+        return buf.raw
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        _lib.check(self._h, self._L.bc_comm_init(self._h, int(world), int(rank), ctypes.c_char_p(unique_id)))
+        self.comm_world, self.comm_rank = int(world), int(rank)
+
+    def comm_destroy(self):
+        if self._h:
+            self._L.bc_comm_destroy(self._h)
+
+    def allgather_u32(self, value: int):
+        out = np.zeros(self.comm_world, dtype=np.uint32)
+        _lib.check(self._h, self._L.bc_comm_allgather_u32(self._h, int(value), _lib.ptr(out)))
+        return [int(x) for x in out]
+
+    def halo_merge(self, ref: int, bounds, halos):
+        """Collective and asynchronous: send this rank's halo columns to their owners, add what arrives, cut the
+        slot to the owned columns (csrc/bc_api.cu: bc_halo_merge)."""
+        b = np.ascontiguousarray(bounds, dtype=np.uint32)
+        hl = np.ascontiguousarray(halos, dtype=np.uint32)
+        assert b.shape[0] == self.comm_world + 1 and hl.shape[0] == self.comm_world
+        _lib.check(self._h, self._L.bc_halo_merge(self._h, ref, _lib.ptr(b), _lib.ptr(hl)))
+        self.ref_lens[ref] = int(b[self.comm_rank + 1] - b[self.comm_rank])
+
+    def summary_allreduce_async(self, out, show_n_bases: bool = False):
+        """summary_async + all-reduce over the communicator; `out` as in summary_async, valid after sync()."""
+        n1, n2 = norm_factors(show_n_bases)
+        _lib.check(self._h, self._L.bc_summary_allreduce_async(self._h, int(show_n_bases), n1, n2, _lib.ptr(out[0]),
+                                                               _lib.ptr(out[1]), _lib.ptr(out[2])))
 
     # -- instrumentation
     def timer_start(self):

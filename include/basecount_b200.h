@@ -167,15 +167,38 @@ int bc_amplicons(bc_handle *h, uint32_t ref, int show_n, double norm, double nor
 int bc_amplicons_async(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
                        uint32_t n_tiles, const int32_t *lo, const int32_t *hi, double *out, uint8_t *empty);
 
-/* ---- region sharding (config 5): boundary-column halo exchange --------------- */
-/* Copy / add the u32 counts of columns [col_lo, col_lo + n_cols) of a slot, all six
- * planes (6 * n_cols values, plane-major).  buf is a DEVICE pointer (e.g. a torch tensor
- * handed to torch.distributed send/recv over NCCL). */
+/* ---- region sharding (config 5): one process per GPU, boundary-column halo merge over NCCL ---------------
+ * The reference is cut at `bounds` (the np.linspace split of the reference's tests, tests/test_basecount.py:146-150);
+ * rank r owns global columns [bounds[r], bounds[r+1]) and counts the reads that START there into a slot of
+ * own + halos[r] columns (halos[r] = how far its reads run past its right boundary, known when they are packed).
+ * NCCL is bound at run time (libnccl.so.2, or BASECOUNT_B200_NCCL); nothing here needs PyTorch. */
+/* Rank 0 makes a 128-byte id (ncclGetUniqueId) and hands it to the other ranks by whatever the host has. */
+int bc_comm_unique_id(void *id128);
+/* Collective: every rank's handle joins the communicator (ncclCommInitRank on the handle's device). */
+int bc_comm_init(bc_handle *h, int world, int rank, const void *id128);
+int bc_comm_destroy(bc_handle *h);
+/* Collective, synchronous: out[r] = rank r's value (how the ranks learn each other's halo widths). */
+int bc_comm_allgather_u32(bc_handle *h, uint32_t mine, uint32_t *out);
+/* Collective, ASYNCHRONOUS (compute stream, no host synchronisation): the halo columns of slot `ref` go straight
+ * from the accumulators to the ranks that own them (ncclSend per plane segment; a skip may reach past several
+ * regions), what arrives from the ranks to the left is added to this rank's first columns, and the slot is cut
+ * to the owned columns (bc_set_length) -- so the statistics that follow cover exactly [bounds[rank], bounds[rank+1]).
+ * bounds: world + 1 entries, halos: world entries (bc_comm_allgather_u32). */
+int bc_halo_merge(bc_handle *h, uint32_t ref, const uint32_t *bounds, const uint32_t *halos);
+/* bc_summary_async followed by an all-reduce (sum) of the per-slot scalars over the communicator, on the
+ * compute stream: every rank gets the whole reference's numbers at the next bc_sync. */
+int bc_summary_allreduce_async(bc_handle *h, int show_n, double norm, double norm2,
+                               int64_t *nonzero, int64_t *cov_sum, double *entropy_sum);
+/* Set a slot's length to its first new_len columns (new_len <= its length at bc_begin) ASYNCHRONOUSLY, as a
+ * device-side write on the compute stream: drop the halo columns after a merge, restore them before the next
+ * batch of a stream of samples.  Counts are not touched. */
+int bc_set_length(bc_handle *h, uint32_t ref, uint32_t new_len);
+
+/* Building blocks of the same exchange for a host that moves the halo itself (e.g. torch.distributed): copy / add
+ * the u32 counts of columns [col_lo, col_lo + n_cols) of a slot, all six planes (6 * n_cols values, plane-major);
+ * buf is a DEVICE pointer.  These three wait for the stream. */
 int bc_halo_export(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, uint32_t *dev_buf);
 int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, const uint32_t *dev_buf);
-/* Set a slot's length to its first new_len columns, new_len <= its length at bc_begin: drops the halo
- * columns once they have been sent to the neighbour, so statistics cover only the columns this GPU
- * owns (and restores them before the next batch of a stream of samples).  Counts are not touched. */
 int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len);
 
 /* ---- host-side packer (replaces pybind11's list -> std::vector casters) -------- */

@@ -165,3 +165,38 @@ def test_region_helpers():
     parts = [bdist.select_region(b, int(bounds[r]), int(bounds[r + 1])) for r in range(8)]
     assert sum(p.n for p in parts) == b.n
     assert bdist.halo_columns(parts[0], int(bounds[1]), 4000 - int(bounds[1])) > 0
+
+
+def _failing_worker(rank, world, port, ref_len, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        batch = _reads(7, ref_len)
+        # one read that runs past the end of the reference: only the LAST rank's count raises (count.cpp .at())
+        bad = ReadBatch.from_lists(["ACGT" * 5], [[30] * 20], [ref_len - 5], [[(0, 20)]])
+        batch = synth.concat_batches([batch, bad])
+
+        class Raising(OracleBackend):
+            def count(self, b, mbq):
+                if int((b.starts.astype(np.int64) + 20 > self.length).any()) and rank == world - 1:
+                    raise IndexError("alignment counted past the end of the reference")
+                super().count(b, mbq)
+
+        try:
+            bdist.count_region_sharded(Raising(), dist, rank, world, batch, ref_len)
+            outcome = "returned"
+        except IndexError:
+            outcome = "IndexError"
+        open(os.path.join(out_dir, f"r{rank}.txt"), "w").write(outcome)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_index_error_on_one_rank_raises_on_every_rank(tmp_path):
+    """An alignment past the reference end is an IndexError in the reference (count.cpp:60-64,85); in a
+    region-sharded run only the rank that holds the read sees it, and the others must fail too instead of
+    waiting in the halo exchange."""
+    world = 3
+    mp.spawn(_failing_worker, args=(world, _free_port(), 6001, str(tmp_path)), nprocs=world, join=True)
+    assert [open(tmp_path / f"r{r}.txt").read() for r in range(world)] == ["IndexError"] * world
