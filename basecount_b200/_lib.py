@@ -77,6 +77,7 @@ _SIGNATURES = {
     "bc_last_count_kernel_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float)]),
     "bc_count_kernel_ms_history": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.c_int]),
     "bc_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "bc_h2d_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "bc_set_count_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bc_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "bc_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),

@@ -1341,6 +1341,36 @@ int bc_timer_stop(bc_handle *h, float *ms)
     return BC_OK;
 }
 
+int bc_h2d_probe(bc_handle *h, uint64_t bytes, int reps, double *gb_per_s)
+{
+    if (!h || !gb_per_s || bytes == 0 || reps <= 0) return BC_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    void *host = nullptr, *dev = nullptr;
+    CU(h, cudaHostAlloc(&host, bytes, cudaHostAllocDefault));
+    if (cudaMalloc(&dev, bytes) != cudaSuccess) {
+        cudaFreeHost(host);
+        return fail(h, BC_ERR_CUDA, "bc_h2d_probe: cudaMalloc failed");
+    }
+    std::memset(host, 1, bytes);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, h->copy);      // warm-up
+    cudaEventRecord(a, h->copy);
+    for (int i = 0; i < reps; i++) cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, h->copy);
+    cudaEventRecord(b, h->copy);
+    cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(dev);
+    cudaFreeHost(host);
+    if (e != cudaSuccess || ms <= 0.f) return fail(h, BC_ERR_CUDA, "bc_h2d_probe: copy failed");
+    *gb_per_s = (double)bytes * reps / (ms * 1e-3) / 1e9;
+    return BC_OK;
+}
+
 int bc_last_count_kernel_ms(bc_handle *h, float *ms)
 {
     return bc_count_kernel_ms_history(h, ms, 1) == 1 ? BC_OK : BC_ERR_STATE;

@@ -242,6 +242,12 @@ class Engine:
             raise RuntimeError("bc_count_kernel_ms_history failed")
         return [float(buf[i]) for i in range(got)]
 
+    def h2d_probe(self, nbytes: int, reps: int = 8) -> float:
+        """GB/s of plain pinned host-to-device copies of nbytes on this engine's copy stream (diagnostic)."""
+        g = ctypes.c_double()
+        _lib.check(self._h, self._L.bc_h2d_probe(self._h, int(nbytes), int(reps), ctypes.byref(g)))
+        return float(g.value)
+
     def kernel_launches(self) -> int:
         return int(self._L.bc_kernel_launches(self._h))
 

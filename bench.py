@@ -40,8 +40,9 @@ METRIC = "aligned_bases_per_sec"
 UNIT = "aligned bases/s"
 SAMPLES_PER_GPU = 12
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
-# DRAM bytes per K1 launch from the committed ncu capture (workload, variant, samples, reads/sample)
-NCU_TRAFFIC_BYTES = {("cfg2x12", 0, 12, 124_000): 190_132_480 + 7_092_736}      # capture r2g (profiles/r2_g_k1_summary.md)
+# DRAM bytes per K1 launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures of
+# the default shapes (profiles/r2_*_k1_summary.md)
+NCU_TRAFFIC_BYTES = {"cfg2x12": None, "cfg3": None, "cfg5": None}
 
 
 def parse():
@@ -50,13 +51,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2x12", choices=["cfg2x12", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default=None, choices=["cfg2x12", "cfg3", "cfg5"],
+                    help="one workload only; default: cfg2x12 as the line, with cfg3 / cfg5 sub-records at one GPU and the "
+                         "region-sharded cfg5 sub-record at several")
     ap.add_argument("--samples-per-gpu", type=int, default=SAMPLES_PER_GPU)
     ap.add_argument("--reads-per-sample", type=int, default=124_000)
     ap.add_argument("--cfg5-reads", type=int, default=12_888_833)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gen-samples", default=None, help="internal: synthesise these sample seeds into /tmp and exit")
-    ap.add_argument("--variant", type=int, default=0, help="0 tiled bit-sliced K1, 1 per-base atomics K1, 2 tiled K1 with walk and count in different warps")
+    ap.add_argument("--variant", type=int, default=0, help="0 k1_count_fast + general walker behind it, 1 per-base atomics K1, 2 the general walker alone")
     return ap.parse_args()
 
 
@@ -105,17 +108,17 @@ def make_samples(seeds, n_reads):
     return out
 
 
-def build_workload(args, rank):
+def build_workload(args, rank, workload):
     """Returns (list of ReadBatch lists [one per alternating batch], ref_lens, label)."""
     from basecount_b200 import synth
     from basecount_b200.records import select_reads
-    if args.workload == "cfg2x12":
+    if workload == "cfg2x12":
         s = args.samples_per_gpu
         base = 100 + rank * 2 * s
         sets = [make_samples(range(base, base + s), args.reads_per_sample),
                 make_samples(range(base + s, base + 2 * s), args.reads_per_sample)]
         return sets, [synth.SARS2_LEN] * s, f"cfg2_summarise_x{s}_samples_per_gpu"
-    if args.workload == "cfg3":
+    if workload == "cfg3":
         sets = [[select_reads(synth.deep_short_read_sample(seed=3 + 10 * rank + i), 0, 0)] for i in range(2)]
         return sets, [synth.SARS2_LEN], "cfg3_2M_reads_150bp"
     n = args.cfg5_reads
@@ -210,7 +213,7 @@ def cpu_baseline(samples, ref_len, n_samples=3):
         t_count += a
         t_stats += b
     return {"value": bases / (t_count + t_stats), "unit": UNIT, "cores": 1,
-            "kind": "reference" if use_ref else "port",
+            "kind": "reference+port" if use_ref else "port",
             "sample": f"{len(chosen)} of the step's samples ({bases} aligned bases): "
                       f"{'compiled count.cpp bcount (oracle/_ref)' if use_ref else 'C port of bcount'} {t_count:.2f}s "
                       f"+ python port of get_stats/summarise {t_stats:.2f}s; Python-list inputs prebuilt"}
@@ -241,7 +244,10 @@ def run_reference(args):
     from oracle import bcount as obc
     use_ref = obc.load_ref_bcount() is not None
     cores = os.cpu_count() or 1
-    per_step = max(1, min(args.samples_per_gpu, cores))
+    # our arm's step at N GPUs is 12 x N samples (weak scaling); the CPU arm keeps every host core busy with one
+    # sample each, up to that many -- a bounded sample of the step: the RATE it measures does not depend on how
+    # many samples a step holds once all cores are busy
+    per_step = max(1, min(args.samples_per_gpu * max(args.gpus, 1), cores))
     make_samples(range(100, 100 + per_step), args.reads_per_sample)          # fill the /tmp cache once, serially
     ctx = mp.get_context("fork")
     workers = []
@@ -269,15 +275,18 @@ def run_reference(args):
         a.send("stop")
         pr.join(timeout=10)
     value = bases * steps / dt
-    sample = (f"each step = {per_step} samples x {args.reads_per_sample} reads, one persistent process per sample on "
-              f"{cores} host cores; Python-list inputs prebuilt (pysam's job); steps capped at {steps}, warmup {warm}")
+    kind = "reference+port" if use_ref else "port"
+    sample = (f"bounded sample of the {args.samples_per_gpu * max(args.gpus, 1)}-sample step: {per_step} samples x "
+              f"{args.reads_per_sample} reads per timed step, one persistent process per sample on {cores} host cores "
+              f"(all busy); compiled count.cpp bcount (oracle/_ref) + python port of get_stats / summarise "
+              f"(the reference's main.py is not on the GPU box); Python-list inputs prebuilt (pysam's job); "
+              f"steps capped at {steps}, warmup {warm}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"cfg2_summarise_x{per_step}_samples", "reads_per_sample": args.reads_per_sample,
-                       "ref_len": synth.SARS2_LEN},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": per_step, "kind": "reference" if use_ref else "port",
-                             "sample": sample},
+            "config": {"workload": f"cfg2_summarise_x{args.samples_per_gpu}_samples_per_gpu", "samples_per_timed_step": per_step,
+                       "reads_per_sample": args.reads_per_sample, "ref_len": synth.SARS2_LEN},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": per_step, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -330,107 +339,360 @@ def bam_end_to_end(eng, with_reference):
     return out
 
 
-# ----------------------------------------------------------------------------- config 5 over N GPUs
-def run_region_sharded(args, local_reads, ref_len, label, rank, world, local, barrier, max_over_ranks, sum_over_ranks):
-    """One reference cut into `world` regions (strong scaling).  A step = zero the accumulators, count
-    the rank's reads (resident in HBM), send the halo columns to the ranks that own them (NCCL
-    send/recv on device buffers), add the received ones, cut the slot back to the owned columns,
-    the --summarise reductions and the all-reduce of the three scalars."""
-    import torch
-    import torch.distributed as dist
-    from basecount_b200 import dist as bdist
+# ----------------------------------------------------------------------------- measuring one workload
+def _peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def _pinned_out(n_slots):
+    from basecount_b200 import _lib as bclib
+    return (bclib.pinned_empty(n_slots, np.int64), bclib.pinned_empty(n_slots, np.int64),
+            bclib.pinned_empty(n_slots, np.float64))
+
+
+def oracle_guard(eng, workload, sets, ref_lens):
+    """The timed configuration must produce the ORACLE's counts (oracle/ is the checker here, never what is timed):
+    one sample of the step through oracle.bcount_flat, cell for cell.  For config 5 the first megabase -- reads are
+    taken by start, and a read that starts at or beyond a column never touches it, so the prefix is exact."""
+    from oracle import bcount as obc
+    from basecount_b200 import synth
+    b = sets[0][0]
+    got = eng.counts(0)
+    if workload == "cfg5":
+        cut = min(1_000_000, ref_lens[0])
+        idx = np.flatnonzero(b.starts < cut)
+        part = synth.take_batch(b, idx)
+        want = obc.bcount_flat(min(ref_lens[0], cut + 4096), 0, part).astype(np.int64)[:cut]
+        assert np.array_equal(got[:cut], want), "config 5: the first megabase differs from the oracle"
+        return f"first {cut} columns of the matrix ({idx.size} reads) equal oracle.bcount_flat"
+    want = obc.bcount_flat(ref_lens[0], 0, b).astype(np.int64)
+    assert np.array_equal(got, want), f"{workload}: sample 0 differs from the oracle"
+    return f"sample 0 of the step ({b.n} reads, {ref_lens[0]} x 6 cells) equals oracle.bcount_flat"
+
+
+def measure_workload(args, workload, rank, local, world, barrier, max_over_ranks, sum_over_ranks, steps, warmup,
+                     want_clocks=True):
+    """value / e2e / roofline of one workload on this rank's GPU (sample-sharded over ranks: no data-path collective)."""
     from basecount_b200.engine import Engine
     from basecount_b200.pack import pack_batches
+    sets, ref_lens, label = build_workload(args, rank, workload)
+    eng = Engine(local)
+    eng.set_count_variant(args.variant)
+    eng.begin(ref_lens)
+    packed = [pack_batches(s, 0, pinned=True) for s in sets]
+    resident = [eng.upload(p) for p in packed]
+    bases_per_step = [p.aligned_bases for p in packed]
+    alg_bytes = [p.algorithmic_bytes(ref_lens) for p in packed]
+    n_slots = len(ref_lens)
+    d2h_bytes = n_slots * 24
+    outs = [_pinned_out(n_slots) for _ in range(max(steps, warmup, 1))]
+
+    tiles = None
+    if workload == "cfg3":
+        # BASELINE configs[2] is --summarise-with-bed: the 98-amplicon scheme's windows go through K3 every step
+        from basecount_b200 import synth as _synth
+        from basecount_b200.scheme import load_scheme
+        bed = f"/tmp/bc_bench_artic_like_{rank}.bed"
+        _synth.artic_like_bed(bed)
+        sch = load_scheme(bed)
+        tiles = ([t[2]["inside_start"] for t in sch], [t[2]["inside_end"] for t in sch])
+        amp_outs = [(np.empty((6, len(sch)), np.float64), np.zeros(len(sch), np.uint8)) for _ in outs]
+        d2h_bytes += len(sch) * 49                # six float64 vectors + the empty-window flags
+
+    def step(i, out, src):
+        """Queue one step; results land in the pinned `out` arrays (valid after eng.sync())."""
+        eng.reset()
+        eng.push(src[i % len(src)])               # resident batch, or pinned host SoA -> H2D -> K1
+        eng.summary_async(out, False)             # K2 + K3, D2H of the per-sample scalars
+        if tiles is not None:                     # K2 rows + K3 segmented mean / median, results at the next sync
+            eng.amplicons_async(0, tiles[0], tiles[1], *amp_outs[i % len(amp_outs)])
+
+    step(0, outs[0], resident)
+    eng.sync()
+    guard = oracle_guard(eng, workload, sets, ref_lens)
+    nz, cs = outs[0][0].copy(), outs[0][1].copy()
+    c0 = eng.counts(0)
+    assert int(cs[0]) == int(c0[:, :5].sum()) and int(nz[0]) == int((c0[:, :5].sum(axis=1) != 0).sum())
+
+    # ---- value: inputs resident in HBM; the K steps are queued back to back (each step's
+    #      summary is copied to its own pinned slot) and the stream is drained at the end
+    for i in range(warmup):
+        step(i, outs[i], resident)
+    eng.sync()
+    clocks = ClockSampler(local) if want_clocks else None
+    if clocks:
+        clocks.start()
+    barrier()
+    launches0 = eng.kernel_launches()
+    eng.timer_start()
+    t_wall0 = time.perf_counter()
+    for i in range(steps):
+        step(i, outs[i], resident)
+    ms_dev = eng.timer_stop()
+    eng.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = eng.kernel_launches() - launches0
+    hist = eng.count_kernel_ms_history(min(steps, 256))          # most recent first
+    k1_ms = [(m, (steps - 1 - k) % len(resident)) for k, m in enumerate(hist)]
+    for i in range(steps):                                        # every step must have produced its summary
+        assert int(outs[i][1].sum()) > 0
+    ms_dev = max_over_ranks(ms_dev)
+    total_bases = sum_over_ranks(float(sum(bases_per_step[i % len(resident)] for i in range(steps))))
+    value = total_bases / (ms_dev * 1e-3)
+    clk = None
+    if clocks:
+        # the timed region is only milliseconds long, so keep the same steps running until nvidia-smi
+        # (100 ms period) has seen ~1.5 s of this load
+        t_end = time.perf_counter() + 1.5
+        i = 0
+        while time.perf_counter() < t_end:
+            step(i, outs[i % len(outs)], resident)
+            i += 1
+            if i % 64 == 0:
+                eng.sync()
+        eng.sync()
+        clk = clocks.stop()
+        clk["window"] = "timed region plus the same steps repeated for 1.5 s"
+
+    # ---- e2e: pinned host buffers through the C ABI, copies inside the timed region
+    for i in range(min(warmup, 3)):
+        step(i, outs[i], packed)
+    eng.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i, outs[i], packed)
+        eng.sync()                                # the caller reads this step's result before the next
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_bases / e2e_s
+    h2d = int(np.mean([packed[i % len(packed)].h2d_bytes() for i in range(steps)]))
+
+    # ---- roofline of the counting kernel (K1): algorithmic bytes / its own device time
+    peak, peak_src = _peak()
+    k1_avg_ms = float(np.mean([m for m, _ in k1_ms]))
+    k1_bytes = float(np.mean([alg_bytes[j] for _, j in k1_ms]))
+    achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9
+    k1_bases = float(np.mean([bases_per_step[j] for _, j in k1_ms]))
+    traffic = NCU_TRAFFIC_BYTES.get(workload) if (args.variant == 0 and _is_default_shape(args, workload)) else None
+    rec = {
+        "value": value, "unit": UNIT, "ms_per_step": ms_dev / steps, "steps": steps, "warmup": warmup,
+        "config": {"workload": label, "samples_per_gpu": n_slots, "reads_per_step_per_gpu": packed[0].n_reads,
+                   "aligned_bases_per_step_per_gpu": bases_per_step[0], "ref_len": ref_lens[0],
+                   "l2": f"inputs {packed[0].h2d_bytes() / 1e6:.0f} MB per step"
+                         + (" > 126 MB L2; " if packed[0].h2d_bytes() > 126e6 else "; ")
+                         + (f"{len(resident)} resident batches alternate" if len(resident) > 1 else
+                            "count planes + inputs exceed L2" if ref_lens[0] * 24 + packed[0].h2d_bytes() > 126e6 else
+                            "the accumulators are re-zeroed (both sets alternate) every step"),
+                   "timing": "CUDA events on the engine's compute stream; max over ranks", "k1_variant": args.variant,
+                   "oracle_guard": guard},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": 1e3 * e2e_s / steps, "timing": "host wall clock, device-synchronised both sides",
+                "h2d_gbs_step": h2d / (e2e_s / steps) / 1e9},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                                       "kernel on this workload (profiles/r2_*_k1_summary.md); null if not captured",
+                     "kernel": {0: "k1_count_fast (+ k1_count_tiled over what it defers: nothing on this workload)",
+                                1: "k1_count_per_base", 2: "k1_count_tiled"}[args.variant],
+                     "kernel_ms": k1_avg_ms, "algorithmic_bytes_per_launch": k1_bytes,
+                     "bytes_per_aligned_base": k1_bytes / k1_bases, "kernel_aligned_bases_per_s": k1_bases / (k1_avg_ms * 1e-3),
+                     "step_over_kernel": (value / max(world, 1)) / (k1_bases / (k1_avg_ms * 1e-3)),
+                     "peak_source": peak_src},
+        "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": t_wall,
+    }
+    state = {"eng": eng, "resident": resident, "sets": sets, "ref_lens": ref_lens, "packed": packed, "h2d": h2d}
+    return rec, state
+
+
+def _is_default_shape(args, workload):
+    if workload == "cfg2x12":
+        return args.samples_per_gpu == SAMPLES_PER_GPU and args.reads_per_sample == 124_000
+    if workload == "cfg5":
+        return args.cfg5_reads == 12_888_833
+    return True
+
+
+def release(state):
+    for r in state["resident"]:
+        r.free()
+    state["eng"].close()
+
+
+def h2d_control(eng, h2d_bytes, barrier, max_over_ranks, reps=8):
+    """Plain pinned cudaMemcpyAsync of one step's input bytes on every rank at once (bc_h2d_probe: cudaHostAlloc
+    memory, the engine's copy stream, CUDA events): what the platform gives the end-to-end path to work with
+    (PCIe / host memory shared by the ranks of one box).  Minimum over ranks."""
+    barrier()
+    g = eng.h2d_probe(h2d_bytes, reps)
+    return -max_over_ranks(-g)
+
+
+def cpu_baseline_cfg3(batch, ref_len):
+    """Reference CPU path of --summarise-with-bed on a quarter of the step's reads, one core: compiled bcount
+    (oracle/_ref) + the oracle's port of get_stats, the summarise block and the amplicon block (main.py:501-595)."""
+    from oracle import bcount as obc
+    from oracle import stats as ost
+    from basecount_b200 import synth
+    use_ref = obc.load_ref_bcount() is not None
+    part = synth.take_batch(batch, np.arange(0, batch.n, 4))
+    lists = part.to_lists()
+    bed = "/tmp/bc_bench_artic_like_cpu.bed"
+    synth.artic_like_bed(bed)
+    t0 = time.perf_counter()
+    counts = obc.load_ref_bcount()(ref_len, 0, *lists) if use_ref else obc.bcount_flat(ref_len, 0, part).tolist()
+    t1 = time.perf_counter()
+    cov, ent, sec = ost.per_position_vectors(counts)
+    ost.summary(cov, ent, ref_len)
+    win = [(d["inside_start"], d["inside_end"]) for _, _, d in ost.scheme_windows(bed)]
+    ost.amplicon_vectors(cov, ent, sec, win)
+    t2 = time.perf_counter()
+    bases = part.aligned_bases()
+    return {"value": bases / (t2 - t0), "unit": UNIT, "cores": 1, "kind": "reference+port" if use_ref else "port",
+            "sample": f"every 4th read of one step ({part.n} reads, {bases} aligned bases): bcount {t1 - t0:.2f}s + python "
+                      f"port of get_stats / summarise / amplicon block {t2 - t1:.2f}s; Python-list inputs prebuilt"}
+
+
+def cpu_baseline_cfg5(batch, ref_len):
+    """Reference CPU path of --summarise on the first megabase of the reference, one core (the full 64.4 Mb
+    would take ~12 minutes in get_stats alone): rate = aligned bases of that prefix / time."""
+    from oracle import bcount as obc
+    from oracle import stats as ost
+    from basecount_b200 import synth
+    use_ref = obc.load_ref_bcount() is not None
+    cut = min(1_000_000, ref_len)
+    part = synth.take_batch(batch, np.flatnonzero(batch.starts < cut - 200))
+    lists = part.to_lists()
+    t0 = time.perf_counter()
+    counts = obc.load_ref_bcount()(cut, 0, *lists) if use_ref else obc.bcount_flat(cut, 0, part).tolist()
+    t1 = time.perf_counter()
+    cov, ent, _ = ost.per_position_vectors(counts)
+    ost.summary(cov, ent, cut)
+    t2 = time.perf_counter()
+    bases = part.aligned_bases()
+    return {"value": bases / (t2 - t0), "unit": UNIT, "cores": 1, "kind": "reference+port" if use_ref else "port",
+            "sample": f"the first {cut} positions ({part.n} reads, {bases} aligned bases; the rate is what the full "
+                      f"reference would run at, extrapolated): bcount {t1 - t0:.2f}s + python port of get_stats / "
+                      f"summarise {t2 - t1:.2f}s; Python-list inputs prebuilt"}
+
+
+# ----------------------------------------------------------------------------- config 5 over N GPUs
+def measure_region_sharded(args, rank, world, local, barrier, max_over_ranks, sum_over_ranks, steps, warmup):
+    """One reference cut into `world` regions (strong scaling).  A step = restore the halo
+    columns, zero the accumulators, count the rank's reads (resident in HBM), bc_halo_merge (NCCL send/recv of the
+    halo plane segments to the ranks that own them, add what arrives, cut the slot to the owned columns), the
+    --summarise reductions and the all-reduce of the three scalars -- all enqueued on the engine's compute
+    stream by the C-ABI library: no host synchronisation inside a step, the K steps are queued back to back."""
+    import torch.distributed as dist
+    from basecount_b200 import dist as bdist
+    from basecount_b200 import synth
+    from basecount_b200.engine import Engine
+    from basecount_b200.pack import pack_batches
+    sets, ref_lens, label = build_workload(args, rank, "cfg5")
+    local_reads, ref_len = sets[0][0], ref_lens[0]
     bounds = bdist.region_bounds(ref_len, world)
     lo, hi = int(bounds[rank]), int(bounds[rank + 1])
-    h = bdist.halo_columns(local_reads, hi - lo, ref_len - hi)
-    mine = torch.tensor([h], dtype=torch.int64, device="cuda")
-    gathered = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    halos = [int(t.item()) for t in gathered]                 # known once the reads are packed
+    own = hi - lo
+    h = bdist.halo_columns(local_reads, own, ref_len - hi)
     eng = Engine(local)
-    be = bdist.GpuBackend(eng, torch.device("cuda", local))
-    eng.begin([hi - lo + h])
+    bdist.engine_comm(eng, dist, rank, world)                 # the process group only carries the 128-byte id
+    halos = eng.allgather_u32(h)                              # known once the reads are packed
+    eng.begin([own + h])
     packed = pack_batches([local_reads], 0, pinned=True)
     resident = eng.upload(packed)
     bases = packed.aligned_bases
+    outs = [_pinned_out(1) for _ in range(max(steps, warmup, 1))]
 
-    def step():
-        eng.truncate(0, hi - lo + h)                          # the halo columns are back
+    def step(i, src):
+        eng.set_length(0, own + h)                            # the halo columns are back (device-side write)
         eng.reset()
-        eng.push(resident)
-        eng.sync()
-        bdist.exchange_halos(be, dist, rank, world, bounds, halos)
-        eng.truncate(0, hi - lo)
-        return bdist.summary_region_sharded(be, dist, world, ref_len)
+        eng.push(src)
+        eng.halo_merge(0, bounds, halos)
+        eng.summary_allreduce_async(outs[i % len(outs)], False)
 
-    res = step()
-    # size-independent checks: every aligned base of every rank is in exactly one cell of the merged
-    # matrix (sum of coverage + N column), and all ranks hold the same all-reduced summary
+    step(0, resident)
+    eng.sync()
+    # checks: every aligned base of every rank is in exactly one cell of the merged matrix; every rank holds the
+    # same all-reduced summary; rank 0's columns equal the oracle's (nothing reaches it from the left)
     total_bases = sum_over_ranks(float(bases))
-    cells = sum_over_ranks(float(eng.counts(0).sum()))
+    got = eng.counts(0)
+    cells = sum_over_ranks(float(got.sum()))
     assert cells == total_bases, (cells, total_bases)
-    chk = torch.tensor([res[0], float(res[1]), float(res[2])], dtype=torch.float64, device="cuda")
-    ref = chk.clone()
-    dist.broadcast(ref, 0)
-    assert torch.equal(chk, ref)
-    for _ in range(args.warmup):
-        step()
+    mine = [float(outs[0][0][0]), float(outs[0][1][0]), float(outs[0][2][0])]
+    for v in mine:
+        assert max_over_ranks(v) == v and -max_over_ranks(-v) == v, "ranks disagree on the all-reduced summary"
+    assert int(mine[1]) == int(total_bases - sum_over_ranks(float(got[:, 5].sum())))
+    guard = None
+    if rank == 0:
+        from oracle import bcount as obc
+        cut = min(1_000_000, own)
+        part = synth.take_batch(local_reads, np.flatnonzero(local_reads.starts < cut))
+        want = obc.bcount_flat(cut + 4096, 0, part).astype(np.int64)[:cut]
+        assert np.array_equal(got[:cut], want), "region-sharded: rank 0's first megabase differs from the oracle"
+        guard = f"rank 0: first {cut} owned columns equal oracle.bcount_flat; cells over ranks == aligned bases"
+    for i in range(warmup):
+        step(i, resident)
+    eng.sync()
     clocks = ClockSampler(local)
     clocks.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.kernel_launches()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
+    eng.timer_start()
+    for i in range(steps):
+        step(i, resident)
+    ms = eng.timer_stop()
+    eng.sync()
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = max_over_ranks(ms)
     launches = eng.kernel_launches() - launches0
+    t_end = time.perf_counter() + 1.0                          # let nvidia-smi see the load
+    i = 0
+    while time.perf_counter() < t_end:
+        step(i, resident)
+        i += 1
+        if i % 32 == 0:
+            eng.sync()
+    eng.sync()
     clk = clocks.stop()
-    hist = eng.count_kernel_ms_history(min(args.steps, 256))
+    hist = eng.count_kernel_ms_history(min(steps, 256))
     k1_ms = max_over_ranks(float(np.mean(hist)))
     # e2e: the same step from pinned host buffers (H2D inside), result read back every step
-    def step_e2e():
-        eng.truncate(0, hi - lo + h)
-        eng.reset()
-        eng.push(packed)
-        eng.sync()
-        bdist.exchange_halos(be, dist, rank, world, bounds, halos)
-        eng.truncate(0, hi - lo)
-        return bdist.summary_region_sharded(be, dist, world, ref_len)
-    step_e2e()
+    step(0, packed)
+    eng.sync()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    for i in range(steps):
+        step(i, packed)
+        eng.sync()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
-    alg = packed.algorithmic_bytes([hi - lo + h])
+    peak, peak_src = _peak()
+    alg = packed.algorithmic_bytes([own + h])
     achieved = alg / (k1_ms * 1e-3) / 1e9
-    line = {"metric": METRIC, "value": total_bases * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": label, "ref_len": ref_len, "reads_total": int(sum_over_ranks(float(packed.n_reads))),
-                       "aligned_bases_total": total_bases, "halo_columns": halos,
-                       "collective": "NCCL send/recv of the halo columns + all-reduce of 3 scalars",
-                       "l2": f"inputs {packed.h2d_bytes() / 1e6:.0f} MB per rank per step; count planes "
-                             f"{(hi - lo) * 24 / 1e6:.0f} MB per rank",
-                       "timing": "CUDA events around the K steps (each step host-synchronised for the exchange); max over ranks"},
-            "e2e": {"value": total_bases * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": packed.h2d_bytes(),
-                    "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "timing": "host wall clock, device-synchronised both sides"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k1_count_tiled", "kernel_ms": k1_ms,
-                         "algorithmic_bytes_per_launch": alg, "note": "per rank (max over ranks of the mean K1 time)"},
-            "gpu_launches": int(launches), "clocks": clk, "cpu_baseline": None}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    rec = {"value": total_bases * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms / steps, "scaling": "strong",
+           "config": {"workload": label, "ref_len": ref_len, "reads_total": int(sum_over_ranks(float(packed.n_reads))),
+                      "aligned_bases_total": total_bases, "halo_columns": halos,
+                      "collective": "bc_halo_merge: ncclSend/ncclRecv of the halo plane segments + k_halo_add, then "
+                                    "ncclAllReduce of 3 scalars per step, all on the compute stream (library-owned communicator)",
+                      "l2": f"inputs {packed.h2d_bytes() / 1e6:.0f} MB per rank per step; count planes {own * 24 / 1e6:.0f} MB per rank",
+                      "timing": "CUDA events on the engine's compute stream around K steps queued back to back; max over ranks",
+                      "oracle_guard": guard},
+           "e2e": {"value": total_bases * steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": packed.h2d_bytes(),
+                   "d2h_bytes_per_step": 24, "ms_per_step": 1e3 * e2e_s / steps,
+                   "timing": "host wall clock, device-synchronised both sides"},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": None, "kernel": "k1_count_fast", "kernel_ms": k1_ms, "algorithmic_bytes_per_launch": alg,
+                        "note": "per rank (max over ranks of the mean K1 time)", "peak_source": peak_src},
+           "gpu_launches": int(launches), "clocks": clk}
     resident.free()
+    eng.comm_destroy()
     eng.close()
+    return rec
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -476,171 +738,61 @@ def main():
 
     import __graft_entry__ as ge
     ge.build()
-    from basecount_b200.engine import Engine
     from basecount_b200.hostbind import bind_to_device_node
-    from basecount_b200.pack import pack_batches
 
     numa = bind_to_device_node(local)              # pinned buffers on the GPU's NUMA node (matters for e2e at N > 1)
-    sets, ref_lens, label = build_workload(args, rank)
-    if args.workload == "cfg5" and world > 1:
-        run_region_sharded(args, sets[0][0], ref_lens[0], label, rank, world, local, barrier, max_over_ranks, sum_over_ranks)
+    comm = (barrier, max_over_ranks, sum_over_ranks)
+    default_line = args.workload is None
+    workload = args.workload or "cfg2x12"
+
+    if workload == "cfg5" and world > 1:           # explicit: the region-sharded run as the line itself
+        rec = measure_region_sharded(args, rank, world, local, *comm, args.steps, args.warmup)
+        line = {"metric": METRIC, "higher_is_better": True, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "cpu_baseline": None, **rec}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
         dist.destroy_process_group()
         return
-    eng = Engine(local)
-    eng.set_count_variant(args.variant)
-    eng.begin(ref_lens)
-    packed = [pack_batches(s, 0, pinned=True) for s in sets]
-    resident = [eng.upload(p) for p in packed]
-    bases_per_step = [p.aligned_bases for p in packed]
-    alg_bytes = [p.algorithmic_bytes(ref_lens) for p in packed]
-    d2h_bytes = len(ref_lens) * 24
 
-    from basecount_b200 import _lib as bclib
-    n_slots = len(ref_lens)
-
-    def pinned_out():
-        return (bclib.pinned_empty(n_slots, np.int64), bclib.pinned_empty(n_slots, np.int64),
-                bclib.pinned_empty(n_slots, np.float64))
-
-    outs = [pinned_out() for _ in range(max(args.steps, args.warmup, 1))]
-
-    tiles = None
-    if args.workload == "cfg3":
-        # BASELINE configs[2] is --summarise-with-bed: the 98-amplicon scheme's windows go through K3 every step
-        from basecount_b200 import synth as _synth
-        from basecount_b200.scheme import load_scheme
-        bed = f"/tmp/bc_bench_artic_like_{rank}.bed"
-        _synth.artic_like_bed(bed)
-        sch = load_scheme(bed)
-        tiles = ([t[2]["inside_start"] for t in sch], [t[2]["inside_end"] for t in sch])
-        amp_outs = [(np.empty((6, len(sch)), np.float64), np.zeros(len(sch), np.uint8)) for _ in outs]
-        d2h_bytes += len(sch) * 49                # six float64 vectors + the empty-window flags
-
-    def step_resident(i, out):
-        """Queue one step; results land in the pinned `out` arrays (valid after eng.sync())."""
-        eng.reset()
-        eng.push(resident[i % len(resident)])
-        eng.summary_async(out, False)             # K2 + K3, D2H of the per-sample scalars
-        if tiles is not None:                     # K2 rows + K3 segmented mean / median, results at the next sync
-            eng.amplicons_async(0, tiles[0], tiles[1], *amp_outs[i % len(amp_outs)])
-
-    def step_e2e(i, out):
-        eng.reset()
-        eng.push(packed[i % len(packed)])         # pinned host SoA -> H2D -> K1
-        eng.summary_async(out, False)
-        if tiles is not None:
-            eng.amplicons_async(0, tiles[0], tiles[1], *amp_outs[i % len(amp_outs)])
-
-    # ---- correctness guard: the timed configuration must produce the oracle's summary
-    # (size-independent property: the synthetic reads hold only A,C,G,T,N, so every aligned base
-    # lands in exactly one cell of its sample's matrix)
-    step_resident(0, outs[0])
-    eng.sync()
-    nz, cs = outs[0][0].copy(), outs[0][1].copy()
-    c0 = eng.counts(0)
-    assert int(c0.sum()) == sets[0][0].aligned_bases(), "cells do not add up to the aligned bases"
-    assert int(cs[0]) == int(c0[:, :5].sum()) and int(nz[0]) == int((c0[:, :5].sum(axis=1) != 0).sum())
-
-    # ---- value: inputs resident in HBM; the K steps are queued back to back (each step's
-    #      summary is copied to its own pinned slot) and the stream is drained at the end
-    for i in range(args.warmup):
-        step_resident(i, outs[i])
-    eng.sync()
-    clocks = ClockSampler(local)
-    clocks.start()
-    barrier()
-    launches0 = eng.kernel_launches()
-    eng.timer_start()
-    t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        step_resident(i, outs[i])
-    ms_dev = eng.timer_stop()
-    eng.sync()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = eng.kernel_launches() - launches0
-    hist = eng.count_kernel_ms_history(min(args.steps, 256))          # most recent first
-    k1_ms = [(m, (args.steps - 1 - k) % len(resident)) for k, m in enumerate(hist)]
-    for i in range(args.steps):                                        # every step must have produced its summary
-        assert int(outs[i][1].sum()) > 0
-    ms_dev = max_over_ranks(ms_dev)
-    total_bases = sum_over_ranks(float(sum(bases_per_step[i % len(resident)] for i in range(args.steps))))
-    value = total_bases / (ms_dev * 1e-3)
-    # clocks: the timed region is only milliseconds long, so keep the same steps running until
-    # nvidia-smi (100 ms period) has seen ~1.5 s of this load
-    t_end = time.perf_counter() + 1.5
-    i = 0
-    while time.perf_counter() < t_end:
-        step_resident(i, outs[i % len(outs)])
-        i += 1
-        if i % 64 == 0:
-            eng.sync()
-    eng.sync()
-    clk = clocks.stop()
-    clk["window"] = "timed region plus the same steps repeated for 1.5 s"
-
-    # ---- e2e: pinned host buffers through the C ABI, copies inside the timed region
-    for i in range(args.warmup):
-        step_e2e(i, outs[i])
-    eng.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i, outs[i])
-        eng.sync()                                # the caller reads this step's result before the next
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = total_bases / e2e_s
-    h2d = int(np.mean([packed[i % len(packed)].h2d_bytes() for i in range(args.steps)]))
-
-    # ---- roofline of the counting kernel (K1): algorithmic bytes / its own device time
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    k1_avg_ms = float(np.mean([m for m, _ in k1_ms]))
-    k1_bytes = float(np.mean([alg_bytes[j] for _, j in k1_ms]))
-    achieved = k1_bytes / (k1_avg_ms * 1e-3) / 1e9
-    k1_bases = float(np.mean([bases_per_step[j] for _, j in k1_ms]))
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32", "data": "synthetic",
-        "config": {"workload": label, "samples_per_gpu": len(ref_lens), "reads_per_step_per_gpu": packed[0].n_reads,
-                   "aligned_bases_per_step_per_gpu": bases_per_step[0], "ref_len": ref_lens[0],
-                   "l2": f"inputs {packed[0].h2d_bytes() / 1e6:.0f} MB per step > 126 MB L2; two resident batches alternate",
-                   "timing": "CUDA events on the engine's compute stream; max over ranks", "k1_variant": args.variant,
-                   "host_numa": numa},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": 1e3 * e2e_s / args.steps, "timing": "host wall clock, device-synchronised both sides"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, args.variant, args.samples_per_gpu, args.reads_per_sample)),
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                       "kernel on this workload (profiles/r2_g_k1_summary.md); null if not captured",
-                     "kernel": {0: "k1_count_tiled", 1: "k1_count_per_base", 2: "k1_count_split"}[args.variant],
-                     "kernel_ms": k1_avg_ms, "algorithmic_bytes_per_launch": k1_bytes,
-                     "bytes_per_aligned_base": k1_bytes / k1_bases, "kernel_aligned_bases_per_s": k1_bases / (k1_avg_ms * 1e-3),
-                     "peak_source": peak_src},
-        "gpu_launches": int(launches),
-        "clocks": clk,
-        "wall_s_timed_region": t_wall,
-    }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "cfg2x12":
-        line["cpu_baseline"] = cpu_baseline(sets[0], ref_lens[0])
+    rec, state = measure_workload(args, workload, rank, local, world, *comm, args.steps, args.warmup)
+    rec["config"]["host_numa"] = numa
+    line = {"metric": METRIC, "value": rec.pop("value"), "unit": rec.pop("unit"), "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic"}
+    rec.pop("steps"), rec.pop("warmup")
+    line.update(rec)
+    # what the platform gives the end-to-end path: plain pinned copies of the same bytes, all ranks at once
+    ctl = h2d_control(state["eng"], state["h2d"], barrier, max_over_ranks)
+    line["e2e"]["h2d_gbs_control"] = ctl
+    line["e2e"]["note"] = ("end to end is bound by the host-to-device copy: h2d_gbs_step is what a step achieves per GPU, "
+                           "h2d_gbs_control a plain pinned cudaMemcpyAsync of the same bytes on every rank at once")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and workload == "cfg2x12":
+        line["cpu_baseline"] = cpu_baseline(state["sets"][0], state["ref_lens"][0])
     elif rank == 0:
         line["cpu_baseline"] = None
-    if rank == 0 and world == 1 and args.workload == "cfg2x12":
-        for r in resident:
+    if rank == 0 and world == 1 and workload == "cfg2x12":
+        for r in state["resident"]:
             r.free()
-        resident = []
-        line["bam_e2e"] = bam_end_to_end(eng, not args.no_cpu_baseline)
+        state["resident"] = []
+        line["bam_e2e"] = bam_end_to_end(state["eng"], not args.no_cpu_baseline)
+    release(state)
+
+    if default_line and world == 1:
+        # the other single-GPU shapes of BASELINE.json (configs[2] and configs[4]) as sub-records of the same line
+        sub = {}
+        for w, cpu in (("cfg3", cpu_baseline_cfg3), ("cfg5", cpu_baseline_cfg5)):
+            r, st = measure_workload(args, w, rank, local, world, *comm, min(args.steps, 10), min(args.warmup, 3),
+                                     want_clocks=False)
+            r["cpu_baseline"] = None if args.no_cpu_baseline else cpu(st["sets"][0][0], st["ref_lens"][0])
+            release(st)
+            sub[w] = r
+        line["configs"] = sub
+    if default_line and world > 1:
+        # the split with a data-path collective (configs[4], strong scaling) beside the sample-sharded line
+        line["region_sharded"] = measure_region_sharded(args, rank, world, local, *comm, min(args.steps, 10),
+                                                        min(args.warmup, 3))
     if rank == 0:
         print(json.dumps(line), flush=True)
-    for r in resident:
-        r.free()
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -217,6 +217,9 @@ int bc_pack_reads(uint32_t n_reads, const uint8_t *seq, const uint8_t *qual, con
 /* CUDA-event timing on the compute stream (bench.py: kernel-only figures). */
 int bc_timer_start(bc_handle *h);
 int bc_timer_stop(bc_handle *h, float *ms);
+/* Diagnostic: GB/s of `reps` plain cudaMemcpyAsync copies of `bytes` from pinned host memory to the device on the
+ * handle's copy stream (CUDA events) -- what the platform gives the end-to-end path of bc_push_batch to work with. */
+int bc_h2d_probe(bc_handle *h, uint64_t bytes, int reps, double *gb_per_s);
 /* Device time of the last counting-kernel launch alone (events around K1), and launches so far. */
 int bc_last_count_kernel_ms(bc_handle *h, float *ms);
 /* Device times of the last n counting-kernel launches (ms[0] = most recent; ring of 256).

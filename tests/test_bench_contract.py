@@ -21,7 +21,7 @@ def test_reference_arm_prints_one_json_line():
     assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["value"] > 0 and line["ms_per_step"] > 0
     assert line["config"]["workload"].startswith("cfg2_summarise")
     cb = line["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == line["value"]
+    assert cb["kind"] in ("reference", "reference+port", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
 
