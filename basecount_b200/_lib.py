@@ -79,6 +79,9 @@ _SIGNATURES = {
     "bc_kernel_launches": (ctypes.c_uint64, [ctypes.c_void_p]),
     "bc_h2d_probe": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "bc_set_count_variant": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bc_rows_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "bc_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "bc_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "bc_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),

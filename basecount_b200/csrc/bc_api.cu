@@ -914,9 +914,9 @@ int bc_counts(bc_handle *h, uint32_t ref, int64_t *out)
 }
 
 static int run_rows(bc_handle *h, uint32_t ref, int K, double norm, double norm2, bool want_cov, bool want_pc,
-                    bool want_ent, bool want_sec, bool want_flags)
+                    bool want_ent, bool want_sec, bool want_flags, uint32_t lo = 0, uint32_t n = 0xFFFFFFFFu)
 {
-    const uint32_t L = h->ref_len[ref];
+    const uint32_t L = n == 0xFFFFFFFFu ? h->ref_len[ref] : n;      // a window [lo, lo + n) of the slot, or all of it
     int rc;
     if (want_cov && (rc = ensure(h, h->scratch_cov, (size_t)L * 8))) return rc;
     if (want_pc && (rc = ensure(h, h->scratch_pc, (size_t)L * 8 * K))) return rc;
@@ -924,7 +924,7 @@ static int run_rows(bc_handle *h, uint32_t ref, int K, double norm, double norm2
     if (want_sec && (rc = ensure(h, h->scratch_sec, (size_t)L * 8))) return rc;
     if (want_flags && (rc = ensure(h, h->scratch_flags, (size_t)L))) return rc;
     k2_stats_rows<<<(L + 255) / 256, 256, 0, h->compute>>>(
-        h->d_counts, h->d_counts64, h->stride, h->col_base[ref], L, K, norm, norm2,
+        h->d_counts, h->d_counts64, h->stride, (uint64_t)h->col_base[ref] + lo, L, K, norm, norm2,
         want_cov ? (long long *)h->scratch_cov.p : nullptr, want_pc ? (double *)h->scratch_pc.p : nullptr,
         want_ent ? (double *)h->scratch_ent.p : nullptr, want_sec ? (double *)h->scratch_sec.p : nullptr,
         want_flags ? (uint8_t *)h->scratch_flags.p : nullptr);
@@ -949,6 +949,36 @@ int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, 
     if (entropy) CU(h, cudaMemcpyAsync(entropy, h->scratch_ent.p, (size_t)L * 8, cudaMemcpyDeviceToHost, h->compute));
     if (secondary) CU(h, cudaMemcpyAsync(secondary, h->scratch_sec.p, (size_t)L * 8, cudaMemcpyDeviceToHost, h->compute));
     if (flags) CU(h, cudaMemcpyAsync(flags, h->scratch_flags.p, (size_t)L, cudaMemcpyDeviceToHost, h->compute));
+    CU(h, cudaStreamSynchronize(h->compute));
+    return BC_OK;
+}
+
+int bc_rows_window(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, uint32_t lo, uint32_t n,
+                   int64_t *counts, int64_t *coverage, double *pc, double *entropy, double *secondary, uint8_t *flags)
+{
+    if (!h) return BC_ERR_ARG;
+    if (ref >= h->n_refs) return fail(h, BC_ERR_ARG, "reference slot out of range");
+    if ((uint64_t)lo + n > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "bc_rows_window: window past the end of the slot");
+    if (n == 0) return BC_OK;
+    CU(h, cudaSetDevice(h->device));
+    const int K = show_n ? 6 : 5;
+    int rc;
+    if (counts) {
+        const uint64_t cells = (uint64_t)n * kPlanes;
+        if ((rc = ensure(h, h->scratch_i64, cells * sizeof(long long)))) return rc;
+        k_export_counts<<<(unsigned)((cells + 255) / 256), 256, 0, h->compute>>>(
+            h->d_counts, h->d_counts64, h->stride, (uint64_t)h->col_base[ref] + lo, n, (long long *)h->scratch_i64.p);
+        h->launches++;
+        CU(h, cudaMemcpyAsync(counts, h->scratch_i64.p, cells * sizeof(long long), cudaMemcpyDeviceToHost, h->compute));
+    }
+    if (coverage || pc || entropy || secondary || flags) {
+        if ((rc = run_rows(h, ref, K, norm, norm2, coverage, pc, entropy, secondary, flags, lo, n))) return rc;
+        if (coverage) CU(h, cudaMemcpyAsync(coverage, h->scratch_cov.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->compute));
+        if (pc) CU(h, cudaMemcpyAsync(pc, h->scratch_pc.p, (size_t)n * 8 * K, cudaMemcpyDeviceToHost, h->compute));
+        if (entropy) CU(h, cudaMemcpyAsync(entropy, h->scratch_ent.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->compute));
+        if (secondary) CU(h, cudaMemcpyAsync(secondary, h->scratch_sec.p, (size_t)n * 8, cudaMemcpyDeviceToHost, h->compute));
+        if (flags) CU(h, cudaMemcpyAsync(flags, h->scratch_flags.p, (size_t)n, cudaMemcpyDeviceToHost, h->compute));
+    }
     CU(h, cudaStreamSynchronize(h->compute));
     return BC_OK;
 }

@@ -79,13 +79,20 @@ class Engine:
         _lib.check(self._h, self._L.bc_reset(self._h))
 
     # -- the operator
-    def push(self, batch):
-        """Queue one batch (PackedBatch in host memory, or ResidentBatch in HBM). Asynchronous."""
+    def push(self, batch, keep: int = 0):
+        """Queue one batch (PackedBatch in host memory, or ResidentBatch in HBM). Asynchronous.
+
+        Host buffers must outlive the asynchronous copy.  By default every pushed batch is held until sync();
+        keep=2 holds only the last two: the library has two staging sets and bc_push_batch waits for the set it
+        is about to overwrite, so when push k returns, batch k - 2 has been copied and counted -- a stream of
+        chunks then needs host memory for two chunks, not for the file."""
         if isinstance(batch, ResidentBatch):
             _lib.check(self._h, self._L.bc_push_batch(self._h, ctypes.byref(batch.struct)))
             return
         self._keepalive.append(batch)           # host buffers must outlive the async copies
         _lib.check(self._h, self._L.bc_push_batch(self._h, ctypes.byref(batch.as_struct())))
+        if keep > 0 and len(self._keepalive) > keep:
+            del self._keepalive[:-keep]
 
     def sync(self):
         try:
@@ -114,6 +121,19 @@ class Engine:
         _lib.check(self._h, self._L.bc_stats(self._h, ref, int(show_n_bases), n1, n2, _lib.ptr(cov), _lib.ptr(pc),
                                              _lib.ptr(ent), _lib.ptr(sec), _lib.ptr(flags)))
         return {"coverage": cov, "pc": pc, "entropy": ent, "secondary": sec, "flags": flags}
+
+    def rows_window(self, ref: int, lo: int, n: int, show_n_bases: bool = False, bufs=None):
+        """Counts and per-position statistics of columns [lo, lo + n) of a slot: (counts n x 6, stats dict as stats()).
+        `bufs` (from a previous call with the same n and show_n_bases) is reused instead of allocating."""
+        k = 6 if show_n_bases else 5
+        n1, n2 = norm_factors(show_n_bases)
+        if bufs is None or bufs[0].shape[0] != n:
+            bufs = (np.empty((n, 6), np.int64), np.empty(n, np.int64), np.empty((k, n), np.float64), np.empty(n, np.float64),
+                    np.empty(n, np.float64), np.empty(n, np.uint8))
+        cnt, cov, pc, ent, sec, flags = bufs
+        _lib.check(self._h, self._L.bc_rows_window(self._h, ref, int(show_n_bases), n1, n2, int(lo), int(n), _lib.ptr(cnt),
+                                                   _lib.ptr(cov), _lib.ptr(pc), _lib.ptr(ent), _lib.ptr(sec), _lib.ptr(flags)))
+        return cnt, {"coverage": cov, "pc": pc, "entropy": ent, "secondary": sec, "flags": flags}, bufs
 
     def summary(self, show_n_bases: bool = False):
         r = len(self.ref_lens)

@@ -88,9 +88,11 @@ class _RecordSource:
     def __init__(self, bam):
         self.native = None
         self.rec = None
-        if not isinstance(bam, Records) and _decoder_choice() == "native":
+        from . import bamio as _bamio
+        if isinstance(bam, _bamio.NativeBam) or (not isinstance(bam, Records) and _decoder_choice() == "native"):
             from . import bamio
-            self.native = bamio.NativeBam(bam)
+            # (an already opened NativeBam lets a caller open the next file while this one is being counted)
+            self.native = bam if isinstance(bam, _bamio.NativeBam) else bamio.NativeBam(bam)
             self.ref_names, self.ref_lengths, self.n = self.native.ref_names, self.native.ref_lengths, self.native.n
             self.ref_id, _, self.mapq, self.flag = self.native.core()
         else:
@@ -209,20 +211,31 @@ def _count_into(eng, rec, ids, lengths, num_reads, min_base_quality, min_mapping
         for k in range(chunk_size, total, chunk_size):
             cuts.append(int(np.searchsorted(csum, k, side="left")) + 1)
         cuts.append(rec.n)
+        # Pushes are asynchronous (H2D on the copy stream, K1 on the compute stream, two staging sets in the
+        # library): the next chunk is decoded and packed while the device counts this one; one synchronisation at
+        # the end, where an alignment past the reference end surfaces as IndexError (count.cpp .at()).
         for a, b in zip(cuts[:-1], cuts[1:]):
             if b <= a:
                 continue
-            if rec.native is not None and len(ids) == 1:
-                # one native pass: selection (main.py:165-166), soft-clip trimming and 2-bit packing
-                packed = rec.native.pack(ids[0], min_mapping_quality, min_base_quality, a, b)
-                num_reads[0] += packed.n_reads
+            if rec.native is not None:
+                # one native pass per reference: selection (main.py:165-166), soft-clip trimming, CIGAR normal form
+                # and 2-bit packing straight from the records; a batch fills one slot of the handle
+                for j, rid in enumerate(ids):
+                    packed = rec.native.pack(rid, min_mapping_quality, min_base_quality, a, b)
+                    if packed.n_reads == 0:
+                        continue
+                    num_reads[j] += packed.n_reads
+                    if len(ids) > 1:
+                        off = np.zeros(len(ids) + 1, dtype=np.uint32)
+                        off[j + 1:] = packed.n_reads
+                        packed.ref_read_off, packed.n_refs = off, len(ids)
+                    eng.push(packed, keep=2)
             else:
                 batches = [rec.select(a, b, rid, min_mapping_quality, want_qual=min_base_quality > 0) for rid in ids]
                 for j, bt in enumerate(batches):
                     num_reads[j] += bt.n
-                packed = pack_batches(batches, min_base_quality)
-            eng.push(packed)
-            eng.sync()
+                eng.push(pack_batches(batches, min_base_quality), keep=2)
+        eng.sync()
 
 
 def build_rows(ref, counts, st, show_n_bases=False, long_format=False):
@@ -251,6 +264,13 @@ def build_rows(ref, counts, st, show_n_bases=False, long_format=False):
         else:
             rows.append([ref, i + 1, cov[i], *cnt[i], *p, e, s])
     return rows
+
+
+def _offset_rows(rows, first):
+    """build_rows numbers positions from 1: shift a window's rows to their place in the reference."""
+    for r in rows:
+        r[1] += first
+        yield r
 
 
 def format_rows_text(ref, counts, st, show_n_bases=False, long_format=False, decimal_places=3, first_pos=1,
@@ -356,6 +376,43 @@ class BaseCount:
                 return None
             out.append(t)
         return out
+
+    def write_tsv(self, out, decimal_places=3, window=1 << 19, header=True, threads=0):
+        """Stream the per-position TSV (what `run` prints, main.py:454-466) to the text file object `out`, one window
+        of `window` positions at a time: the device computes the next window's rows (K2) and copies them back
+        while the native emitter formats the current one, so a 64 Mb reference never needs more host memory than
+        two windows.  Returns the number of data rows written.  Falls back to the Python formatting loop, window by
+        window, outside the emitter's exactness envelope (decimal_places not in 0..4)."""
+        from concurrent.futures import ThreadPoolExecutor
+        p = self._pile
+        k = 6 if self._show_n else 5
+        if header:
+            out.write("\t".join(self.columns) + "\n")
+        rows = 0
+        with ThreadPoolExecutor(max_workers=1) as pool:      # the one thread that talks to the engine while we format
+            for i, ref in enumerate(self.references):
+                L = p.lengths[i]
+                cuts = list(range(0, L, max(int(window), 1))) + [L]
+                spans = list(zip(cuts[:-1], cuts[1:]))
+                bufs = [None, None]
+                fut = pool.submit(p.engine.rows_window, i, spans[0][0], spans[0][1] - spans[0][0], self._show_n, None) if spans else None
+                for w, (a, b) in enumerate(spans):
+                    cnt, st, bufs[w % 2] = fut.result()
+                    if w + 1 < len(spans):
+                        na, nb = spans[w + 1]
+                        fut = pool.submit(p.engine.rows_window, i, na, nb - na, self._show_n, bufs[(w + 1) % 2])
+                    text = format_rows_text(ref, cnt, st, self._show_n, self._long, decimal_places, first_pos=a + 1,
+                                            threads=threads)
+                    if text is None:
+                        lines = []
+                        for row in _offset_rows(build_rows(ref, cnt, st, self._show_n, self._long), a):
+                            lines.append("\t".join([x if isinstance(x, str) else str(round(x, decimal_places)) for x in row]))
+                        text = "\n".join(lines)
+                    if text:
+                        out.write(text)
+                        out.write("\n")
+                    rows += (b - a) * (k if self._long else 1)
+        return rows
 
     def _index(self, reference):
         if reference not in self.reference_lengths:
@@ -485,14 +542,9 @@ def run(argv=None):
                    long_format=args.long_format)
 
     if (not args.summarise) and (bed is None):
-        out = ["\t".join(bc.columns)]
-        texts = bc.rows_text(decimal_places)            # native emitter, byte-identical to the loop below
-        if texts is not None:
-            out += [t for t in texts if t]
-        else:
-            for row in bc.rows():
-                out.append("\t".join([x if isinstance(x, str) else str(round(x, decimal_places)) for x in row]))
-        print("\n".join(out))
+        import sys
+        # rows stream out window by window (native emitter, byte-identical to str(round(x, d)) per cell, main.py:461)
+        bc.write_tsv(sys.stdout, decimal_places)
         return
 
     for ref in bc.references:

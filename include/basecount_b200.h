@@ -139,6 +139,12 @@ int bc_counts(bc_handle *h, uint32_t ref, int64_t *out);
 int bc_stats(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2,
              int64_t *coverage, double *pc, double *entropy, double *secondary, uint8_t *flags);
 
+/* bc_counts and bc_stats for the window [lo, lo + n) of a slot only (any output may be NULL; counts is n x 6 int64,
+ * pc is pc[k * n + i]): what lets `basecount BAM_FILE` print a 64 Mb reference window by window (main.py:456-466)
+ * without the host ever holding more than one window of rows. */
+int bc_rows_window(bc_handle *h, uint32_t ref, int show_n, double norm, double norm2, uint32_t lo, uint32_t n,
+                   int64_t *counts, int64_t *coverage, double *pc, double *entropy, double *secondary, uint8_t *flags);
+
 /* --summarise reductions for ALL slots in one pass (main.py:479-485): per slot the
  * number of positions with coverage != 0, the sum of coverage and the sum of entropy
  * (entropy = 1 at zero coverage). */
