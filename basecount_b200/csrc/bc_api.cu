@@ -98,6 +98,12 @@ struct bc_handle {
     // the next synchronisation and the values are handed to the callers' arrays there
     struct PendingCopy { size_t off; size_t bytes; void *dst; };   // arena bytes owed to a caller's array
     std::vector<PendingCopy> pending;
+    // summarise partials owed to a caller as per-slot sums: slot r's partials are `count[r]` SummaryPartial records at
+    // arena offset off + first[r] * sizeof(SummaryPartial), added on the host in index order
+    struct PendingReduce { size_t off; std::vector<uint32_t> first, count; int64_t *nz, *cs; double *es; };
+    std::vector<PendingReduce> pending_reduce;
+    std::vector<uint32_t> part_off_host;  // first partial of every slot (host copy of d_part_off)
+    size_t total_partials = 0;
     char *d_results = nullptr, *h_results = nullptr;         // device arena and its pinned mirror
     size_t results_cap = 0, results_used = 0;
     double *d_log2_tab = nullptr;         // log2 of small integers for the summarise reductions (k2_stats.cuh)
@@ -158,7 +164,7 @@ static int ensure(bc_handle *h, DevBuf &b, size_t bytes)
 // Queue the copy of the result arena to its pinned mirror (no-op without pending summaries).
 static int fetch_summaries(bc_handle *h)
 {
-    if (h->pending.empty()) return BC_OK;
+    if (h->pending.empty() && h->pending_reduce.empty()) return BC_OK;
     CU(h, cudaMemcpyAsync(h->h_results, h->d_results, h->results_used, cudaMemcpyDeviceToHost, h->compute));
     return BC_OK;
 }
@@ -168,6 +174,23 @@ static void deliver_summaries(bc_handle *h)
 {
     for (auto &p : h->pending) std::memcpy(p.dst, h->h_results + p.off, p.bytes);
     h->pending.clear();
+    for (auto &q : h->pending_reduce) {
+        const SummaryPartial *all = reinterpret_cast<const SummaryPartial *>(h->h_results + q.off);
+        for (size_t r = 0; r < q.first.size(); r++) {
+            long long nz = 0, cs = 0;
+            double es = 0.0;
+            for (uint32_t i = 0; i < q.count[r]; i++) {
+                const SummaryPartial &sp = all[q.first[r] + i];
+                nz += sp.nonzero;
+                cs += sp.cov_sum;
+                es += sp.ent_sum;
+            }
+            q.nz[r] = nz;
+            q.cs[r] = cs;
+            q.es[r] = es;
+        }
+    }
+    h->pending_reduce.clear();
     h->results_used = 0;
 }
 
@@ -1044,39 +1067,65 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
             h->part_off_cap = R;
         }
         CU(h, cudaMemcpy(h->d_part_off, off.data(), (size_t)R * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        h->part_off_host = off;
+        h->total_partials = need;
         h->part_off_refs = R;
         h->summary_max_blocks = maxb;
     }
-    size_t off = 0;
-    {
-        int rcr = reserve_results(h, (size_t)R * 24, &off);
-        if (rcr) return rcr;
-    }
-    long long *d_nz = (long long *)(h->d_results + off);   // device arena, fetched at the next synchronisation
-    long long *d_cs = d_nz + R;
-    double *d_es = (double *)(d_cs + R);
     const int K = show_n ? 6 : 5;
     (void)norm2;                                          // --summarise does not need the secondary entropy
-    if (h->d_counts64)
-        k2_summary<true><<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(
-            h->d_counts, h->d_counts64, h->stride, h->d_col_base, h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off,
-            h->d_partials, h->d_part_off + R, d_nz, d_cs, d_es);
-    else
-        k2_summary<false><<<dim3(h->summary_max_blocks, R), 256, 0, h->compute>>>(
-            h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K, norm, min_cov, h->d_log2_tab, h->d_part_off,
-            h->d_partials, h->d_part_off + R, d_nz, d_cs, d_es);
-    h->launches += 1;
-    if (allreduce && h->comm_world > 1) {
-        // every rank holds the sums over the columns it owns: the reference's numbers are the sums over ranks
-        // (main.py:479-485).  nonzero and cov_sum are adjacent int64 arrays; entropy sums are float64.
-        bcnccl::Api &nc = bcnccl::api();
-        ncclResult_t r1 = nc.AllReduce(d_nz, d_nz, (size_t)R * 2, ncclInt64, ncclSum, h->comm, h->compute);
-        ncclResult_t r2 = r1 == ncclSuccess ? nc.AllReduce(d_es, d_es, (size_t)R, ncclFloat64, ncclSum, h->comm, h->compute) : r1;
-        if (r2 != ncclSuccess) return fail(h, BC_ERR_CUDA, nc.GetErrorString(r2));
+    const dim3 grid(h->summary_max_blocks, R);
+    size_t off = 0;
+    if (!allreduce) {
+        // per-CTA partials straight into the result arena; the host adds them up when it fetches the arena
+        int rcr = reserve_results(h, h->total_partials * sizeof(SummaryPartial), &off);
+        if (rcr) return rcr;
+        SummaryPartial *d_part = reinterpret_cast<SummaryPartial *>(h->d_results + off);
+        if (h->d_counts64)
+            k2_summary<true, false><<<grid, 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride, h->d_col_base, h->d_ref_len,
+                                                                  K, norm, min_cov, h->d_log2_tab, h->d_part_off, d_part, nullptr,
+                                                                  nullptr, nullptr, nullptr);
+        else
+            k2_summary<false, false><<<grid, 256, 0, h->compute>>>(h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K,
+                                                                   norm, min_cov, h->d_log2_tab, h->d_part_off, d_part, nullptr,
+                                                                   nullptr, nullptr, nullptr);
+        h->launches += 1;
+        bc_handle::PendingReduce q;
+        q.off = off;
+        q.first = h->part_off_host;
+        q.count.resize(R);
+        for (uint32_t r = 0; r < R; r++) q.count[r] = summary_blocks(h->ref_len[r]);
+        q.nz = nonzero;
+        q.cs = cov_sum;
+        q.es = entropy_sum;
+        h->pending_reduce.push_back(std::move(q));
+    } else {
+        int rcr = reserve_results(h, (size_t)R * 24, &off);
+        if (rcr) return rcr;
+        long long *d_nz = (long long *)(h->d_results + off);   // device arena, fetched at the next synchronisation
+        long long *d_cs = d_nz + R;
+        double *d_es = (double *)(d_cs + R);
+        if (h->d_counts64)
+            k2_summary<true, true><<<grid, 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride, h->d_col_base, h->d_ref_len, K,
+                                                                 norm, min_cov, h->d_log2_tab, h->d_part_off, h->d_partials,
+                                                                 h->d_part_off + R, d_nz, d_cs, d_es);
+        else
+            k2_summary<false, true><<<grid, 256, 0, h->compute>>>(h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K, norm,
+                                                                  min_cov, h->d_log2_tab, h->d_part_off, h->d_partials,
+                                                                  h->d_part_off + R, d_nz, d_cs, d_es);
+        h->launches += 1;
+        if (h->comm_world > 1) {
+            // every rank holds the sums over the columns it owns: the reference's numbers are the sums over ranks
+            // (main.py:479-485).  nonzero and cov_sum are adjacent int64 arrays; entropy sums are float64.
+            bcnccl::Api &nc = bcnccl::api();
+            ncclResult_t r1 = nc.AllReduce(d_nz, d_nz, (size_t)R * 2, ncclInt64, ncclSum, h->comm, h->compute);
+            ncclResult_t r2 = r1 == ncclSuccess ? nc.AllReduce(d_es, d_es, (size_t)R, ncclFloat64, ncclSum, h->comm, h->compute) : r1;
+            if (r2 != ncclSuccess) return fail(h, BC_ERR_CUDA, nc.GetErrorString(r2));
+        }
+        h->pending.push_back({off, (size_t)R * 8, nonzero});
+        h->pending.push_back({off + (size_t)R * 8, (size_t)R * 8, cov_sum});
+        h->pending.push_back({off + (size_t)R * 16, (size_t)R * 8, entropy_sum});
     }
-    h->pending.push_back({off, (size_t)R * 8, nonzero});
-    h->pending.push_back({off + (size_t)R * 8, (size_t)R * 8, cov_sum});
-    h->pending.push_back({off + (size_t)R * 16, (size_t)R * 8, entropy_sum});
     CU(h, cudaGetLastError());
     if (sync) {
         int rcf = fetch_summaries(h);

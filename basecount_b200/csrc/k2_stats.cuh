@@ -120,6 +120,46 @@ __device__ __forceinline__ double neumaier_entropy_tab(const long long *c, int n
     return hi;
 }
 
+// The same for uint32 counts (no int64 fold: a position's coverage is at most the reads since the last fold, < 2^32)
+// and without the compensated sum: a SUM of entropies tolerates the ~1e-16 that plain addition of <= 6 positive
+// terms and one reciprocal (c * (1 / cov) instead of c / cov for the minor classes) cost, and the kernel was bound
+// by instruction issue -- 260 instructions per position at whole-genome depth, mostly 64-bit integer compares,
+// branches around empty classes and the compensation.  Terms of empty classes and of a class that holds the whole
+// coverage are 0.0 in both tables (k_fill_log2), so nothing is skipped and nothing branches.
+// cov in (0, kLog2Tab).
+__device__ __forceinline__ double summary_entropy_u32(const uint32_t (&c)[6], int K, uint32_t cov, const double *__restrict__ tab)
+{
+    if (cov < (uint32_t)kTermTab) {                        // shallow: every term straight from the table
+        const double *__restrict__ row = tab + kLog2Tab + cov * (uint32_t)kTermTab;
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+            if (i < K) s += row[c[i]];
+        return s;
+    }
+    uint32_t ctop = c[0];
+#pragma unroll
+    for (int i = 1; i < 6; i++)
+        if (i < K) ctop = max(ctop, c[i]);
+    const double tot = (double)cov, inv = 1.0 / tot, ltot = tab[cov];
+    double s = 0.0;
+    bool top_pending = true;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (i >= K) continue;
+        if (top_pending && c[i] == ctop) {                 // the first maximum keeps the exact expression of main.py:11
+            top_pending = false;
+            if (ctop != cov) {
+                const double p = (double)ctop / tot;
+                s += -(p * log2(p));
+            }
+        } else if (c[i] != 0u) {                           // 2c <= cov: |log2 p| >= 1, no cancellation in the difference
+            s += -(((double)c[i] * inv) * (tab[c[i]] - ltot));
+        }
+    }
+    return s;
+}
+
 // Coverage and entropy only (what the --summarise reductions need, main.py:479-485).
 __device__ __forceinline__ void position_cov_entropy(const long long *c, int K, double norm, long long &cov_out,
                                                      double &ent_out, const double *__restrict__ tab)
@@ -247,7 +287,11 @@ __device__ __forceinline__ void summary_cta_sum(long long &nz, long long &cs, do
 // index order, then the fixed-order CTA sum -- the result does not depend on which CTA was last.
 // min_cov < 0: nonzero = positions with coverage != 0, ent_sum over all positions; min_cov >= 0: nonzero =
 // positions with coverage >= min_cov, ent_sum over those (BaseCount.mean_entropy, main.py:342-359).
-template <bool HAS64>
+// FINAL = false: the kernel stops at the per-CTA partials (written to `partials`, which then lies in the result arena
+// the host fetches at the next synchronisation) and the HOST adds a slot's partials in index order -- a launch then
+// has no __threadfence / atomic round trip per CTA and no last-CTA phase, which were a fifth of its duration on the
+// viral-sample shape.  FINAL = true keeps the sums on the device (the all-reduce over ranks needs them there).
+template <bool HAS64, bool FINAL>
 __global__ void __launch_bounds__(256)
 k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restrict__ c64, uint64_t stride,
            const uint32_t *__restrict__ col_base, const uint32_t *__restrict__ ref_len, int K, double norm,
@@ -262,20 +306,58 @@ k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restric
     const uint64_t base = col_base[r];
     long long nz = 0, cs = 0;
     double es = 0.0;
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < L; pos += nb * blockDim.x) {
-        long long c[6];
+    const uint32_t *__restrict__ const col0 = c32 + base;
+    // Four positions per trip with all their count loads issued first: a thread's positions are independent, and one
+    // after the other each paid the full load -> table look-up latency chain (the kernel is latency-bound on the
+    // viral-sample shape: 4 positions per thread, 5 warps per scheduler).  Same positions in the same order.
+    constexpr int kPP = 4;
+    const uint32_t pstride = nb * blockDim.x;
+    for (uint32_t pos0 = blockIdx.x * blockDim.x + threadIdx.x; pos0 < L; pos0 += kPP * pstride) {
+      uint32_t ub[kPP][6];
+      if (!HAS64) {
 #pragma unroll
-        for (int p = 0; p < kPlanes; p++) {
-            c[p] = 0;
-            if (p < K) {
-                const uint64_t a = (uint64_t)p * stride + base + pos;
-                c[p] = (long long)c32[a];
-                if (HAS64) c[p] += (long long)c64[a];
-            }
-        }
+          for (int j = 0; j < kPP; j++) {
+              const uint32_t pj = pos0 + (uint32_t)j * pstride;
+#pragma unroll
+              for (int p = 0; p < kPlanes; p++) ub[j][p] = (p < K && pj < L && pj >= pos0) ? col0[(uint64_t)p * stride + pj] : 0u;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < kPP; j++) {
+        const uint32_t pos = pos0 + (uint32_t)j * pstride;
+        if (pos >= L || pos < pos0) continue;
         long long cov;
         double ent;
-        position_cov_entropy(c, K, norm, cov, ent, log2_tab);
+        if (!HAS64) {
+            uint32_t u[6], ucov = 0u;
+#pragma unroll
+            for (int p = 0; p < kPlanes; p++) {
+                u[p] = ub[j][p];
+                ucov += u[p];
+            }
+            cov = (long long)ucov;
+            if (ucov == 0u) {
+                ent = 1.0;                                 // main.py:34-36
+            } else if (ucov < (uint32_t)kLog2Tab) {
+                ent = norm * summary_entropy_u32(u, K, ucov, log2_tab);
+            } else {                                       // beyond the tables: the exact expression for every class
+                long long c[6];
+#pragma unroll
+                for (int p = 0; p < kPlanes; p++) c[p] = (long long)u[p];
+                ent = norm * neumaier_entropy(c, K, cov, -1);
+            }
+        } else {
+            long long c[6];
+#pragma unroll
+            for (int p = 0; p < kPlanes; p++) {
+                c[p] = 0;
+                if (p < K) {
+                    const uint64_t a = (uint64_t)p * stride + base + pos;
+                    c[p] = (long long)c32[a] + (long long)c64[a];
+                }
+            }
+            position_cov_entropy(c, K, norm, cov, ent, log2_tab);
+        }
         if (min_cov < 0) {                                 // --summarise (main.py:479-485)
             nz += (cov != 0);
             es += ent;
@@ -284,6 +366,7 @@ k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restric
             es += ent;
         }
         cs += cov;
+      }
     }
     __shared__ long long s_nz[8], s_cs[8];
     __shared__ double s_es[8];
@@ -294,9 +377,12 @@ k2_summary(const uint32_t *__restrict__ c32, const unsigned long long *__restric
         p[blockIdx.x].nonzero = nz;
         p[blockIdx.x].cov_sum = cs;
         p[blockIdx.x].ent_sum = es;
-        __threadfence();                                   // the partial is visible before the arrival is
-        s_last = atomicAdd(arrive + r, 1u) == nb - 1u;
+        if (FINAL) {
+            __threadfence();                               // the partial is visible before the arrival is
+            s_last = atomicAdd(arrive + r, 1u) == nb - 1u;
+        }
     }
+    if (!FINAL) return;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
