@@ -41,8 +41,9 @@ UNIT = "aligned bases/s"
 SAMPLES_PER_GPU = 12
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 # DRAM bytes per K1 launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures of
-# the default shapes (profiles/r2_*_k1_summary.md)
-NCU_TRAFFIC_BYTES = {"cfg2x12": None, "cfg3": None, "cfg5": None}
+# the default shapes (profiles/r4_a_k1_summary.md)
+# dram__bytes_read.sum + dram__bytes_write.sum of k1_count_fast, one launch, ncu --set full (profiles/r4_a_k1_summary.md)
+NCU_TRAFFIC_BYTES = {"cfg2x12": 197_192_960, "cfg3": 118_753_536, "cfg5": 2_832_785_000}
 
 
 def parse():
@@ -575,7 +576,7 @@ def measure_workload(args, workload, rank, local, world, barrier, max_over_ranks
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                                       "kernel on this workload (profiles/r2_*_k1_summary.md); null if not captured",
+                                       "kernel on this workload (profiles/r4_a_k1_summary.md); null if not captured",
                      "kernel": {0: "k1_count_fast (+ k1_count_tiled over what it defers: nothing on this workload)",
                                 1: "k1_count_per_base", 2: "k1_count_tiled"}[args.variant],
                      "kernel_ms": k1_avg_ms, "algorithmic_bytes_per_launch": k1_bytes,
