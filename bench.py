@@ -36,12 +36,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line, the JSON record: everything else a process writes to file descriptor 1 while the
+# bench runs (NCCL prints "NCCL version ..." there at the first communicator, make, child processes) goes to stderr.
+_JSON_FD = None
+
+
+def claim_stdout():
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "aligned_bases_per_sec"
 UNIT = "aligned bases/s"
 SAMPLES_PER_GPU = 12
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
-# DRAM bytes per K1 launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full captures of
-# the default shapes (profiles/r4_a_k1_summary.md)
+# DRAM bytes per K1 launch from the committed ncu --set full captures of the default shapes:
 # dram__bytes_read.sum + dram__bytes_write.sum of k1_count_fast, one launch, ncu --set full (profiles/r4_a_k1_summary.md)
 NCU_TRAFFIC_BYTES = {"cfg2x12": 197_192_960, "cfg3": 118_753_536, "cfg5": 2_832_785_000}
 
@@ -290,7 +307,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": per_step, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- BAM file -> summary
@@ -778,6 +795,7 @@ def measure_region_sharded(args, rank, world, local, barrier, max_over_ranks, su
 # ----------------------------------------------------------------------------- our arm
 def main():
     args = parse()
+    claim_stdout()
     if args.gen_samples:
         for seed in args.gen_samples.split(","):
             _generate_sample((int(seed), args.reads_per_sample))
@@ -830,7 +848,7 @@ def main():
         line = {"metric": METRIC, "higher_is_better": True, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "cpu_baseline": None, **rec}
         if rank == 0:
-            print(json.dumps(line), flush=True)
+            emit(line)
         dist.destroy_process_group()
         return
 
@@ -875,7 +893,7 @@ def main():
     if default_line:
         line["bam_e2e_batch"] = bam_batch_end_to_end(local, SAMPLES_PER_GPU, *comm)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
