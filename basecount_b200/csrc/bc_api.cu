@@ -66,8 +66,19 @@ struct Resident {                // a batch kept in HBM by bc_batch_upload
 struct bc_handle {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t copy = nullptr, compute = nullptr, side = nullptr;
+    cudaStream_t copy = nullptr, compute = nullptr, side = nullptr, stats = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr, counted = nullptr, checked = nullptr;
+    // The asynchronous --summarise reduction (bc_summary_async) runs on its own low-priority stream behind everything
+    // queued on the compute stream so far, so that in a pipeline of steps the summary of step i runs beside the
+    // counting kernel of step i + 1 (which, after bc_reset, writes the OTHER set of accumulators) instead of between
+    // two counting kernels.  stats_busy: work is queued there that the compute stream has not waited for; stats_set:
+    // the accumulator set it reads.  Anything that writes that set, a slot length or the result arena joins first.
+    cudaEvent_t stats_ready = nullptr, stats_done = nullptr;
+    bool stats_busy = false;
+    bool stats_overlap = true;            // BASECOUNT_B200_SUMMARY_STREAM=0: summaries stay on the compute stream (A/B runs)
+    int stats_set = 0;
+    cudaEvent_t set_free_stats[2] = {nullptr, nullptr};
+    bool set_free_stats_valid[2] = {false, false};
     std::string err;
 
     uint32_t n_refs = 0;
@@ -140,6 +151,21 @@ struct bc_handle {
         }                                                                                        \
     } while (0)
 
+// The compute stream waits for what is queued on the summary stream (see bc_handle::stats).
+static int join_stats(bc_handle *h)
+{
+    if (h->stats_busy) {
+        CU(h, cudaStreamWaitEvent(h->compute, h->stats_done, 0));
+        h->stats_busy = false;
+    }
+    return BC_OK;
+}
+#define JOIN_STATS(h)                 \
+    do {                              \
+        int rcj__ = join_stats(h);    \
+        if (rcj__) return rcj__;      \
+    } while (0)
+
 static int fail(bc_handle *h, int code, const char *msg)
 {
     h->err = msg;
@@ -165,6 +191,7 @@ static int ensure(bc_handle *h, DevBuf &b, size_t bytes)
 static int fetch_summaries(bc_handle *h)
 {
     if (h->pending.empty() && h->pending_reduce.empty()) return BC_OK;
+    JOIN_STATS(h);
     CU(h, cudaMemcpyAsync(h->h_results, h->d_results, h->results_used, cudaMemcpyDeviceToHost, h->compute));
     return BC_OK;
 }
@@ -303,7 +330,12 @@ int bc_create(int device, bc_handle **out)
             return bail(e, "stream");
         if ((e = cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, least)) != cudaSuccess)
             return bail(e, "stream");
+        if ((e = cudaStreamCreateWithPriority(&h->stats, cudaStreamNonBlocking, least)) != cudaSuccess)
+            return bail(e, "stream");
     }
+    if (const char *o = std::getenv("BASECOUNT_B200_SUMMARY_STREAM")) h->stats_overlap = std::atoi(o) != 0;
+    if ((e = cudaEventCreateWithFlags(&h->stats_ready, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+    if ((e = cudaEventCreateWithFlags(&h->stats_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->counted, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
@@ -311,6 +343,7 @@ int bc_create(int device, bc_handle **out)
     for (int i = 0; i < 2; i++) {
         if ((e = cudaEventCreateWithFlags(&h->set_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
         if ((e = cudaEventCreateWithFlags(&h->set_zeroed[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
+        if ((e = cudaEventCreateWithFlags(&h->set_free_stats[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     }
     for (cudaEvent_t *ev : {&h->t0, &h->t1})
         if ((e = cudaEventCreate(ev)) != cudaSuccess) return bail(e, "event");
@@ -357,7 +390,10 @@ void bc_destroy(bc_handle *h)
         if (h->d_counts_set[i]) cudaFree(h->d_counts_set[i]);
         if (h->set_free[i]) cudaEventDestroy(h->set_free[i]);
         if (h->set_zeroed[i]) cudaEventDestroy(h->set_zeroed[i]);
+        if (h->set_free_stats[i]) cudaEventDestroy(h->set_free_stats[i]);
     }
+    if (h->stats_ready) cudaEventDestroy(h->stats_ready);
+    if (h->stats_done) cudaEventDestroy(h->stats_done);
     if (h->d_counts64) cudaFree(h->d_counts64);
     if (h->d_col_base) cudaFree(h->d_col_base);
     if (h->d_ref_len) cudaFree(h->d_ref_len);
@@ -380,6 +416,7 @@ void bc_destroy(bc_handle *h)
     if (h->copy) cudaStreamDestroy(h->copy);
     if (h->compute) cudaStreamDestroy(h->compute);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->stats) cudaStreamDestroy(h->stats);
     delete h;
 }
 
@@ -402,6 +439,8 @@ int bc_begin(bc_handle *h, uint32_t n_refs, const uint32_t *ref_lens)
     if (n_refs == 0 || !ref_lens) return fail(h, BC_ERR_ARG, "bc_begin: need at least one reference");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaDeviceSynchronize());
+    h->stats_busy = false;
+    h->set_free_stats_valid[0] = h->set_free_stats_valid[1] = false;
     uint64_t total = 0;
     std::vector<uint32_t> cb(n_refs), rl(n_refs);
     for (uint32_t r = 0; r < n_refs; r++) {
@@ -459,14 +498,23 @@ int bc_reset(bc_handle *h)
     // the previous switch is done.  It is zeroed on the side stream, behind the overflow check of the last batch
     // (i.e. not beside its K1), and the compute stream only waits for that memset.
     CU(h, cudaEventRecord(h->set_free[h->cur_set], h->compute));
+    // ... and so may the summaries queued on their own stream (all of them read the set in use when they were queued)
+    h->set_free_stats_valid[h->cur_set] = h->stats_busy;
+    if (h->stats_busy) CU(h, cudaEventRecord(h->set_free_stats[h->cur_set], h->stats));
     h->cur_set ^= 1;
     h->d_counts = h->d_counts_set[h->cur_set];
     CU(h, cudaStreamWaitEvent(h->side, h->set_free[h->cur_set], 0));
+    if (h->set_free_stats_valid[h->cur_set]) {
+        CU(h, cudaStreamWaitEvent(h->side, h->set_free_stats[h->cur_set], 0));
+        h->set_free_stats_valid[h->cur_set] = false;
+    }
     CU(h, cudaMemsetAsync(h->d_counts, 0, (size_t)h->stride * kPlanes * sizeof(uint32_t), h->side));
     CU(h, cudaEventRecord(h->set_zeroed[h->cur_set], h->side));
     CU(h, cudaStreamWaitEvent(h->compute, h->set_zeroed[h->cur_set], 0));
-    if (h->d_counts64)
+    if (h->d_counts64) {                                 // (one copy for both sets: a summary may still read it)
+        JOIN_STATS(h);
         CU(h, cudaMemsetAsync(h->d_counts64, 0, (size_t)h->stride * kPlanes * sizeof(unsigned long long), h->compute));
+    }
     h->reads_since_fold = 0;
     return BC_OK;
 }
@@ -611,9 +659,12 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
                         uint32_t mean_words, Chunk *d_deferred, uint32_t *d_ctrl, Resident *res, cudaEvent_t copied)
 {
     if (v.n_reads == 0) return BC_OK;
+    // a summary that still reads THIS set of accumulators (no bc_reset since it was queued) comes first
+    if (h->stats_busy && h->stats_set == h->cur_set) JOIN_STATS(h);
     // uint32 counters cannot wrap while fewer than 2^32 reads went in since the last fold
     if (h->reads_since_fold + v.n_reads > 0xFFFFFFFFull) {
         const uint64_t n = h->stride * kPlanes;
+        JOIN_STATS(h);
         if (!h->d_counts64) {
             CU(h, cudaMalloc(&h->d_counts64, n * sizeof(unsigned long long)));
             CU(h, cudaMemsetAsync(h->d_counts64, 0, n * sizeof(unsigned long long), h->compute));
@@ -704,7 +755,8 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
     h->launches++;
     CU(h, cudaEventRecord(h->counted, h->compute));
     CU(h, cudaStreamWaitEvent(h->side, h->counted, 0));
-    k1_check_overflow<<<std::min<unsigned>((v.n_reads + 255) / 256, (unsigned)h->sm_count * 2), 256, 0, h->side>>>(v, cv);
+    // (128-thread CTAs: 3,328 registers, small enough to run on an SM beside the three CTAs of the next counting kernel)
+    k1_check_overflow<<<std::min<unsigned>((v.n_reads + 127) / 128, (unsigned)h->sm_count * 4), 128, 0, h->side>>>(v, cv);
     CU(h, cudaEventRecord(h->checked, h->side));
     h->launches++;
     if (v.n_exc && !(h->dbg_skip & 2)) CU(h, cudaStreamWaitEvent(h->compute, h->join, 0));
@@ -1055,6 +1107,7 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
             maxb = std::max(maxb, nb);
         }
         CU(h, cudaStreamSynchronize(h->compute));         // earlier summaries still read the old offsets
+        CU(h, cudaStreamSynchronize(h->stats));
         if (need > h->partials_cap || R != h->part_off_cap || !h->d_part_off) {
             if (h->d_partials) CU(h, cudaFree(h->d_partials));
             if (h->d_part_off) CU(h, cudaFree(h->d_part_off));
@@ -1081,14 +1134,26 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
         int rcr = reserve_results(h, h->total_partials * sizeof(SummaryPartial), &off);
         if (rcr) return rcr;
         SummaryPartial *d_part = reinterpret_cast<SummaryPartial *>(h->d_results + off);
+        // asynchronous: on the summary stream, behind everything the compute stream holds so far (see bc_handle::stats)
+        cudaStream_t sstream = h->compute;
+        if (!sync && h->stats_overlap) {
+            sstream = h->stats;
+            CU(h, cudaEventRecord(h->stats_ready, h->compute));
+            CU(h, cudaStreamWaitEvent(h->stats, h->stats_ready, 0));
+        }
         if (h->d_counts64)
-            k2_summary<true, false><<<grid, 256, 0, h->compute>>>(h->d_counts, h->d_counts64, h->stride, h->d_col_base, h->d_ref_len,
-                                                                  K, norm, min_cov, h->d_log2_tab, h->d_part_off, d_part, nullptr,
-                                                                  nullptr, nullptr, nullptr);
+            k2_summary<true, false><<<grid, 256, 0, sstream>>>(h->d_counts, h->d_counts64, h->stride, h->d_col_base, h->d_ref_len,
+                                                               K, norm, min_cov, h->d_log2_tab, h->d_part_off, d_part, nullptr,
+                                                               nullptr, nullptr, nullptr);
         else
-            k2_summary<false, false><<<grid, 256, 0, h->compute>>>(h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K,
-                                                                   norm, min_cov, h->d_log2_tab, h->d_part_off, d_part, nullptr,
-                                                                   nullptr, nullptr, nullptr);
+            k2_summary<false, false><<<grid, 256, 0, sstream>>>(h->d_counts, nullptr, h->stride, h->d_col_base, h->d_ref_len, K,
+                                                                norm, min_cov, h->d_log2_tab, h->d_part_off, d_part, nullptr,
+                                                                nullptr, nullptr, nullptr);
+        if (sstream == h->stats) {
+            CU(h, cudaEventRecord(h->stats_done, h->stats));
+            h->stats_busy = true;
+            h->stats_set = h->cur_set;
+        }
         h->launches += 1;
         bc_handle::PendingReduce q;
         q.off = off;
@@ -1227,6 +1292,7 @@ int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, co
     if (ref >= h->n_refs || (uint64_t)col_lo + n_cols > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "halo out of range");
     if (n_cols == 0) return BC_OK;
     CU(h, cudaSetDevice(h->device));
+    JOIN_STATS(h);
     h->side_needs_compute = true;
     k_halo_add<<<(n_cols * kPlanes + 255) / 256, 256, 0, h->compute>>>(h->d_counts, h->stride,
                                                                       (uint64_t)h->col_base[ref] + col_lo, n_cols, dev_buf);
@@ -1241,6 +1307,7 @@ int bc_truncate(bc_handle *h, uint32_t ref, uint32_t new_len)
     if (ref >= h->n_refs || new_len > h->slot_cap[ref]) return fail(h, BC_ERR_ARG, "bc_truncate: out of range");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->side));               // an overflow check may still read the old length
+    JOIN_STATS(h);                                       // ... and so may a summary on its own stream
     h->ref_len[ref] = new_len;
     h->side_needs_compute = true;
     h->part_off_refs = 0;
@@ -1258,6 +1325,7 @@ int bc_set_length(bc_handle *h, uint32_t ref, uint32_t new_len)
     CU(h, cudaSetDevice(h->device));
     // the overflow check of the last batch (side stream) may still read the old length: order the write behind it
     CU(h, cudaStreamWaitEvent(h->compute, h->checked, 0));
+    JOIN_STATS(h);                                       // ... and so may a summary on its own stream
     h->ref_len[ref] = new_len;
     h->side_needs_compute = true;
     k_set_u32<<<1, 1, 0, h->compute>>>(h->d_ref_len + ref, new_len);
@@ -1355,6 +1423,7 @@ int bc_halo_merge(bc_handle *h, uint32_t ref, const uint32_t *bounds, const uint
         return fail(h, BC_ERR_ARG, "bc_halo_merge: the slot must hold the owned columns plus this rank's halo");
     if (h->d_counts64) return fail(h, BC_ERR_STATE, "bc_halo_merge: accumulators were folded to int64");
     CU(h, cudaSetDevice(h->device));
+    JOIN_STATS(h);
     struct Seg { int peer; uint64_t col; uint64_t n; };
     std::vector<Seg> sends, recvs;
     // what this rank sends: its halo covers global columns [hi, hi + halos[me])
@@ -1414,6 +1483,7 @@ int bc_timer_stop(bc_handle *h, float *ms)
 {
     if (!h || !ms) return BC_ERR_ARG;
     CU(h, cudaStreamWaitEvent(h->compute, h->checked, 0));   // work forked to the side stream belongs to the timed region
+    JOIN_STATS(h);                                           // ... and so do the summaries on theirs
     CU(h, cudaEventRecord(h->t1, h->compute));
     CU(h, cudaEventSynchronize(h->t1));
     CU(h, cudaEventElapsedTime(ms, h->t0, h->t1));

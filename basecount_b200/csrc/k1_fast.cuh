@@ -14,7 +14,10 @@
 //     two blocks ahead (indices clamped to the block's end, so a lane without a read holds an empty read and
 //     the last lane always holds the block's end offsets: no shuffles, no validity predicates);
 //   * the (at most three) CIGAR words of a read are loaded straight from HBM one block ahead -- no CIGAR
-//     staging, no staged-range bookkeeping;
+//     staging, no staged-range bookkeeping.  (Loading them by POSITION at the same time as the offsets and
+//     handing each lane its own through shared memory removes the dependent load and the register rotation --
+//     60 fewer instructions per block -- and was measured SLOWER: the exchange sits on the block's critical
+//     path, the rotation's moves do not.  profiles/r4_e_k1_times.txt);
 //   * sequence words are staged by one 1-D TMA bulk copy per block (two with a quality mask) into a ring of
 //     stages; the range a stage holds is recomputed from the metadata instead of being parked in shared memory;
 //   * the decode knows two shapes only, "M" and "M, I or D, M", in the packers' CIGAR normal form (cigar_canon.h);
@@ -27,6 +30,27 @@ namespace bc {
 
 #ifndef BC_K1F_MINCTAS
 #define BC_K1F_MINCTAS 3
+#endif
+// Register cap of the kernel (0: what three CTAs per SM allow, 168).  160 leaves 4,096 registers of an SM free beside
+// its three CTAs; a summarise kernel of 64-thread CTAs that fits there was measured (profiles/r4_g_step_ab.txt) and
+// lost: two warps per SM of dependent FP64 chains take 250 us.
+#ifndef BC_K1F_REGS
+#define BC_K1F_REGS 0
+#endif
+#if BC_K1F_REGS
+#define BC_K1F_BOUNDS __maxnreg__(BC_K1F_REGS)                      // (cannot be combined with __launch_bounds__)
+#else
+#define BC_K1F_BOUNDS __launch_bounds__(kK1Threads, BC_K1F_MINCTAS)
+#endif
+// A/B switches of tools/ab_variants.py (the defaults are the measured winners)
+#ifndef BC_K1F_MASK3
+#define BC_K1F_MASK3 1          // 1: lo&m, hi&m, (lo&m)&(hi&m) with m folded in (3 LOP3 per word); 0: m first, then 3 parallel ANDs
+#endif
+#ifndef BC_K1F_CSA_BRANCH
+#define BC_K1F_CSA_BRANCH 1     // 1: a parked carry is computed in the branch that parks it; 0: ahead of the branch
+#endif
+#ifndef BC_K1F_NL0_SMEM
+#define BC_K1F_NL0_SMEM 1       // 1: the lane's window offset comes back from shared memory (one VIADDMNMX per bound)
 #endif
 constexpr uint32_t kFastSeqBuf = 3u * kSeqCap;   // staged 64-bit plane words per warp: 3 stages of kSeqCap words, or 4 of 3/4 kSeqCap
 constexpr uint32_t kFastStageShort = kFastSeqBuf / 4u;
@@ -50,7 +74,6 @@ struct K1FastCfg {
     static constexpr uint32_t kWin = 32u * kW * G;
     static constexpr uint32_t kMaxFit = kWin - 31u;
     static constexpr uint32_t kCols = kFlushStride * kW * G;
-    static constexpr uint32_t lut_bytes = 528;
     // per warp: ring | sequence stages | quality-mask stages | flush rows | difference array | mbarriers.  A piece's
     // unclamped word index reaches up to 64*G columns before or after its data: the ring in front and the flush
     // rows behind keep those (masked-away) reads inside the CTA's shared memory.
@@ -63,7 +86,7 @@ struct K1FastCfg {
     static constexpr uint32_t cov_bytes = HAS_OK ? 0u : (kWin + 4u) * 4u;
     static constexpr uint32_t bar_off = cov_off + cov_bytes;
     static constexpr uint32_t warp_bytes = bar_off + 32u;
-    static constexpr uint32_t cta_bytes = lut_bytes + kK1WarpsPerCta * warp_bytes;
+    static constexpr uint32_t cta_bytes = kK1WarpsPerCta * warp_bytes;      // + the statically allocated mask table
     static_assert(seq_off % 16 == 0 && ok_off % 16 == 0 && frow_off % 16 == 0 && cov_off % 16 == 0 && bar_off % 16 == 0 &&
                       warp_bytes % 16 == 0,
                   "TMA destinations are 16-byte aligned");
@@ -77,7 +100,6 @@ __host__ __device__ constexpr uint32_t k1_fast_cta_smem_bytes()
     return K1FastCfg<G, HAS_OK>::cta_bytes;
 }
 
-// Predicated read-only load without a branch: 0 when the predicate is off.
 __device__ __forceinline__ uint32_t ldg_if(const uint32_t *p, bool on)
 {
     uint32_t v = 0u;
@@ -90,15 +112,18 @@ __device__ __forceinline__ void red_shared_add(uint32_t a, uint32_t v)
 }
 
 // Masked words of one ring entry (a piece) for a lane's two window words: lo, hi, lo & hi (and the mask itself when
-// "valid" is counted bit-sliced).  Entry layout as in k1_count.cuh.
+// "valid" is counted bit-sliced).  Entry: x / y = 8 * first / end column of the piece relative to the window (the
+// byte offset of its mask in the table), z = bit index of window column 0 in the staged data, w = shared address
+// of the plane word that holds window column 0.  nL0_8 = -8 * (the lane's first window column); lut = the mask
+// table's shared address, a link-time constant that ends up as the immediate of the LDS.
 template <bool HAS_OK, int NC>
-__device__ __forceinline__ void fast_piece(const uint4 e, uint32_t (&x)[kW][NC], int L0, uint32_t lutb, uint32_t lane_seq_off,
+__device__ __forceinline__ void fast_piece(const uint4 e, uint32_t (&x)[kW][NC], int nL0_8, uint32_t lut, uint32_t lane_seq_off,
                                            uint32_t seqb, uint32_t okb)
 {
-    const int a_c = __viaddmin_s32_relu((int)e.x, -L0, 64);      // clamp(first - L0, 0, 64)
-    const int e_c = __viaddmin_s32_relu((int)e.y, -L0, 64);
-    const uint2 ga = lds64(lutb + 8u * (uint32_t)a_c), ge = lds64(lutb + 8u * (uint32_t)e_c);
-    uint32_t m[kW] = {ga.x & ~ge.x, ga.y & ~ge.y};
+    const uint32_t a_c = (uint32_t)__viaddmin_s32_relu((int)e.x, nL0_8, 512);   // 8 * clamp(first - L0, 0, 64)
+    const uint32_t e_c = (uint32_t)__viaddmin_s32_relu((int)e.y, nL0_8, 512);
+    const uint2 ga = lds64(lut + a_c), ge = lds64(lut + e_c);
+    const uint32_t g1[kW] = {ga.x, ga.y}, g0[kW] = {ge.x, ge.y};                 // columns at or above first / end
     const uint32_t wa = e.w + lane_seq_off;
     const uint2 r0 = lds64(wa), r1 = lds64(wa + 8u), r2 = lds64(wa + 16u);
     const uint32_t lo[kW] = {__funnelshift_r(r0.x, r1.x, e.z), __funnelshift_r(r1.x, r2.x, e.z)};
@@ -106,15 +131,29 @@ __device__ __forceinline__ void fast_piece(const uint4 e, uint32_t (&x)[kW][NC],
     if (HAS_OK) {
         const uint32_t oa = okb + (uint32_t)((int)(wa - seqb) >> 1);
         const uint32_t o0 = lds32(oa), o1 = lds32(oa + 4u), o2 = lds32(oa + 8u);
-        m[0] &= __funnelshift_r(o0, o1, e.z);
-        m[1] &= __funnelshift_r(o1, o2, e.z);
-    }
+        const uint32_t ok[kW] = {__funnelshift_r(o0, o1, e.z), __funnelshift_r(o1, o2, e.z)};
 #pragma unroll
-    for (int w = 0; w < kW; w++) {
-        x[w][0] = lo[w] & m[w];
-        x[w][1] = hi[w] & m[w];
-        x[w][2] = lo[w] & hi[w] & m[w];
-        if (NC > 3) x[w][3] = m[w];
+        for (int w = 0; w < kW; w++) {
+            const uint32_t m = ok[w] & g1[w] & ~g0[w];
+            x[w][0] = lo[w] & m;
+            x[w][1] = hi[w] & m;
+            x[w][2] = x[w][0] & x[w][1];
+            if (NC > 3) x[w][3] = m;
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < kW; w++) {
+#if BC_K1F_MASK3
+            x[w][0] = lo[w] & g1[w] & ~g0[w];                                     // three LOP3 per window word
+            x[w][1] = hi[w] & g1[w] & ~g0[w];
+            x[w][2] = x[w][0] & x[w][1];
+#else
+            const uint32_t m = g1[w] & ~g0[w];
+            x[w][0] = lo[w] & m;
+            x[w][1] = hi[w] & m;
+            x[w][2] = lo[w] & hi[w] & m;
+#endif
+        }
     }
 }
 
@@ -136,14 +175,37 @@ __device__ __forceinline__ void csa_half(const uint32_t (&x)[4][kW][NC], uint32_
     }
 }
 
+// majority / parity of three words as ONE instruction each that the compiler neither merges with an identical
+// expression in another branch nor moves out of its branch (see csa_upper)
+__device__ __forceinline__ uint32_t maj3_here(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm volatile("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
 // The upper levels of one trip (eight pieces per read slot): the two weight-4 carries of its halves meet in plane 2
 // with no pending register; the weight-8 carry is parked every other trip (pb), the weight-16 carry every fourth
 // (pc), and the weight-32 carry ripples through planes 5.. every eighth.  cnt = pieces per slot counted before
-// this trip (a multiple of 8).
+// this trip (a multiple of 8).  A carry that is parked is COMPUTED in the branch that parks it, straight into the
+// pending register: computed ahead of the branch it cost a register move per counter in every trip.
 template <int NC, int NB>
 __device__ __forceinline__ void csa_upper(const uint32_t (&c2a)[kW][NC], const uint32_t (&c2b)[kW][NC], uint32_t (&pl)[kW][NC][NB],
                                           uint32_t (&pb)[kW][NC], uint32_t (&pc)[kW][NC], uint32_t cnt)
 {
+#if !BC_K1F_CSA_BRANCH
+#define maj3_here maj3
+#endif
+    if (!(cnt & 8u)) {
+#pragma unroll
+        for (int w = 0; w < kW; w++)
+#pragma unroll
+            for (int k = 0; k < NC; k++) {
+                pb[w][k] = maj3_here(pl[w][k][2], c2a[w][k], c2b[w][k]);
+                pl[w][k][2] ^= c2a[w][k] ^ c2b[w][k];
+            }
+        return;
+    }
     uint32_t c3[kW][NC];
 #pragma unroll
     for (int w = 0; w < kW; w++) {
@@ -153,43 +215,35 @@ __device__ __forceinline__ void csa_upper(const uint32_t (&c2a)[kW][NC], const u
             pl[w][k][2] ^= c2a[w][k] ^ c2b[w][k];
         }
     }
-    if (!(cnt & 8u)) {
+    if (!(cnt & 16u)) {
 #pragma unroll
         for (int w = 0; w < kW; w++)
 #pragma unroll
-            for (int k = 0; k < NC; k++) pb[w][k] = c3[w][k];
-    } else {
-        uint32_t c4[kW][NC];
-#pragma unroll
-        for (int w = 0; w < kW; w++) {
-#pragma unroll
             for (int k = 0; k < NC; k++) {
-                c4[w][k] = maj3(pl[w][k][3], pb[w][k], c3[w][k]);
+                pc[w][k] = maj3_here(pl[w][k][3], pb[w][k], c3[w][k]);
                 pl[w][k][3] ^= pb[w][k] ^ c3[w][k];
             }
-        }
-        if (!(cnt & 16u)) {
+        return;
+    }
 #pragma unroll
-            for (int w = 0; w < kW; w++)
+    for (int w = 0; w < kW; w++) {
 #pragma unroll
-                for (int k = 0; k < NC; k++) pc[w][k] = c4[w][k];
-        } else {
+        for (int k = 0; k < NC; k++) {
+            const uint32_t c4 = maj3(pl[w][k][3], pb[w][k], c3[w][k]);
+            pl[w][k][3] ^= pb[w][k] ^ c3[w][k];
+            uint32_t c = maj3(pl[w][k][4], pc[w][k], c4);
+            pl[w][k][4] ^= pc[w][k] ^ c4;
 #pragma unroll
-            for (int w = 0; w < kW; w++) {
-#pragma unroll
-                for (int k = 0; k < NC; k++) {
-                    uint32_t c = maj3(pl[w][k][4], pc[w][k], c4[w][k]);
-                    pl[w][k][4] ^= pc[w][k] ^ c4[w][k];
-#pragma unroll
-                    for (int p = 5; p < NB; p++) {        // ripple the weight-32 carry upwards
-                        const uint32_t t = pl[w][k][p] & c;
-                        pl[w][k][p] ^= c;
-                        c = t;
-                    }
-                }
+            for (int p = 5; p < NB; p++) {        // ripple the weight-32 carry upwards
+                const uint32_t t = pl[w][k][p] & c;
+                pl[w][k][p] ^= c;
+                c = t;
             }
         }
     }
+#if !BC_K1F_CSA_BRANCH
+#undef maj3_here
+#endif
 }
 
 // Convert the warp's vertical counters to integers and add them to the HBM planes (the flush of k1_count.cuh with
@@ -373,7 +427,7 @@ __device__ __forceinline__ void flush_fast(uint32_t (&pl)[kW][NC][NB], uint32_t 
 }
 
 template <int G, bool HAS_OK>
-__global__ void __launch_bounds__(kK1Threads, BC_K1F_MINCTAS)
+__global__ void BC_K1F_BOUNDS
 k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t rpb, uint32_t nst,
               Chunk *__restrict__ deferred, uint32_t *__restrict__ n_deferred)
 {
@@ -381,30 +435,39 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
     constexpr int S = C::S, Q = C::Q, Q2 = C::Q2, NC = C::NC, NB = C::NB;
     constexpr uint32_t kWin = C::kWin;
     extern __shared__ __align__(128) unsigned char k1_smem[];
+    // lut[v] = the 64 window columns of a lane at or above column v (v in [0, 64]).  Statically allocated: its shared
+    // address is a constant, so a mask lookup is one LDS [8 * v + constant].
+    __shared__ uint2 k1f_lut[66];
 
     uint32_t lane_u;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_u));
     const int lane = (int)lane_u;
     const int warp_in_cta = threadIdx.x >> 5;
 
-    // lut[v] = the 64 window columns of a lane at or above column v (v in [0, 64])
-    uint2 *lut = reinterpret_cast<uint2 *>(k1_smem);
     for (int v = threadIdx.x; v <= 64; v += kK1Threads)
-        lut[v] = make_uint2(v < 32 ? 0xFFFFFFFFu << v : 0u, v <= 32 ? 0xFFFFFFFFu : (v < 64 ? 0xFFFFFFFFu << (v - 32) : 0u));
+        k1f_lut[v] = make_uint2(v < 32 ? 0xFFFFFFFFu << v : 0u, v <= 32 ? 0xFFFFFFFFu : (v < 64 ? 0xFFFFFFFFu << (v - 32) : 0u));
     __syncthreads();                                // the only CTA-wide barrier: warps are independent from here on
 
     const uint32_t warp_id = blockIdx.x * kK1WarpsPerCta + warp_in_cta;
     if (warp_id >= n_chunks) return;
 
-    unsigned char *wsm = k1_smem + C::lut_bytes + (size_t)warp_in_cta * C::warp_bytes;
+    unsigned char *wsm = k1_smem + (size_t)warp_in_cta * C::warp_bytes;
     uint16_t *frow = reinterpret_cast<uint16_t *>(wsm + C::frow_off);          // flush only
-    const uint32_t lutb = opaque(smem_u32(k1_smem));
+    const uint32_t lut = smem_u32(k1f_lut);
     const uint32_t wb = opaque(smem_u32(wsm));                                 // the warp's region
     const uint32_t ringb = wb + C::ring_off, seqb = wb + C::seq_off, okb = wb + C::ok_off, barb = wb + C::bar_off,
-                   covb = wb + C::cov_off;
+                   covb = wb + C::cov_off, xchb = wb + C::frow_off;
 
     const int slot = lane / G, wl = lane % G;
-    const int L0 = 32 * kW * wl;                    // window column of this lane's bit 0
+    // -8 * (window column of this lane's bit 0), through shared memory: a value ptxas cannot re-derive from the lane
+    // number, so the clamp in fast_piece is ONE add-min-relu instead of a multiply-add and a min-relu per bound
+#if BC_K1F_NL0_SMEM
+    sts32(xchb + 4u * (uint32_t)lane, (uint32_t)(-8 * 32 * kW * wl));
+    int nL0_8;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(nL0_8) : "r"(xchb + 4u * (uint32_t)lane) : "memory");
+#else
+    const int nL0_8 = -8 * 32 * kW * wl;
+#endif
     const uint32_t lt_mask = opaque((1u << lane) - 1u);
     const uint32_t trip_ringb = opaque(ringb + 16u * (uint32_t)slot);          // ring entry of this slot in a trip
     const uint32_t lane_seq_off = 8u * kW * (uint32_t)wl;                      // byte offset of this lane's window words
@@ -458,11 +521,10 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
         c.c2 = ldg_if(p + 2, n > 2u);
         return c;
     };
-    // Stage the sequence words of a block: [first word & ~3, last word rounded up) clipped to a stage.
-    auto issue_block = [&](const Meta &m, uint32_t stg) {
-        const uint32_t s0 = __shfl_sync(kFull, m.wb, 0), s1 = __shfl_sync(kFull, m.we, 31);
+    // Stage the sequence words [t_lo, t_hi) of a block: [first word & ~3, last word rounded up) clipped to a stage.
+    auto issue_block = [&](uint32_t t_lo, uint32_t t_hi, uint32_t stg) {
         if (lane == 0) {
-            const uint32_t s_lo = s0 & ~3u, s_n = min(((s1 + 3u) & ~3u) - s_lo, stage_words);  // 32 B / 16 B aligned sources
+            const uint32_t s_lo = t_lo & ~3u, s_n = min(((t_hi + 3u) & ~3u) - s_lo, stage_words);  // 32 B / 16 B aligned sources
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of this stage
             const uint32_t bar = barb + 8u * stg;
             mbar_expect_tx_s(bar, s_n * 8u + (HAS_OK ? s_n * 4u : 0u));
@@ -472,10 +534,21 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
             }
         }
     };
+    auto block_end_woff = [&](uint32_t blk) {                                // seq_woff at the end of block blk (one address per warp)
+        return __ldg(bv.seq_woff + min(rb + (blk + 1u) * rpb, re));
+    };
 
     Meta M0 = load_meta(0), M1 = load_meta(1);
-    issue_block(M0, 0);
-    if (nblk > 1) issue_block(M1, 1);
+    uint32_t t_next;                                // seq_woff at the end of the last block staged so far
+    {
+        const uint32_t t0 = __ldg(bv.seq_woff + rb), t1 = block_end_woff(0);
+        issue_block(t0, t1, 0);
+        t_next = t1;
+        if (nblk > 1) {
+            t_next = block_end_woff(1);
+            issue_block(t1, t_next, 1);
+        }
+    }
     Cig C0 = load_cig(M0);
 
     uint32_t phases = 0;                            // bit s: parity to wait for on stage s
@@ -512,7 +585,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
     // quality mask the piece also enters the coverage difference array here.
     auto push_entry = [&](uint32_t at, uint32_t rel, uint32_t n, int qbit) {
         const int z = qbit - (int)rel;
-        sts128(ringb + 16u * (at & (kFastRing - 1u)), make_uint4(rel, rel + n, (uint32_t)z, seqb + (uint32_t)((z >> 5) * 8)));
+        sts128(ringb + 16u * (at & (kFastRing - 1u)), make_uint4(8u * rel, 8u * (rel + n), (uint32_t)z, seqb + (uint32_t)((z >> 5) * 8)));
         if (NC == 3) {
             red_shared_add(covb + 4u * rel, 1u);
             red_shared_add(covb + 4u * (rel + n), 0xFFFFFFFFu);
@@ -526,6 +599,8 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
         const bool last = (j == nblk);
         const Meta M2 = load_meta(j + 2u);                                   // in flight during this block
         const Cig C1 = load_cig(M1);
+        const uint32_t t_lo = t_next;
+        t_next = block_end_woff(j + 2u);                                     // (clamped to the chunk's end: always loadable)
         if (!last) {
             mbar_wait_s(barb + 8u * st, (phases >> st) & 1u);
             phases ^= 1u << st;
@@ -614,7 +689,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
                         }
                         if (!(cnt != 0u && (left || last))) break;
                     }
-                    flush_fast<G, NC, NB>(pl, pb, pc, cnt, frow, covb, plane0 + win_lo, cv.stride, lane);
+                    flush_fast<G, NC, NB>(pl, pb, pc, cnt, frow, covb, plane0 + opaque(win_lo), cv.stride, lane);
                     cnt = 0u;
                     continue;
                 }
@@ -629,7 +704,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
                     for (int q = 0; q < 4; q++) e[q] = lds128(ea + 16u * (uint32_t)(q * S));
                     uint32_t x[4][kW][NC];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) fast_piece<HAS_OK, NC>(e[q], x[q], L0, lutb, lane_seq_off, seqb, okb);
+                    for (int q = 0; q < 4; q++) fast_piece<HAS_OK, NC>(e[q], x[q], nL0_8, lut, lane_seq_off, seqb, okb);
                     csa_half<NC, NB>(x, pl, c2a);
                 }
                 {
@@ -638,7 +713,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
                     for (int q = 0; q < 4; q++) e[q] = lds128(ea + 16u * (uint32_t)(Q + q * S));
                     uint32_t x[4][kW][NC];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) fast_piece<HAS_OK, NC>(e[q], x[q], L0, lutb, lane_seq_off, seqb, okb);
+                    for (int q = 0; q < 4; q++) fast_piece<HAS_OK, NC>(e[q], x[q], nL0_8, lut, lane_seq_off, seqb, okb);
                     csa_half<NC, NB>(x, pl, c2b);
                 }
                 csa_upper<NC, NB>(c2a, c2b, pl, pb, pc, cnt);
@@ -648,7 +723,7 @@ k1_count_fast(BatchView bv, CountView cv, const Chunk *__restrict__ chunks, uint
             // move the window to the lowest pending piece (the counters were flushed above)
             win_lo = __reduce_min_sync(kFull, min(nA ? rpA : 0xFFFFFFFFu, nB ? ppB : 0xFFFFFFFFu)) & ~31u;
         }
-        if (want_issue) issue_block(M2, st + 2u >= nst ? st + 2u - nst : st + 2u);
+        if (want_issue) issue_block(t_lo, t_next, st + 2u >= nst ? st + 2u - nst : st + 2u);
 
         // ---- rotate the pipelines
         // (the values loaded at the top of this block are first touched HERE, by instructions the compiler cannot

@@ -189,3 +189,57 @@ def test_summarise_entropy_paths_vs_oracle(eng, shape):
             keep = cov_a >= thr
             assert int(sel[0]) == int(keep.sum()) and int(cs2[0]) == int(cov_a.sum())
             assert float(es2[0]) == pytest.approx(float(ent_a[keep].sum()), rel=TIGHT, abs=1e-300)
+
+
+def test_pipelined_summaries_see_their_own_step(eng):
+    """bc_summary_async runs on its own stream, beside the counting kernel of the NEXT step (which, after
+    bc_reset, writes the other set of accumulators).  A pipeline of steps over three different batches with no
+    synchronisation in between must hand every step the summary of ITS batch; a push with no reset in between
+    (same accumulators) must wait for the queued summary; a length change must wait for it too."""
+    from basecount_b200.pack import pack_batches
+    L = 4000
+    batches = [select_reads(synth.amplicon_sample(seed=60 + k, n_reads=900 + 400 * k, ref_len=L, ref_name="p"), 0, 0)
+               for k in range(3)]
+    packed = [pack_batches(b, 0) for b in batches]
+    want = []
+    for p in packed:                                      # synchronous references, one batch at a time
+        eng.begin([L])
+        eng.push(p)
+        eng.sync()
+        want.append(tuple(np.array(a).copy() for a in eng.summary(False)))
+    eng.begin([L])
+    outs = []
+    for i in range(12):
+        s = (np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.float64))
+        eng.reset()
+        eng.push(packed[i % 3])
+        eng.summary_async(s, False)
+        outs.append(s)
+    eng.sync()
+    for i, s in enumerate(outs):
+        w = want[i % 3]
+        assert int(s[0][0]) == int(w[0][0]) and int(s[1][0]) == int(w[1][0]) and float(s[2][0]) == float(w[2][0]), i
+    # no reset between the queued summary and the next push: the summary must not see the second batch
+    eng.begin([L])
+    eng.push(packed[0])
+    s0 = (np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.float64))
+    eng.summary_async(s0, False)
+    eng.push(packed[1])
+    s01 = (np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.float64))
+    eng.summary_async(s01, False)
+    eng.sync()
+    assert int(s0[1][0]) == int(want[0][1][0]) and float(s0[2][0]) == float(want[0][2][0])
+    assert int(s01[1][0]) == int(want[0][1][0]) + int(want[1][1][0])
+    # a device-side length change behind a queued summary: the summary still covers the old length
+    eng.begin([L])
+    eng.push(packed[2])
+    s2 = (np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.float64))
+    eng.summary_async(s2, False)
+    eng.set_length(0, L // 2)
+    half = (np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.float64))
+    eng.summary_async(half, False)
+    eng.sync()
+    assert int(s2[1][0]) == int(want[2][1][0]) and float(s2[2][0]) == float(want[2][2][0])
+    assert int(half[1][0]) == int(eng.counts(0)[:, :5].sum()) < int(want[2][1][0])
+    eng.set_length(0, L)
+    eng.sync()
