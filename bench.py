@@ -400,6 +400,51 @@ def bam_batch_end_to_end(local, n_files, barrier, max_over_ranks, sum_over_ranks
                        "next file opened on a second thread while the current one is packed and counted"}
 
 
+def tsv_stream_end_to_end(with_reference, ref_len=4_000_000):
+    """`basecount BAM_FILE` (BASELINE configs[0]'s mode) at a whole-genome shape: a 4 Mb reference at 30x (800 k reads x
+    150 bp -- configs[4]'s shape at 1/16 of its length) from the BAM path to the per-position TSV on disk, streamed
+    window by window (BaseCount.write_tsv: bc_rows_window + the native emitter, main.py:454-466).  rows/s from file
+    path to the last byte written; the first 50,000 rows are compared byte for byte with the oracle's text, and the
+    reference's own Python path (get_stats + str(round())) is timed on those rows beside it."""
+    from basecount_b200 import BaseCount, bamio, synth
+    path = f"/tmp/bc_bench_region_{ref_len}.bam"
+    if not os.path.exists(path):
+        rec = synth.uniform_short_read_sample(seed=5, ref_len=ref_len, n_reads=ref_len * 30 // 150, read_len=150, ref_name="chr20s")
+        bamio.write_bam(path, rec)
+    out_path = "/tmp/bc_bench_rows.tsv"
+    best, rows, size = None, 0, 0
+    for _ in range(2):
+        t0 = time.perf_counter()
+        with BaseCount(path) as bc, open(out_path, "w") as f:
+            rows = bc.write_tsv(f)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        size = os.path.getsize(out_path)
+    rec = {"seconds": best, "rows": rows, "value": rows / best, "unit": "rows/s", "tsv_mb": size / 1e6, "ref_len": ref_len,
+           "bam_mb": os.path.getsize(path) / 1e6,
+           "path": "native BAM decode -> K1 -> K2 rows per 524,288-position window -> native emitter (tsv_format.h) -> file"}
+    if with_reference:
+        from oracle import bcount as obc
+        from oracle import stats as ost
+        from basecount_b200.records import select_reads
+        n_check = 50_000
+        b = select_reads(synth.uniform_short_read_sample(seed=5, ref_len=ref_len, n_reads=ref_len * 30 // 150, read_len=150,
+                                                         ref_name="chr20s"), 0, 0)            # what the BAM was written from
+        part = synth.take_batch(b, np.flatnonzero(b.starts < n_check))
+        counts = obc.bcount_flat(n_check + 4096, 0, part)[:n_check].tolist()
+        t0 = time.perf_counter()
+        want = ost.format_tsv(ost.columns(), ost.rows(counts, "chr20s"))
+        dt_ref = time.perf_counter() - t0
+        with open(out_path) as f:
+            got = "".join(next(f) for _ in range(n_check + 1))
+        assert got == want[:len(got)] and len(got) > n_check, "streamed TSV differs from the oracle's text"
+        rec["oracle_guard"] = f"header + first {n_check} rows equal the oracle's text byte for byte"
+        rec["reference"] = {"value": n_check / dt_ref, "unit": "rows/s", "cores": 1, "kind": "port",
+                            "sample": f"python port of get_stats + str(round(x, 3)) (main.py:14-79,454-466) on the first {n_check} "
+                                      "positions; counting and BAM decode not included"}
+    return rec
+
+
 def region_bam_end_to_end(rank, world, local, barrier, max_over_ranks, sum_over_ranks, ref_len=4_000_000):
     """BASELINE configs[4] through the BAM path, scaled to a 4 Mb reference (800 k reads x 150 bp; writing a
     64 Mb BAM with the in-repo writer would take minutes): every rank opens ITS region of one coordinate-sorted,
@@ -889,6 +934,8 @@ def main():
         state["resident"] = []
         line["bam_e2e"] = bam_end_to_end(state["eng"], not args.no_cpu_baseline)
     release(state)
+    if rank == 0 and world == 1 and default_line:
+        line["tsv_stream"] = tsv_stream_end_to_end(not args.no_cpu_baseline)
 
     if default_line and world == 1:
         # the other single-GPU shapes of BASELINE.json (configs[2] and configs[4]) as sub-records of the same line
