@@ -99,6 +99,9 @@ _SIGNATURES = {
     "bc_free_text": (None, [ctypes.c_void_p]),
     # native BAM decode (host code in the same library)
     "bc_bam_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "bc_bam_stream_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "bc_bam_stream_next": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]),
+    "bc_bam_stream_close": (None, [ctypes.c_void_p]),
     "bc_bam_last_error": (ctypes.c_char_p, []),
     "bc_bgzf_crc32": (ctypes.c_uint32, [ctypes.c_void_p, ctypes.c_uint64]),
     "bc_inflate_raw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64]),

@@ -238,6 +238,19 @@ class NativeBam:
         if rc != 0 or not h.value:
             msg = self._L.bc_bam_last_error()
             raise ValueError(msg.decode() if msg else "cannot read BAM file")
+        self._adopt(h)
+
+    @classmethod
+    def _from_handle(cls, h):
+        """A NativeBam over a bc_bam the library has already opened (a span of a NativeBamStream)."""
+        from . import _lib
+        self = cls.__new__(cls)
+        self._h = None
+        self._L = _lib.lib()
+        self._adopt(h)
+        return self
+
+    def _adopt(self, h):
         self._h = h
         self.n = int(self._L.bc_bam_num_records(h))
         nref = int(self._L.bc_bam_num_refs(h))
@@ -344,6 +357,75 @@ def _native_pack(self, ref_id: int, min_mapping_quality: int = 0, min_base_quali
 
 
 NativeBam.pack = _native_pack
+
+
+class NativeBamStream:
+    """A BAM file read span by span (bc_bam_stream_*): iterating yields NativeBam objects that each hold the whole
+    records starting in the next ~span_bytes of the inflated stream, so host memory is bounded by the span (two of them:
+    the next span is inflated on a second thread while the caller works on the current one) whatever the size of the
+    file -- the role of the reference's fetch(until_eof=True) loop with its chunk_size (main.py:127,142).  The first
+    span exists even for a file without records, so `ref_names` / `ref_lengths` are always available from it.
+    The caller closes every span it is handed."""
+
+    def __init__(self, path: str, threads: int = 0, span_bytes: int | None = None):
+        import ctypes
+        import os
+        from . import _lib
+        self._L = _lib.lib()
+        self._s = None
+        s = ctypes.c_void_p()
+        rc = self._L.bc_bam_stream_open(str(path).encode(), int(threads), ctypes.byref(s))
+        if rc != 0 or not s.value:
+            msg = self._L.bc_bam_last_error()
+            raise ValueError(msg.decode() if msg else "cannot read BAM file")
+        self._s = s
+        if span_bytes is None:
+            span_bytes = int(float(os.environ.get("BASECOUNT_B200_SPAN_MB", "512")) * (1 << 20))
+        self.span_bytes = max(int(span_bytes), 1)
+
+    def _next(self):
+        import ctypes
+        h = ctypes.c_void_p()
+        rc = self._L.bc_bam_stream_next(self._s, self.span_bytes, ctypes.byref(h))
+        if rc != 0:
+            msg = self._L.bc_bam_last_error()
+            raise ValueError(msg.decode() if msg else "cannot read BAM file")
+        return NativeBam._from_handle(h) if h.value else None
+
+    def __iter__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(self._next)
+            while True:
+                try:
+                    span = fut.result()
+                except BaseException:
+                    raise
+                if span is None:
+                    return
+                fut = pool.submit(self._next)
+                try:
+                    yield span
+                except GeneratorExit:
+                    nxt = fut.result()
+                    if nxt is not None:
+                        nxt.close()
+                    raise
+
+    def close(self):
+        if self._s is not None:
+            self._L.bc_bam_stream_close(self._s)
+            self._s = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 def write_bai(bam_path: str, bai_path: str | None = None, threads: int = 0) -> str:

@@ -493,6 +493,207 @@ inline int bc_bam_open_impl(const char *path, int threads, bc_bam **out, std::st
     return 0;
 }
 
+// ---- a BAM file read span by span (bounded host memory) ----------------------------------------------------------
+// bc_bam_open_impl holds the whole inflated file, which a whole-genome BAM (hundreds of GB inflated) does not
+// allow.  A stream maps the file, scans the BGZF block headers once (no inflation), parses the header from the
+// first blocks, and then hands out consecutive SPANS: an ordinary bc_bam holding the records that start in the next
+// ~max_bytes of the inflated stream (whole records only; the record that straddles the end opens the next span).
+// Everything that works on a bc_bam -- core, select, one-pass pack -- works on a span; the host counts span after
+// span into the same accumulators (the counts do not depend on where the cuts fall, main.py:142).
+struct bc_bam_stream {
+    void *map = nullptr;
+    uint64_t fsize = 0;
+    std::vector<bcbam::Block> blocks;
+    uint64_t total = 0;                     // inflated bytes of the whole file
+    std::vector<std::string> ref_names;
+    std::vector<uint32_t> ref_lens;
+    uint64_t cur = 0;                       // inflated offset of the next record
+    bool first = true;                      // the first span is handed out even when it holds no record
+    int threads = 1;
+    ~bc_bam_stream()
+    {
+        if (map && fsize) ::munmap(map, fsize);
+    }
+};
+
+namespace bcbam {
+
+// Inflate blocks [i0, i1) of the mapped file into dst (dst[0] = inflated offset blocks[i0].u0).
+inline bool inflate_blocks(const uint8_t *file, const std::vector<Block> &blocks, uint64_t i0, uint64_t i1, uint8_t *dst, int threads)
+{
+    if (i1 <= i0) return true;
+    const uint64_t base = blocks[i0].u0;
+    std::atomic<int> bad(0);
+    parallel_for(threads, i1 - i0, 16, [&](uint64_t a, uint64_t e) {
+        z_stream zs;
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            bad = 1;
+            return;
+        }
+        std::unique_ptr<FastInflater> fi(fast_inflate_enabled() ? new FastInflater() : nullptr);
+        for (uint64_t i = i0 + a; i < i0 + e; i++) {
+            const Block &k = blocks[i];
+            if (k.isize == 0) continue;
+            if (!inflate_block_checked(fi.get(), &zs, file + k.c0, k.c1 - k.c0, dst + (k.u0 - base), k.isize, k.crc)) bad = 1;
+        }
+        inflateEnd(&zs);
+    });
+    return !bad;
+}
+
+// First block index whose inflated range ends beyond offset u (blocks.size() if none).
+inline uint64_t block_of(const std::vector<Block> &blocks, uint64_t u)
+{
+    uint64_t lo = 0, hi = blocks.size();
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) / 2;
+        if (blocks[mid].u0 + blocks[mid].isize <= u) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace bcbam
+
+inline int bc_bam_stream_open_impl(const char *path, int threads, bc_bam_stream **out, std::string &err)
+{
+    using namespace bcbam;
+    const int fd = ::open(path, O_RDONLY);
+    if (fd < 0) {
+        err = std::string("cannot open ") + path;
+        return 1;
+    }
+    struct stat st;
+    if (::fstat(fd, &st) != 0 || st.st_size < 0) {
+        ::close(fd);
+        err = "cannot size the file";
+        return 1;
+    }
+    std::unique_ptr<bc_bam_stream> s(new bc_bam_stream());
+    s->fsize = (uint64_t)st.st_size;
+    s->map = s->fsize ? ::mmap(nullptr, s->fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    ::close(fd);
+    if (s->fsize && s->map == MAP_FAILED) {
+        s->map = nullptr;
+        err = "cannot map the file";
+        return 1;
+    }
+    s->threads = threads > 0 ? threads : (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    const uint8_t *file = static_cast<const uint8_t *>(s->map);
+    if (!scan_blocks(file, s->fsize, s->blocks, s->total, err)) return 2;
+    // the header (SAM spec 4.2) from a prefix of the inflated stream, doubled until it holds all of it
+    uint64_t want = 1u << 20;
+    for (;;) {
+        const uint64_t i1 = std::min<uint64_t>(block_of(s->blocks, std::min(want, s->total)) + 1, s->blocks.size());
+        const uint64_t have = i1 ? s->blocks[i1 - 1].u0 + s->blocks[i1 - 1].isize : 0;
+        ByteVec r;
+        r.resize(have);
+        if (!inflate_blocks(file, s->blocks, 0, i1, r.data(), s->threads)) {
+            err = "corrupt BGZF block (inflate or CRC failed)";
+            return 2;
+        }
+        const bool all = have >= s->total;
+        auto retry = [&]() { return !all; };                 // truncated inside this prefix: look at a longer one
+        if (r.size() < 12 || std::memcmp(r.data(), "BAM\1", 4) != 0) {
+            if (r.size() < 12 && retry()) { want *= 2; continue; }
+            err = "not a BAM file (bad magic)";
+            return 2;
+        }
+        uint64_t p = 8ull + rd32(&r[4]);
+        bool cut = p + 4 > r.size();
+        uint32_t n_ref = cut ? 0u : rd32(&r[p]);
+        p += 4;
+        s->ref_names.clear();
+        s->ref_lens.clear();
+        for (uint32_t i = 0; i < n_ref && !cut; i++) {
+            if (p + 4 > r.size()) { cut = true; break; }
+            const uint32_t l_name = rd32(&r[p]);
+            if (l_name == 0) {
+                err = "truncated BAM header";
+                return 2;
+            }
+            if (p + 8ull + l_name > r.size()) { cut = true; break; }
+            s->ref_names.emplace_back((const char *)&r[p + 4], l_name - 1);
+            s->ref_lens.push_back(rd32(&r[p + 4 + l_name]));
+            p += 8ull + l_name;
+        }
+        if (cut) {
+            if (retry()) { want *= 2; continue; }
+            err = "truncated BAM header";
+            return 2;
+        }
+        s->cur = p;
+        break;
+    }
+    *out = s.release();
+    return 0;
+}
+
+// The next span (see bc_bam_stream): *out = nullptr at the end of the file.
+inline int bc_bam_stream_next_impl(bc_bam_stream *s, uint64_t max_bytes, bc_bam **out, std::string &err)
+{
+    using namespace bcbam;
+    *out = nullptr;
+    if (s->cur >= s->total && !s->first) return 0;
+    const uint8_t *file = static_cast<const uint8_t *>(s->map);
+    if (max_bytes < (1u << 16)) max_bytes = 1u << 16;
+    for (;;) {
+        std::unique_ptr<bc_bam> b(new bc_bam());
+        b->threads = s->threads;
+        b->ref_names = s->ref_names;
+        b->ref_lens = s->ref_lens;
+        const uint64_t i0 = block_of(s->blocks, s->cur);
+        const uint64_t end_want = s->total - s->cur > max_bytes ? s->cur + max_bytes : s->total;
+        const uint64_t i1 = end_want >= s->total ? s->blocks.size() : std::min<uint64_t>(block_of(s->blocks, end_want) + 1, s->blocks.size());
+        const uint64_t base = i0 < s->blocks.size() ? s->blocks[i0].u0 : s->total;
+        const uint64_t have = i1 > i0 ? s->blocks[i1 - 1].u0 + s->blocks[i1 - 1].isize - base : 0;
+        b->raw.resize(have);
+        if (!inflate_blocks(file, s->blocks, i0, i1, b->raw.data(), s->threads)) {
+            err = "corrupt BGZF block (inflate or CRC failed)";
+            return 2;
+        }
+        const ByteVec &r = b->raw;
+        uint64_t p = s->cur - base;
+        b->rec_off.reserve((size_t)(r.size() / 256 + 16));
+        while (p + 4 <= r.size()) {
+            const uint64_t step = 4ull + rd32(&r[p]);
+            if (p + step > r.size()) break;                    // straddles the end of the span: opens the next one
+            b->rec_off.push_back(p);
+            if (p + 8 * step < r.size()) {
+                __builtin_prefetch(&r[p + 4 * step]);
+                __builtin_prefetch(&r[p + 8 * step]);
+            }
+            p += step;
+        }
+        const bool at_end = i1 >= s->blocks.size();
+        if (b->rec_off.empty() && !at_end) {                  // one record longer than the span: look at a longer one
+            max_bytes *= 2;
+            continue;
+        }
+        if (at_end && p != r.size()) {
+            err = "truncated BAM record";
+            return 2;
+        }
+        b->rec_off.push_back(p);
+        std::atomic<int> malformed(0);
+        bc_bam *bp = b.get();
+        parallel_for(b->threads, b->rec_off.size() - 1, 1 << 13, [&](uint64_t a, uint64_t e) {
+            RecView v;
+            for (uint64_t i = a; i < e; i++)
+                if (!view(bp, i, v)) malformed = 1;
+        });
+        if (malformed) {
+            err = "malformed BAM record";
+            return 2;
+        }
+        s->cur = base + p;
+        s->first = false;
+        *out = b.release();
+        return 0;
+    }
+}
+
 // ref_id / pos / mapq / flag of every record (what count_alignments needs to place its chunk cuts).
 inline void bc_bam_core_impl(const bc_bam *b, int32_t *ref_id, int32_t *pos, uint8_t *mapq, uint16_t *flag)
 {

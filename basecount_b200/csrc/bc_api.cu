@@ -1719,6 +1719,23 @@ int bc_bam_open(const char *path, int threads, bc_bam **out)
     return rc == 0 ? BC_OK : BC_ERR_ARG;
 }
 
+int bc_bam_stream_open(const char *path, int threads, bc_bam_stream **out)
+{
+    if (!path || !out) return BC_ERR_ARG;
+    *out = nullptr;
+    g_bam_err.clear();
+    return bc_bam_stream_open_impl(path, threads, out, g_bam_err) == 0 ? BC_OK : BC_ERR_ARG;
+}
+
+int bc_bam_stream_next(bc_bam_stream *s, uint64_t max_inflated_bytes, bc_bam **out)
+{
+    if (!s || !out) return BC_ERR_ARG;
+    g_bam_err.clear();
+    return bc_bam_stream_next_impl(s, max_inflated_bytes, out, g_bam_err) == 0 ? BC_OK : BC_ERR_ARG;
+}
+
+void bc_bam_stream_close(bc_bam_stream *s) { delete s; }
+
 int bc_bam_index_build(const char *bam_path, const char *bai_path, int threads)
 {
     if (!bam_path || !bai_path) return BC_ERR_ARG;

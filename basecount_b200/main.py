@@ -178,64 +178,88 @@ class Pileup:
 
 def count_alignments(bam, references=None, min_base_quality=0, min_mapping_quality=0, chunk_size=1000000,
                      show_n_bases=False, engine=None) -> Pileup:
-    """BAM -> device count matrices (the numeric part of get_basecounts, main.py:119-189)."""
-    rec = _RecordSource(bam)
+    """BAM -> device count matrices (the numeric part of get_basecounts, main.py:119-189).  A file path read by the
+    native decoder is taken span by span (bamio.NativeBamStream), so host memory is bounded by the span size whatever
+    the size of the file, as the reference's fetch(until_eof=True) loop is by its chunk_size (main.py:127,142)."""
+    from . import bamio as _bamio
     owns = engine is None
     eng = None
+    stream = None
+    spans = None
+    if not isinstance(bam, (Records, _bamio.NativeBam)) and _decoder_choice() == "native":
+        stream = _bamio.NativeBamStream(bam)
+        spans = iter(stream)
+        first = next(spans)                               # (exists even for a file without records)
+    else:
+        first = bam
+    rec = None
     try:
+        rec = _RecordSource(first)
         refs = get_references(rec.ref_names, references)
         ids = [rec.ref_names.index(r) for r in refs]
         lengths = [int(rec.ref_lengths[i]) for i in ids]
         eng = engine if engine is not None else Engine(0)
         num_reads = [0] * len(refs)
-        _count_into(eng, rec, ids, lengths, num_reads, min_base_quality, min_mapping_quality, chunk_size)
+        if ids:
+            eng.begin(lengths)
+            while rec is not None:
+                _push_chunks(eng, rec, ids, num_reads, min_base_quality, min_mapping_quality, chunk_size)
+                rec.close()
+                rec = None
+                nxt = next(spans, None) if spans is not None else None
+                if nxt is not None:
+                    rec = _RecordSource(nxt)
+            # one synchronisation at the end, where an alignment past the reference end surfaces as IndexError
+            eng.sync()
     except BaseException:
         if owns and eng is not None:
             eng.close()
         raise
     finally:
-        rec.close()
+        if rec is not None:
+            rec.close()
+        if spans is not None:
+            spans.close()                                 # (closes the span the reader had prefetched)
+        if stream is not None:
+            stream.close()
     return Pileup(eng, refs, lengths, num_reads, show_n_bases, owns_engine=owns)
 
 
-def _count_into(eng, rec, ids, lengths, num_reads, min_base_quality, min_mapping_quality, chunk_size):
-    if ids:
-        eng.begin(lengths)
-        # The reference flushes every `chunk_size` kept reads (main.py:142); the counts do not
-        # depend on where the chunks fall, so chunking here only bounds the packed buffers.
-        keep = ((rec.flag & FLAG_UNMAPPED) == 0) & (rec.mapq >= min_mapping_quality) & np.isin(rec.ref_id, ids)
-        csum = np.cumsum(keep)
-        total = int(csum[-1]) if csum.size else 0
-        chunk_size = max(int(chunk_size), 1)
-        cuts = [0]
-        for k in range(chunk_size, total, chunk_size):
-            cuts.append(int(np.searchsorted(csum, k, side="left")) + 1)
-        cuts.append(rec.n)
-        # Pushes are asynchronous (H2D on the copy stream, K1 on the compute stream, two staging sets in the
-        # library): the next chunk is decoded and packed while the device counts this one; one synchronisation at
-        # the end, where an alignment past the reference end surfaces as IndexError (count.cpp .at()).
-        for a, b in zip(cuts[:-1], cuts[1:]):
-            if b <= a:
-                continue
-            if rec.native is not None:
-                # one native pass per reference: selection (main.py:165-166), soft-clip trimming, CIGAR normal form
-                # and 2-bit packing straight from the records; a batch fills one slot of the handle
-                for j, rid in enumerate(ids):
-                    packed = rec.native.pack(rid, min_mapping_quality, min_base_quality, a, b)
-                    if packed.n_reads == 0:
-                        continue
-                    num_reads[j] += packed.n_reads
-                    if len(ids) > 1:
-                        off = np.zeros(len(ids) + 1, dtype=np.uint32)
-                        off[j + 1:] = packed.n_reads
-                        packed.ref_read_off, packed.n_refs = off, len(ids)
-                    eng.push(packed, keep=2)
-            else:
-                batches = [rec.select(a, b, rid, min_mapping_quality, want_qual=min_base_quality > 0) for rid in ids]
-                for j, bt in enumerate(batches):
-                    num_reads[j] += bt.n
-                eng.push(pack_batches(batches, min_base_quality), keep=2)
-        eng.sync()
+def _push_chunks(eng, rec, ids, num_reads, min_base_quality, min_mapping_quality, chunk_size):
+    """Count the kept reads of `rec` (a whole file or one span of it) into the engine's accumulators."""
+    # The reference flushes every `chunk_size` kept reads (main.py:142); the counts do not
+    # depend on where the chunks fall, so chunking here only bounds the packed buffers.
+    keep = ((rec.flag & FLAG_UNMAPPED) == 0) & (rec.mapq >= min_mapping_quality) & np.isin(rec.ref_id, ids)
+    csum = np.cumsum(keep)
+    total = int(csum[-1]) if csum.size else 0
+    chunk_size = max(int(chunk_size), 1)
+    cuts = [0]
+    for k in range(chunk_size, total, chunk_size):
+        cuts.append(int(np.searchsorted(csum, k, side="left")) + 1)
+    cuts.append(rec.n)
+    # Pushes are asynchronous (H2D on the copy stream, K1 on the compute stream, two staging sets in the
+    # library): the next chunk is decoded and packed while the device counts this one.
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b <= a:
+            continue
+        if rec.native is not None:
+            # one native pass per reference: selection (main.py:165-166), soft-clip trimming, CIGAR normal form
+            # and 2-bit packing straight from the records; a batch fills one slot of the handle
+            for j, rid in enumerate(ids):
+                packed = rec.native.pack(rid, min_mapping_quality, min_base_quality, a, b)
+                if packed.n_reads == 0:
+                    continue
+                num_reads[j] += packed.n_reads
+                if len(ids) > 1:
+                    off = np.zeros(len(ids) + 1, dtype=np.uint32)
+                    off[j + 1:] = packed.n_reads
+                    packed.ref_read_off, packed.n_refs = off, len(ids)
+                eng.push(packed, keep=2)
+        else:
+            batches = [rec.select(a, b, rid, min_mapping_quality, want_qual=min_base_quality > 0) for rid in ids]
+            for j, bt in enumerate(batches):
+                num_reads[j] += bt.n
+            eng.push(pack_batches(batches, min_base_quality), keep=2)
 
 
 def build_rows(ref, counts, st, show_n_bases=False, long_format=False):

@@ -255,6 +255,15 @@ uint64_t bc_canonical_cigars(uint32_t n_reads, const uint32_t *cigar, const uint
 typedef struct bc_bam bc_bam;
 /* threads <= 0: one per host core (at most 32).  Errors: bc_bam_last_error() (thread-local text). */
 int bc_bam_open(const char *path, int threads, bc_bam **out);
+/* The same file span by span, for files whose inflated size exceeds host memory (the reference's
+ * fetch(until_eof=True) loop, main.py:127, is O(chunk) too): bc_bam_stream_next hands out an ordinary bc_bam
+ * holding the whole records that start in the next ~max_inflated_bytes of the inflated stream (*out = NULL at the
+ * end of the file; the first span is handed out even if it holds no record, so the header is always available
+ * through bc_bam_num_refs / bc_bam_ref_name / bc_bam_ref_len).  Close every span with bc_bam_close. */
+typedef struct bc_bam_stream bc_bam_stream;
+int bc_bam_stream_open(const char *path, int threads, bc_bam_stream **out);
+int bc_bam_stream_next(bc_bam_stream *s, uint64_t max_inflated_bytes, bc_bam **out);
+void bc_bam_stream_close(bc_bam_stream *s);
 const char *bc_bam_last_error(void);
 /* The CRC-32 every BGZF block is checked with on the way in (RFC 1952; carry-less-multiply folding where the
  * CPU has it, zlib's crc32 otherwise).  Exported so the decoder's check can be held to zlib's on any bytes. */

@@ -494,3 +494,58 @@ def test_negative_mapping_quality_keeps_every_mapped_read(tmp_path):
     _same_batch(nb.select(0, -1), want)
     assert nb.pack(0, -1, 0).n_reads == want.n
     nb.close()
+
+
+def test_stream_of_spans_equals_the_whole_file(tmp_path):
+    """bamio.NativeBamStream (bc_bam_stream_*: the file span by span, bounded host memory) must hand out exactly the
+    records of the whole-file decoder, in order and whole, for any span size -- spans of one BGZF block, spans that
+    end inside a record, a record longer than the span (the reader doubles it), a file without records (one empty span
+    that still carries the header), two references -- and reject a file cut inside a record."""
+    big = _raw_record(0, 100, 60, 0, [(200_000 << 4) | 0], b"ACGT" * 50_000, [30] * 200_000)       # 300 kB record
+    cases = {"amplicon": synth.amplicon_sample(seed=5, n_reads=6000, ref_len=4000, ref_name="chrT"),
+             "torture": _clip_torture_records(),
+             "empty": synth.take_records(synth.amplicon_sample(seed=5, n_reads=50, ref_len=4000, ref_name="chrT"),
+                                         np.zeros(0, dtype=np.int64))}
+    paths = {}
+    for name, rec in cases.items():
+        paths[name] = str(tmp_path / f"{name}.bam")
+        bamio.write_bam(paths[name], rec)
+    paths["long_record"] = str(tmp_path / "long.bam")
+    with open(paths["long_record"], "wb") as fh:
+        small = _raw_record(0, 7, 60, 0, [(4 << 4) | 0], b"ACGT", [30] * 4)
+        fh.write(_bam_with([small, big, small, small], ref_len=300_000))
+    for name, p in paths.items():
+        whole = bamio.NativeBam(p, 2)
+        w_core = whole.core()
+        for span_bytes in (1, 70_000, 200_000, 1 << 30):               # (the library's floor is one BGZF block, 64 KiB)
+            with bamio.NativeBamStream(p, 2, span_bytes=span_bytes) as st:
+                spans = list(st)
+            assert len(spans) >= 1 and all(s.ref_names == whole.ref_names and s.ref_lengths == whole.ref_lengths for s in spans)
+            assert sum(s.n for s in spans) == whole.n, (name, span_bytes)
+            if span_bytes < 100_000 and whole.n > 1000:
+                assert len(spans) > 3                                   # it really was cut
+            for k in range(4):
+                got = np.concatenate([s.core()[k] for s in spans]) if spans else np.zeros(0)
+                assert np.array_equal(got, w_core[k]), (name, span_bytes, k)
+            for rid in range(len(whole.ref_names)):
+                want = whole.select(rid, 0)
+                parts = [s.select(rid, 0) for s in spans]
+                assert sum(b.n for b in parts) == want.n
+                assert np.array_equal(np.concatenate([b.starts for b in parts]), want.starts)
+                assert np.array_equal(np.concatenate([b.seq for b in parts]), want.seq)
+                assert np.array_equal(np.concatenate([b.qual for b in parts]), want.qual)
+                assert np.array_equal(np.concatenate([b.cigar for b in parts]), want.cigar)
+            for s in spans:
+                s.close()
+        whole.close()
+    # cut inside the last record: the whole-file decoder and the stream both refuse
+    raw = bamio.encode_bam_bytes(cases["amplicon"])
+    cut = str(tmp_path / "cut.bam")
+    with open(cut, "wb") as fh:
+        fh.write(bamio.bgzf_compress(raw[:-11], 1))
+    with pytest.raises(ValueError):
+        bamio.NativeBam(cut, 2)
+    with pytest.raises(ValueError):
+        with bamio.NativeBamStream(cut, 2, span_bytes=70_000) as st:
+            for s in st:
+                s.close()
