@@ -76,6 +76,7 @@ struct bc_handle {
     cudaEvent_t stats_ready = nullptr, stats_done = nullptr;
     bool stats_busy = false;
     bool stats_overlap = true;            // BASECOUNT_B200_SUMMARY_STREAM=0: summaries stay on the compute stream (A/B runs)
+    bool join_before_count = false;       // BASECOUNT_B200_JOIN_K1=1: every counting kernel waits for the queued summaries (A/B runs)
     int stats_set = 0;
     cudaEvent_t set_free_stats[2] = {nullptr, nullptr};
     bool set_free_stats_valid[2] = {false, false};
@@ -102,6 +103,10 @@ struct bc_handle {
     std::vector<Resident *> resident;
 
     DevBuf scratch_cov, scratch_pc, scratch_ent, scratch_sec, scratch_flags, scratch_i64, scratch_misc;
+    // the amplicon windows of the last bc_amplicons call stay on the device: a pipeline of steps over one scheme
+    // (--summarise-with-bed on sample after sample) uploads them once
+    DevBuf tiles_dev;
+    std::vector<int32_t> tiles_host;
     SummaryPartial *d_partials = nullptr;
     size_t partials_cap = 0;
     // asynchronous summaries: k2_summary writes its scalars into a device arena (a write to mapped host
@@ -334,6 +339,7 @@ int bc_create(int device, bc_handle **out)
             return bail(e, "stream");
     }
     if (const char *o = std::getenv("BASECOUNT_B200_SUMMARY_STREAM")) h->stats_overlap = std::atoi(o) != 0;
+    if (const char *o = std::getenv("BASECOUNT_B200_JOIN_K1")) h->join_before_count = std::atoi(o) != 0;
     if ((e = cudaEventCreateWithFlags(&h->stats_ready, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->stats_done, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
     if ((e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
@@ -380,7 +386,7 @@ void bc_destroy(bc_handle *h)
         }
     }
     for (DevBuf *b : {&h->scratch_cov, &h->scratch_pc, &h->scratch_ent, &h->scratch_sec, &h->scratch_flags,
-                      &h->scratch_i64, &h->scratch_misc})
+                      &h->scratch_i64, &h->scratch_misc, &h->tiles_dev})
         release(*b);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_part_off) cudaFree(h->d_part_off);
@@ -660,7 +666,7 @@ static int launch_count(bc_handle *h, const BatchView &v, const Chunk *d_chunks,
 {
     if (v.n_reads == 0) return BC_OK;
     // a summary that still reads THIS set of accumulators (no bc_reset since it was queued) comes first
-    if (h->stats_busy && h->stats_set == h->cur_set) JOIN_STATS(h);
+    if (h->stats_busy && (h->stats_set == h->cur_set || h->join_before_count)) JOIN_STATS(h);
     // uint32 counters cannot wrap while fewer than 2^32 reads went in since the last fold
     if (h->reads_since_fold + v.n_reads > 0xFFFFFFFFull) {
         const uint64_t n = h->stride * kPlanes;
@@ -1233,13 +1239,22 @@ static int amplicons_impl(bc_handle *h, uint32_t ref, int show_n, double norm, d
     const size_t out_bytes = ((size_t)n_tiles * 49 + 7) / 8 * 8;
     size_t off = 0;
     if ((rc = reserve_results(h, out_bytes, &off))) return rc;
-    if ((rc = ensure(h, h->scratch_misc, (size_t)n_tiles * 8 + 64))) return rc;
     double *d_out = (double *)(h->d_results + off);
     uint8_t *d_empty = (uint8_t *)(h->d_results + off + (size_t)n_tiles * 48);
-    int32_t *d_lo = (int32_t *)h->scratch_misc.p;
+    const bool same_tiles = h->tiles_dev.p && h->tiles_host.size() == (size_t)n_tiles * 2 &&
+                            std::memcmp(h->tiles_host.data(), lo, (size_t)n_tiles * 4) == 0 &&
+                            std::memcmp(h->tiles_host.data() + n_tiles, hi, (size_t)n_tiles * 4) == 0;
+    if (!same_tiles) {
+        // (earlier launches may still read the old windows: the copy is ordered behind them on the same stream, from a
+        //  host copy that lives as long as the handle -- the caller's arrays are done with when this call returns)
+        if ((rc = ensure(h, h->tiles_dev, (size_t)n_tiles * 8 + 64))) return rc;
+        CU(h, cudaStreamSynchronize(h->compute));
+        h->tiles_host.assign(lo, lo + n_tiles);
+        h->tiles_host.insert(h->tiles_host.end(), hi, hi + n_tiles);
+        CU(h, cudaMemcpyAsync(h->tiles_dev.p, h->tiles_host.data(), (size_t)n_tiles * 8, cudaMemcpyHostToDevice, h->compute));
+    }
+    int32_t *d_lo = (int32_t *)h->tiles_dev.p;
     int32_t *d_hi = d_lo + n_tiles;
-    CU(h, cudaMemcpyAsync(d_lo, lo, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, h->compute));
-    CU(h, cudaMemcpyAsync(d_hi, hi, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, h->compute));
     uint32_t cap = 4096;                        // doubles staged per window (32 KB)
     k3_amplicons<<<dim3(n_tiles, 3), kK3Threads, (size_t)cap * sizeof(double), h->compute>>>(
         (const long long *)h->scratch_cov.p, (const double *)h->scratch_ent.p, (const double *)h->scratch_sec.p, L,

@@ -6,6 +6,7 @@ on the engine's compute stream and timed with CUDA events.  Diagnostic only:
 import argparse
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -35,11 +36,13 @@ def main():
             fn(i)
         eng.sync()
         eng.timer_start()
+        t0 = time.perf_counter()
         for i in range(args.reps):
             fn(i)
+        t_host = time.perf_counter() - t0             # what the host needs to QUEUE the iterations (no synchronisation inside)
         ms = eng.timer_stop()
         eng.sync()
-        print(f"{name:34s} {1e3 * ms / args.reps:8.2f} us per iteration")
+        print(f"{name:34s} {1e3 * ms / args.reps:8.2f} us per iteration   (host queues one in {1e6 * t_host / args.reps:6.2f} us)")
 
     timed("reset", lambda i: eng.reset())
     timed("count (K1 + corrections + check)", lambda i: eng.push(resident[i % 2]))
