@@ -1291,6 +1291,7 @@ int bc_halo_export(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols,
 {
     if (!h || !dev_buf) return BC_ERR_ARG;
     if (ref >= h->n_refs || (uint64_t)col_lo + n_cols > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "halo out of range");
+    if (h->d_counts64) return fail(h, BC_ERR_STATE, "bc_halo_export: accumulators were folded to int64 (more than 2^32 reads since bc_begin)");
     if (n_cols == 0) return BC_OK;
     CU(h, cudaSetDevice(h->device));
     h->side_needs_compute = true;
@@ -1305,6 +1306,7 @@ int bc_halo_add(bc_handle *h, uint32_t ref, uint32_t col_lo, uint32_t n_cols, co
 {
     if (!h || !dev_buf) return BC_ERR_ARG;
     if (ref >= h->n_refs || (uint64_t)col_lo + n_cols > h->ref_len[ref]) return fail(h, BC_ERR_ARG, "halo out of range");
+    if (h->d_counts64) return fail(h, BC_ERR_STATE, "bc_halo_add: accumulators were folded to int64 (more than 2^32 reads since bc_begin)");
     if (n_cols == 0) return BC_OK;
     CU(h, cudaSetDevice(h->device));
     JOIN_STATS(h);

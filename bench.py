@@ -180,6 +180,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout=3.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up (process creation, NVML initialisation,
+        the first query) takes driver locks and tens of milliseconds, which must not fall into a timed region that
+        is two milliseconds long."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -561,18 +569,21 @@ def measure_workload(args, workload, rank, local, world, barrier, max_over_ranks
 
     # ---- value: inputs resident in HBM; the K steps are queued back to back (each step's
     #      summary is copied to its own pinned slot) and the stream is drained at the end
+    clocks = ClockSampler(local) if want_clocks and not os.environ.get("BENCH_NO_CLOCKS") else None
+    if clocks:
+        clocks.start()
     for i in range(warmup):
         step(i, outs[i], resident)
     eng.sync()
-    clocks = ClockSampler(local) if want_clocks else None
     if clocks:
-        clocks.start()
+        clocks.wait_first()
     barrier()
     launches0 = eng.kernel_launches()
     eng.timer_start()
     t_wall0 = time.perf_counter()
     for i in range(steps):
         step(i, outs[i], resident)
+    t_queue = time.perf_counter() - t_wall0       # what the host needed to queue the steps (nothing waits inside)
     ms_dev = eng.timer_stop()
     eng.sync()
     barrier()
@@ -661,6 +672,7 @@ def measure_workload(args, workload, rank, local, world, barrier, max_over_ranks
                      "step_over_kernel": (value / max(world, 1)) / (k1_bases / (k1_avg_ms * 1e-3)),
                      "peak_source": peak_src},
         "gpu_launches": int(launches), "clocks": clk, "wall_s_timed_region": t_wall,
+        "host_queue_us_per_step": 1e6 * t_queue / steps,
     }
     state = {"eng": eng, "resident": resident, "sets": sets, "ref_lens": ref_lens, "packed": packed, "h2d": h2d}
     return rec, state
@@ -791,11 +803,12 @@ def measure_region_sharded(args, rank, world, local, barrier, max_over_ranks, su
         want = obc.bcount_flat(cut + 4096, 0, part).astype(np.int64)[:cut]
         assert np.array_equal(got[:cut], want), "region-sharded: rank 0's first megabase differs from the oracle"
         guard = f"rank 0: first {cut} owned columns equal oracle.bcount_flat; cells over ranks == aligned bases"
+    clocks = ClockSampler(local)
+    clocks.start()
     for i in range(warmup):
         step(i, resident)
     eng.sync()
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.wait_first()
     barrier()
     launches0 = eng.kernel_launches()
     eng.timer_start()
