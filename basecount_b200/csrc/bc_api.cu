@@ -1188,9 +1188,13 @@ static int summary_impl(bc_handle *h, int show_n, double norm, double norm2, int
         if (h->comm_world > 1) {
             // every rank holds the sums over the columns it owns: the reference's numbers are the sums over ranks
             // (main.py:479-485).  nonzero and cov_sum are adjacent int64 arrays; entropy sums are float64.
+            // The two reductions are one NCCL group: aggregated into a single launch (one collective's latency per step).
             bcnccl::Api &nc = bcnccl::api();
-            ncclResult_t r1 = nc.AllReduce(d_nz, d_nz, (size_t)R * 2, ncclInt64, ncclSum, h->comm, h->compute);
+            ncclResult_t r0 = nc.GroupStart();
+            ncclResult_t r1 = r0 == ncclSuccess ? nc.AllReduce(d_nz, d_nz, (size_t)R * 2, ncclInt64, ncclSum, h->comm, h->compute) : r0;
             ncclResult_t r2 = r1 == ncclSuccess ? nc.AllReduce(d_es, d_es, (size_t)R, ncclFloat64, ncclSum, h->comm, h->compute) : r1;
+            ncclResult_t r3 = nc.GroupEnd();
+            if (r2 == ncclSuccess) r2 = r3;
             if (r2 != ncclSuccess) return fail(h, BC_ERR_CUDA, nc.GetErrorString(r2));
         }
         h->pending.push_back({off, (size_t)R * 8, nonzero});
