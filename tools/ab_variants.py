@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Build experimental variants of the library next to the product build and print / run the A/B command.
 
-A variant is NAME:DEFINE[,DEFINE...] (the -D macros csrc/*.cuh read: BC_K1_*, BC_K1S_*, BC_K2_PER_CTA, ...), built
+A variant is NAME:DEFINE[,DEFINE...] (the -D macros csrc/*.cuh read: BC_K1_*, BC_K1F_*, BC_K2_PER_CTA, ...), built
 into basecount_b200/csrc/variants/libNAME.so (git-ignored, travels to the GPU box).  On the box every variant
 runs the counting parity tests and tools/phase_times.py through BASECOUNT_B200_LIB, then the product build runs
 phase_times.py on the same box for comparison (box-to-box spread is +-3 %, so only same-box numbers compare).
 
-    python tools/ab_variants.py split96:BC_K1S_REG_WALK=64,BC_K1S_REG_COUNT=96,BC_K1S_MINCTAS=3 k2_512:BC_K2_PER_CTA=512
-    python tools/ab_variants.py --env BASECOUNT_B200_K1=split --run t8:BC_K1S_TRIPS=8,BC_K1_SEQCAP=416,BC_K1_CIGCAP=96
+    python tools/ab_variants.py mask0:BC_K1F_MASK3=0 regs160:BC_K1F_REGS=160 k2_512:BC_K2_PER_CTA=512
+    python tools/ab_variants.py --env BASECOUNT_B200_K1=walker --run seq416:BC_K1_SEQCAP=416,BC_K1_CIGCAP=96
 
 --run executes the command here (on a GPU box); without it the script prints the shell text to hand to gpurun.
 """
@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("variants", nargs="+", help="NAME:DEFINE[,DEFINE...]")
-    ap.add_argument("--env", action="append", default=[], help="KEY=VALUE exported for the variant runs (e.g. BASECOUNT_B200_K1=split)")
+    ap.add_argument("--env", action="append", default=[], help="KEY=VALUE exported for the variant runs (e.g. BASECOUNT_B200_K1=walker)")
     ap.add_argument("--tests", default="tests/test_gpu_counts.py", help="pytest target run for every variant")
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--run", action="store_true")

@@ -1,6 +1,7 @@
 #!/bin/bash
-# On the GPU box: the GPU suite, then value / step / K1 of the three bench workloads with the background-summary
-# and summary-stream switches on and off (same box, same run).   tools/step_ab.sh TAG
+# On the GPU box: the GPU suite, then value / step / K1 of the three bench workloads with the summaries on their own
+# stream (default), with every counting kernel waiting for them, and with them on the compute stream (same box, same
+# run).   tools/step_ab.sh TAG
 tag=${1:-x}
 o=gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > $o/${tag}_pytest_gpu.log 2>&1; tail -4 $o/${tag}_pytest_gpu.log
@@ -14,4 +15,5 @@ print('$label $wl: K1 %.2f us (pipeline %.2f) frac %.3f step %.2f us value %.3g 
   done
 }
 run default X=1
-run no_background BASECOUNT_B200_DEBUG_SKIP=4
+run join_before_count BASECOUNT_B200_JOIN_K1=1
+run summaries_on_compute_stream BASECOUNT_B200_SUMMARY_STREAM=0
