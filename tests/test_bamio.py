@@ -296,6 +296,16 @@ def test_random_records_roundtrip_and_native_selection(tmp_path):
                             nb.pack(rid, mmq, 0)
                         continue
                     _same_batch(nb.select(rid, mmq), want)
+            # the same file as a stream of one-block spans: the records' core fields in order, nothing lost or doubled
+            with bamio.NativeBamStream(p, 2, span_bytes=1) as stream:
+                spans = list(stream)
+            try:
+                assert sum(s.n for s in spans) == rec.n
+                for k, want_k in enumerate(nb.core()):
+                    assert np.array_equal(np.concatenate([s.core()[k] for s in spans]), want_k)
+            finally:
+                for s in spans:
+                    s.close()
         finally:
             nb.close()
 
