@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="cfg2x12,cfg3,cfg5")
     ap.add_argument("--reps", type=int, default=30)
+    ap.add_argument("--cfg5-reads", type=int, default=0, help="a shorter config 5 (the reference length scales with it)")
     a = ap.parse_args()
     import bench
     from basecount_b200 import _lib as bclib
@@ -24,6 +25,8 @@ def main():
     from basecount_b200.pack import pack_batches
     sys.argv = sys.argv[:1]
     args = bench.parse()
+    if a.cfg5_reads:
+        args.cfg5_reads = a.cfg5_reads
     name = os.path.basename(bclib.LIB_PATH)
     for wl in a.workloads.split(","):
         sets, ref_lens, label = bench.build_workload(args, 0, wl)
